@@ -1,0 +1,22 @@
+# Builds the C-ABI library (sm_100a only) and the oracle's C restatement.
+NVCC      ?= nvcc
+NVCCFLAGS ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+CSRC      := eigentrajectory_b200/csrc
+OBJDIR    := build
+SRCS      := $(wildcard $(CSRC)/*.cu)
+OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+LIB       := eigentrajectory_b200/libet_b200.so
+
+all: $(LIB)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/et_b200.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared -cudart static -o $@ $(OBJS)
+
+clean:
+	rm -rf $(OBJDIR) $(LIB)
+
+.PHONY: all clean

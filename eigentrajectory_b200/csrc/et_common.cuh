@@ -1,0 +1,113 @@
+// Shared host/device helpers for libet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/et_b200.h"
+
+namespace et {
+
+// ---- host side -----------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);     // cudaGetLastError -> ET_OK / ET_ERR_CUDA; counts the launch
+int sm_count();                          // SMs of the current device (cached per device)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline cudaStream_t as_stream(et_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+#define ET_REQUIRE(cond, code, ...) \
+  do {                              \
+    if (!(cond)) return ::et::fail((code), __VA_ARGS__); \
+  } while (0)
+
+// ---- device side ---------------------------------------------------------------------
+// Per-pedestrian normaliser state (normalizer.py:17-28).  The rotation is kept as a general
+// 2x2 matrix because TrajNorm.set_params (normalizer.py:36-40) accepts arbitrary state.
+struct NormState {
+  float ox, oy;               // origin  = last observed frame
+  float r00, r01, r10, r11;   // [[c,-s],[s,c]], heading of (last - third_last)
+  float sca;                  // (1/||d||) * 2
+};
+
+// last = obs[T-1], third = obs[T-3].  c,s = d/||d|| equals cos/sin(atan2(dy,dx)) of the
+// reference to <= 3e-7 absolute; the zero vector maps to angle 0 as atan2(0,0) does.
+__device__ __forceinline__ NormState make_norm_state(float lx, float ly, float tx, float ty) {
+  NormState p;
+  p.ox = lx;
+  p.oy = ly;
+  const float dx = lx - tx, dy = ly - ty;
+  const float n2 = dx * dx + dy * dy;
+  const float nrm = sqrtf(n2);
+  float c = 1.f, s = 0.f;
+  if (n2 > 0.f) {
+    const float inv = 1.0f / nrm;
+    c = dx * inv;
+    s = dy * inv;
+  }
+  p.r00 = c; p.r01 = -s; p.r10 = s; p.r11 = c;
+  p.sca = (1.0f / nrm) * 2.0f;   // inf when the pedestrian did not move, as in the reference
+  return p;
+}
+
+// (a,b) <- ((a,b) - ori) @ R * sca
+__device__ __forceinline__ void norm_fwd(float& a, float& b, const NormState& p, int flags) {
+  if (flags & ET_NORM_ORI) { a -= p.ox; b -= p.oy; }
+  if (flags & ET_NORM_ROT) {
+    const float na = a * p.r00 + b * p.r10;
+    const float nb = a * p.r01 + b * p.r11;
+    a = na; b = nb;
+  }
+  if (flags & ET_NORM_SCA) { a *= p.sca; b *= p.sca; }
+}
+
+// (a,b) <- ((a,b) / sca) @ R^T + ori ; inv_sca = 1/sca precomputed by the caller (one IEEE
+// division per pedestrian instead of one per coordinate).
+__device__ __forceinline__ void norm_bwd(float& a, float& b, const NormState& p, float inv_sca, int flags) {
+  if (flags & ET_NORM_SCA) { a *= inv_sca; b *= inv_sca; }
+  if (flags & ET_NORM_ROT) {
+    const float na = a * p.r00 + b * p.r01;
+    const float nb = a * p.r10 + b * p.r11;
+    a = na; b = nb;
+  }
+  if (flags & ET_NORM_ORI) { a += p.ox; b += p.oy; }
+}
+
+// Read a stored state (ori (N,1,2), rot (N,2,2), sca (N,1,1)); absent parts are identity.
+__device__ __forceinline__ NormState load_norm_state(const float* ori, const float* rot, const float* sca,
+                                                     int64_t i, int flags) {
+  NormState p;
+  p.ox = 0.f; p.oy = 0.f; p.r00 = 1.f; p.r01 = 0.f; p.r10 = 0.f; p.r11 = 1.f; p.sca = 1.f;
+  if ((flags & ET_NORM_ORI) && ori) {
+    const float2 o = __ldg(reinterpret_cast<const float2*>(ori) + i);
+    p.ox = o.x; p.oy = o.y;
+  }
+  if ((flags & ET_NORM_ROT) && rot) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(rot) + i);
+    p.r00 = r.x; p.r01 = r.y; p.r10 = r.z; p.r11 = r.w;
+  }
+  if ((flags & ET_NORM_SCA) && sca) p.sca = __ldg(sca + i);
+  return p;
+}
+
+__device__ __forceinline__ void store_norm_state(float* ori, float* rot, float* sca, int64_t i,
+                                                 const NormState& p, int flags) {
+  if ((flags & ET_NORM_ORI) && ori) reinterpret_cast<float2*>(ori)[i] = make_float2(p.ox, p.oy);
+  if ((flags & ET_NORM_ROT) && rot) reinterpret_cast<float4*>(rot)[i] = make_float4(p.r00, p.r01, p.r10, p.r11);
+  if ((flags & ET_NORM_SCA) && sca) sca[i] = p.sca;
+}
+
+// Streaming 128-bit global accesses: data is touched once, keep it out of L1.
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace et

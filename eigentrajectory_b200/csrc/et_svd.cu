@@ -1,0 +1,518 @@
+// Eigen-basis construction (reference: ETDescriptor.truncated_SVD, EigenTrajectory/descriptor.py:91-114).
+//
+// The reference runs LAPACK gesdd on the wide (2T, N) view and discards Vt.  Here the (2T x 2T) Gram matrix
+// G = M M^T is accumulated in ONE pass over the trajectories -- fp32 inputs, products and sums in float64
+// on the FP64 tensor cores (DMMA m8n8k4; fp32 x fp32 products are exact in fp64) -- and a cyclic Jacobi
+// eigen-solve on G yields U and S = sqrt(lambda).  A multi-GPU caller sums G over row shards (one
+// all-reduce) between the two steps.  Small problems (N up to ~2000 rows) can instead run a one-sided
+// Hestenes Jacobi directly on the shared-memory resident tall-skinny (N x 2T) matrix.
+#include <math.h>
+
+#include "et_common.cuh"
+
+namespace et {
+
+// =======================================================================================
+// 1. Gram pass, (T_obs, T_pred) = (8, 12): 160 algorithmic bytes and 436 fp64 FMA per pedestrian.
+// =======================================================================================
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int GR_WARPS = 8;
+constexpr int GR_PITCH = 40;                 // floats per staged pedestrian: 16 obs + 24 pred, conflict-free
+constexpr int GR_NBLK_O = 3, GR_NBLK_P = 6;  // upper-triangular 8x8 blocks of the 16x16 / 24x24 Gram matrices
+constexpr int GR_GO = 16 * 16, GR_GP = 24 * 24;
+
+// workspace layout: [0] uint32 ticket (zero on entry, restored to zero on exit), then at byte 128
+// gridDim.x partial matrices of GR_GO + GR_GP doubles.
+__global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restrict__ obs, const float* __restrict__ pred,
+                                                           int64_t n, int flags, double* __restrict__ G_obs,
+                                                           double* __restrict__ G_pred, unsigned* __restrict__ ticket,
+                                                           double* __restrict__ partials) {
+  __shared__ __align__(16) float xs[GR_WARPS][32 * GR_PITCH];
+  __shared__ double acc_s[GR_GO + GR_GP];
+  __shared__ unsigned is_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  float* xw = xs[warp];
+
+  double co[GR_NBLK_O][2], cp[GR_NBLK_P][2];
+#pragma unroll
+  for (int b = 0; b < GR_NBLK_O; ++b) co[b][0] = co[b][1] = 0.0;
+#pragma unroll
+  for (int b = 0; b < GR_NBLK_P; ++b) cp[b][0] = cp[b][1] = 0.0;
+
+  const int64_t n_tiles = (n + 31) / 32;
+  const int64_t wstride = (int64_t)gridDim.x * GR_WARPS;
+  for (int64_t tile = (int64_t)blockIdx.x * GR_WARPS + warp; tile < n_tiles; tile += wstride) {
+    const int64_t i = tile * 32 + lane;
+    float4* row = reinterpret_cast<float4*>(xw + lane * GR_PITCH);
+    if (i < n) {
+      float x[40];
+      const float4* po = reinterpret_cast<const float4*>(obs + i * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 v = __ldg(po + c);
+        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+      }
+      if (pred) {
+        const float4* pp = reinterpret_cast<const float4*>(pred + i * 24);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const float4 v = __ldg(pp + c);
+          x[16 + 4 * c] = v.x; x[17 + 4 * c] = v.y; x[18 + 4 * c] = v.z; x[19 + 4 * c] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 16; c < 40; ++c) x[c] = 0.f;
+      }
+      if (flags) {
+        const NormState st = make_norm_state(x[14], x[15], x[10], x[11]);
+#pragma unroll
+        for (int t = 0; t < 20; ++t) norm_fwd(x[2 * t], x[2 * t + 1], st, flags);
+      }
+#pragma unroll
+      for (int c = 0; c < 10; ++c) row[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 10; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    // 8 k-steps of 4 pedestrians; fragment f holds x[ped 4*ks + t4][8 f + g] (serves as A and as B)
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks) {
+      const float* xr = xw + (4 * ks + t4) * GR_PITCH + g;
+      double f[5];
+#pragma unroll
+      for (int b = 0; b < 5; ++b) f[b] = (double)xr[8 * b];
+      dmma_m8n8k4(co[0][0], co[0][1], f[0], f[0]);
+      dmma_m8n8k4(co[1][0], co[1][1], f[0], f[1]);
+      dmma_m8n8k4(co[2][0], co[2][1], f[1], f[1]);
+      if (pred) {
+        dmma_m8n8k4(cp[0][0], cp[0][1], f[2], f[2]);
+        dmma_m8n8k4(cp[1][0], cp[1][1], f[2], f[3]);
+        dmma_m8n8k4(cp[2][0], cp[2][1], f[2], f[4]);
+        dmma_m8n8k4(cp[3][0], cp[3][1], f[3], f[3]);
+        dmma_m8n8k4(cp[4][0], cp[4][1], f[3], f[4]);
+        dmma_m8n8k4(cp[5][0], cp[5][1], f[4], f[4]);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---- block reduction (fixed warp order => deterministic) ----
+  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) acc_s[e] = 0.0;
+  __syncthreads();
+  const int bo_r[GR_NBLK_O] = {0, 0, 1}, bo_c[GR_NBLK_O] = {0, 1, 1};
+  const int bp_r[GR_NBLK_P] = {0, 0, 0, 1, 1, 2}, bp_c[GR_NBLK_P] = {0, 1, 2, 1, 2, 2};
+  for (int w = 0; w < GR_WARPS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int b = 0; b < GR_NBLK_O; ++b) {
+        const int r = 8 * bo_r[b] + g, c = 8 * bo_c[b] + 2 * t4;
+        acc_s[r * 16 + c] += co[b][0];
+        acc_s[r * 16 + c + 1] += co[b][1];
+      }
+#pragma unroll
+      for (int b = 0; b < GR_NBLK_P; ++b) {
+        const int r = 8 * bp_r[b] + g, c = 8 * bp_c[b] + 2 * t4;
+        acc_s[GR_GO + r * 24 + c] += cp[b][0];
+        acc_s[GR_GO + r * 24 + c + 1] += cp[b][1];
+      }
+    }
+    __syncthreads();
+  }
+  // mirror the strictly-upper blocks into the lower triangle
+  for (int e = threadIdx.x; e < GR_GO; e += blockDim.x) {
+    const int r = e / 16, c = e % 16;
+    if ((r >> 3) > (c >> 3)) acc_s[e] = acc_s[c * 16 + r];
+  }
+  for (int e = threadIdx.x; e < GR_GP; e += blockDim.x) {
+    const int r = e / 24, c = e % 24;
+    if ((r >> 3) > (c >> 3)) acc_s[GR_GO + e] = acc_s[GR_GO + c * 24 + r];
+  }
+  __syncthreads();
+  double* mine = partials + (size_t)blockIdx.x * (GR_GO + GR_GP);
+  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) mine[e] = acc_s[e];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  // ---- the last block to finish folds all partials in block order and adds them to G ----
+  __threadfence();
+  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) {
+    if (e >= GR_GO && !pred) break;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    unsigned b = 0;
+    for (; b + 4 <= gridDim.x; b += 4) {
+      s0 += __ldcg(partials + (size_t)(b + 0) * (GR_GO + GR_GP) + e);
+      s1 += __ldcg(partials + (size_t)(b + 1) * (GR_GO + GR_GP) + e);
+      s2 += __ldcg(partials + (size_t)(b + 2) * (GR_GO + GR_GP) + e);
+      s3 += __ldcg(partials + (size_t)(b + 3) * (GR_GO + GR_GP) + e);
+    }
+    for (; b < gridDim.x; ++b) s0 += __ldcg(partials + (size_t)b * (GR_GO + GR_GP) + e);
+    const double tot = (s0 + s1) + (s2 + s3);
+    if (e < GR_GO) G_obs[e] += tot;
+    else G_pred[e - GR_GO] += tot;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// Any (T_obs, T_pred): block-wide fp64 accumulation over chunks of 64 staged pedestrians; simple and slow,
+// used off the fast path only.
+constexpr int GG_THREADS = 512, GG_CHUNK = 64, GG_ACC = 16;
+
+__global__ void __launch_bounds__(GG_THREADS) gram_generic(const float* __restrict__ obs, const float* __restrict__ pred,
+                                                           int64_t n, int to2, int tp2, int flags,
+                                                           double* __restrict__ G_obs, double* __restrict__ G_pred) {
+  extern __shared__ float xs[];   // GG_CHUNK rows of (to2 + tp2) floats
+  const int pitch = to2 + tp2;
+  const int n_out = to2 * to2 + tp2 * tp2;
+  double acc[GG_ACC];
+  for (int q = 0; q < GG_ACC; ++q) acc[q] = 0.0;
+  for (int64_t base = (int64_t)blockIdx.x * GG_CHUNK; base < n; base += (int64_t)gridDim.x * GG_CHUNK) {
+    for (int e = threadIdx.x; e < GG_CHUNK * pitch; e += GG_THREADS) {
+      const int m = e / pitch, r = e % pitch;
+      const int64_t i = base + m;
+      float v = 0.f;
+      if (i < n) v = (r < to2) ? __ldg(obs + i * to2 + r) : __ldg(pred + i * tp2 + (r - to2));
+      xs[e] = v;
+    }
+    __syncthreads();
+    if (flags && threadIdx.x < GG_CHUNK && base + threadIdx.x < n) {
+      float* row = xs + threadIdx.x * pitch;
+      const NormState st = make_norm_state(row[to2 - 2], row[to2 - 1], row[to2 - 6], row[to2 - 5]);
+      for (int r = 0; r < pitch; r += 2) norm_fwd(row[r], row[r + 1], st, flags);
+    }
+    __syncthreads();
+    for (int q = 0; q < GG_ACC; ++q) {
+      const int e = threadIdx.x + q * GG_THREADS;
+      if (e >= n_out) break;
+      int off, a, b;
+      if (e < to2 * to2) { off = 0; a = e / to2; b = e % to2; }
+      else { off = to2; a = (e - to2 * to2) / tp2; b = (e - to2 * to2) % tp2; }
+      double sum = 0.0;
+      for (int m = 0; m < GG_CHUNK; ++m) sum = fma((double)xs[m * pitch + off + a], (double)xs[m * pitch + off + b], sum);
+      acc[q] += sum;
+    }
+    __syncthreads();
+  }
+  for (int q = 0; q < GG_ACC; ++q) {
+    const int e = threadIdx.x + q * GG_THREADS;
+    if (e >= n_out) break;
+    if (e < to2 * to2) atomicAdd(G_obs + e, acc[q]);
+    else atomicAdd(G_pred + (e - to2 * to2), acc[q]);
+  }
+}
+
+// =======================================================================================
+// 2. Symmetric eigen-solve of G (m <= 64) by parallel-ordered cyclic Jacobi in float64, one block.
+//    Per-pair threshold |g_pq| <= eps * sqrt(g_pp g_qq) (high relative accuracy on PSD matrices;
+//    exact-zero rows/columns -- the normalised last observed frame -- never rotate).
+// =======================================================================================
+constexpr int EIG_THREADS = 256;
+constexpr int EIG_MAX_SWEEPS = 60;
+
+__global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
+                                                                 float* __restrict__ U, float* __restrict__ S,
+                                                                 double* __restrict__ U64, double* __restrict__ S64) {
+  extern __shared__ double sm[];
+  const int mp = (m + 1) & ~1;   // even size; a padding index never rotates
+  double* A = sm;                // mp x mp (row-major, pitch mp)
+  double* V = A + mp * mp;       // mp x mp
+  double* cs = V + mp * mp;      // mp/2 cosines, mp/2 sines
+  int* pr = reinterpret_cast<int*>(cs + mp);   // pairs p[mp/2], q[mp/2]
+  int* order = pr + mp;                         // mp
+  __shared__ int n_rot;
+  const int tid = threadIdx.x, half = mp / 2;
+
+  for (int e = tid; e < mp * mp; e += EIG_THREADS) {
+    const int r = e / mp, c = e % mp;
+    A[e] = (r < m && c < m) ? 0.5 * (G[r * m + c] + G[c * m + r]) : 0.0;
+    V[e] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
+    if (tid == 0) n_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < mp - 1; ++step) {
+      // round-robin tournament: position 0 fixed, the others rotate
+      if (tid < half) {
+        auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (mp - 1); };
+        int p = player(tid), q = player(mp - 1 - tid);
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double app = A[p * mp + p], aqq = A[q * mp + q], apq = A[p * mp + q];
+        double c = 1.0, s = 0.0;
+        if (q < m && fabs(apq) > 1e-300 && fabs(apq) > 2.2e-16 * sqrt(fabs(app) * fabs(aqq))) {
+          const double tau = (aqq - app) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          s = t * c;
+          atomicAdd(&n_rot, 1);
+        }
+        cs[tid] = c; cs[half + tid] = s; pr[tid] = p; pr[half + tid] = q;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int e = tid; e < half * mp; e += EIG_THREADS) {
+        const int pi = e / mp, r = e % mp;
+        const double c = cs[pi], s = cs[half + pi];
+        if (s != 0.0) {
+          const int p = pr[pi], q = pr[half + pi];
+          const double ap = A[r * mp + p], aq = A[r * mp + q];
+          A[r * mp + p] = c * ap - s * aq;
+          A[r * mp + q] = s * ap + c * aq;
+          const double vp = V[r * mp + p], vq = V[r * mp + q];
+          V[r * mp + p] = c * vp - s * vq;
+          V[r * mp + q] = s * vp + c * vq;
+        }
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < half * mp; e += EIG_THREADS) {
+        const int pi = e / mp, col = e % mp;
+        const double c = cs[pi], s = cs[half + pi];
+        if (s != 0.0) {
+          const int p = pr[pi], q = pr[half + pi];
+          const double ap = A[p * mp + col], aq = A[q * mp + col];
+          A[p * mp + col] = c * ap - s * aq;
+          A[q * mp + col] = s * ap + c * aq;
+        }
+      }
+      __syncthreads();
+      if (tid < half && cs[half + tid] != 0.0) {
+        const int p = pr[tid], q = pr[half + tid];
+        A[p * mp + q] = 0.0;
+        A[q * mp + p] = 0.0;
+      }
+      __syncthreads();
+    }
+    if (n_rot == 0) break;
+    __syncthreads();
+  }
+
+  // order eigenvalues descending (ties: lower index first) -- m <= 64, one thread
+  if (tid == 0) {
+    for (int i = 0; i < m; ++i) order[i] = i;
+    for (int i = 0; i < m; ++i) {
+      int best = i;
+      for (int j = i + 1; j < m; ++j)
+        if (A[order[j] * mp + order[j]] > A[order[best] * mp + order[best]]) best = j;
+      const int t = order[i]; order[i] = order[best]; order[best] = t;
+    }
+  }
+  __syncthreads();
+  if (tid < k) {
+    const int col = order[tid];
+    const double lam = A[col * mp + col];
+    const double sv = sqrt(lam > 0.0 ? lam : 0.0);
+    // canonical sign: the largest-magnitude component (first one on ties) is positive
+    int arg = 0;
+    double big = -1.0;
+    for (int r = 0; r < m; ++r) {
+      const double a = fabs(V[r * mp + col]);
+      if (a > big) { big = a; arg = r; }
+    }
+    const double sign = V[arg * mp + col] < 0.0 ? -1.0 : 1.0;
+    for (int r = 0; r < m; ++r) {
+      const double v = sign * V[r * mp + col];
+      U[r * k + tid] = (float)v;
+      if (U64) U64[r * k + tid] = v;
+    }
+    S[tid] = (float)sv;
+    if (S64) S64[tid] = sv;
+  }
+}
+
+// =======================================================================================
+// 3. Batched small-N SVD: one-sided (Hestenes) Jacobi on a shared-memory resident tall-skinny matrix.
+//    One block per problem; X (n_b x m) is kept column-major in fp32; a warp owns a column pair per step:
+//    alpha = |x_p|^2, beta = |x_q|^2, gamma = x_p . x_q by warp-shuffle reduction (fp64 partial sums),
+//    then the plane rotation is applied to the two columns of X and of V (m x m).  On exit the columns of
+//    V are the left singular vectors of the wide (m x n_b) view and the column norms of X the singular values.
+// =======================================================================================
+constexpr int SVS_THREADS = 384;
+constexpr int SVS_MAX_SWEEPS = 30;
+
+__global__ void __launch_bounds__(SVS_THREADS) svd_small_kernel(const float* __restrict__ traj,
+                                                                const int64_t* __restrict__ offsets, int ld, int m,
+                                                                int k, float* __restrict__ U, float* __restrict__ S) {
+  extern __shared__ float smf[];
+  const int mp = (m + 1) & ~1;
+  float* X = smf;                       // mp columns of pitch ld
+  float* V = X + (size_t)mp * ld;       // mp x mp, column-major (pitch mp)
+  float* nrm = V + mp * mp;             // mp
+  int* order = reinterpret_cast<int*>(nrm + mp);
+  __shared__ int n_rot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = SVS_THREADS / 32;
+  const int64_t r0 = offsets[blockIdx.x];
+  int nb = (int)(offsets[blockIdx.x + 1] - r0);
+  if (nb > ld) nb = ld;   // the host wrapper guarantees max_rows >= every n_b; never write out of bounds
+  const float* src = traj + r0 * m;
+
+  for (int e = tid; e < nb * m; e += SVS_THREADS) {
+    const int r = e / m, c = e % m;
+    X[(size_t)c * ld + r] = __ldg(src + e);
+  }
+  if (mp != m) for (int r = tid; r < nb; r += SVS_THREADS) X[(size_t)m * ld + r] = 0.f;
+  for (int e = tid; e < mp * mp; e += SVS_THREADS) V[e] = (e / mp == e % mp) ? 1.f : 0.f;
+  __syncthreads();
+
+  const int half = mp / 2;
+  for (int sweep = 0; sweep < SVS_MAX_SWEEPS; ++sweep) {
+    if (tid == 0) n_rot = 0;
+    __syncthreads();
+    for (int step = 0; step < mp - 1; ++step) {
+      for (int pi = warp; pi < half; pi += nwarps) {
+        auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (mp - 1); };
+        int p = player(pi), q = player(mp - 1 - pi);
+        if (p > q) { const int t = p; p = q; q = t; }
+        if (q >= m) continue;
+        float* xp = X + (size_t)p * ld;
+        float* xq = X + (size_t)q * ld;
+        double a = 0.0, b = 0.0, g = 0.0;
+        for (int r = lane; r < nb; r += 32) {
+          const double vp = xp[r], vq = xq[r];
+          a = fma(vp, vp, a); b = fma(vq, vq, b); g = fma(vp, vq, g);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+          g += __shfl_xor_sync(0xffffffffu, g, o);
+        }
+        if (fabs(g) > 1e-7 * sqrt(a * b) && fabs(g) > 1e-30) {
+          const double tau = (b - a) / (2.0 * g);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          const double cd = 1.0 / sqrt(1.0 + t * t);
+          const float c = (float)cd, s = (float)(t * cd);
+          for (int r = lane; r < nb; r += 32) {
+            const float vp = xp[r], vq = xq[r];
+            xp[r] = c * vp - s * vq;
+            xq[r] = s * vp + c * vq;
+          }
+          for (int r = lane; r < m; r += 32) {
+            const float vp = V[p * mp + r], vq = V[q * mp + r];
+            V[p * mp + r] = c * vp - s * vq;
+            V[q * mp + r] = s * vp + c * vq;
+          }
+          if (lane == 0) atomicAdd(&n_rot, 1);
+        }
+      }
+      __syncthreads();
+    }
+    if (n_rot == 0) break;
+    __syncthreads();
+  }
+
+  for (int c = warp; c < m; c += nwarps) {
+    double a = 0.0;
+    for (int r = lane; r < nb; r += 32) { const double v = X[(size_t)c * ld + r]; a = fma(v, v, a); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) nrm[c] = (float)sqrt(a);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < m; ++i) order[i] = i;
+    for (int i = 0; i < m; ++i) {
+      int best = i;
+      for (int j = i + 1; j < m; ++j)
+        if (nrm[order[j]] > nrm[order[best]]) best = j;
+      const int t = order[i]; order[i] = order[best]; order[best] = t;
+    }
+  }
+  __syncthreads();
+  if (tid < k) {
+    const int col = order[tid];
+    int arg = 0;
+    float big = -1.f;
+    for (int r = 0; r < m; ++r) {
+      const float a = fabsf(V[col * mp + r]);
+      if (a > big) { big = a; arg = r; }
+    }
+    const float sign = V[col * mp + arg] < 0.f ? -1.f : 1.f;
+    float* Ub = U + (size_t)blockIdx.x * m * k;
+    for (int r = 0; r < m; ++r) Ub[r * k + tid] = sign * V[col * mp + r];
+    S[(size_t)blockIdx.x * k + tid] = nrm[col];
+  }
+}
+
+static int gram_grid() { return sm_count() * 2; }
+
+}  // namespace et
+
+using namespace et;
+
+extern "C" {
+
+size_t et_gram_workspace_bytes(void) { return 128 + (size_t)gram_grid() * (GR_GO + GR_GP) * sizeof(double); }
+
+int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags, double* G_obs,
+            double* G_pred, void* workspace, et_stream_t stream) {
+  ET_REQUIRE(n >= 0, ET_ERR_BADARG, "et_gram: n < 0");
+  ET_REQUIRE(t_obs >= 1 && t_obs <= ET_MAX_T && (!pred || (t_pred >= 1 && t_pred <= ET_MAX_T)), ET_ERR_UNSUPPORTED,
+             "et_gram: T outside [1, %d]", ET_MAX_T);
+  ET_REQUIRE(!flags || t_obs >= 3, ET_ERR_UNSUPPORTED, "et_gram: normalisation needs T_obs >= 3");
+  ET_REQUIRE((obs && G_obs) || n == 0, ET_ERR_BADARG, "et_gram: obs / G_obs null");
+  ET_REQUIRE(!pred || G_pred, ET_ERR_BADARG, "et_gram: pred given but G_pred null");
+  ET_REQUIRE(aligned16(obs) && aligned16(pred), ET_ERR_ALIGN, "et_gram: trajectory pointers must be 16-byte aligned");
+  if (n == 0) return ET_OK;
+  cudaStream_t st = as_stream(stream);
+  if (t_obs == 8 && (!pred || t_pred == 12)) {
+    ET_REQUIRE(workspace, ET_ERR_BADARG, "et_gram: workspace of et_gram_workspace_bytes() zero-initialised bytes required");
+    ET_REQUIRE(aligned16(workspace), ET_ERR_ALIGN, "et_gram: workspace must be 16-byte aligned");
+    int grid = gram_grid();
+    const int64_t need = ((n + 31) / 32 + GR_WARPS - 1) / GR_WARPS;
+    if (grid > need) grid = (int)need;
+    gram_fast<<<grid, GR_WARPS * 32, 0, st>>>(obs, pred, n, flags, G_obs, G_pred, reinterpret_cast<unsigned*>(workspace),
+                                             reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128));
+    return check_launch("gram_fast");
+  }
+  const int to2 = 2 * t_obs, tp2 = pred ? 2 * t_pred : 0;
+  const size_t smem = (size_t)GG_CHUNK * (to2 + tp2) * sizeof(float);
+  ET_REQUIRE(to2 * to2 + tp2 * tp2 <= GG_THREADS * GG_ACC, ET_ERR_UNSUPPORTED, "et_gram: shape too large");
+  int64_t grid = (n + GG_CHUNK - 1) / GG_CHUNK;
+  if (grid > 2 * sm_count()) grid = 2 * sm_count();
+  gram_generic<<<(unsigned)grid, GG_THREADS, smem, st>>>(obs, pred, n, to2, tp2, flags, G_obs, G_pred);
+  return check_launch("gram_generic");
+}
+
+int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64, et_stream_t stream) {
+  ET_REQUIRE(G && U && S, ET_ERR_BADARG, "et_eig_jacobi: null pointer");
+  ET_REQUIRE(m >= 1 && m <= 2 * ET_MAX_T, ET_ERR_UNSUPPORTED, "et_eig_jacobi: m = %d outside [1, %d]", m, 2 * ET_MAX_T);
+  ET_REQUIRE(k >= 1 && k <= m, ET_ERR_BADARG, "et_eig_jacobi: k = %d outside [1, m = %d]", k, m);
+  const int mp = (m + 1) & ~1;
+  const size_t smem = (size_t)(2 * mp * mp + mp) * sizeof(double) + (size_t)2 * mp * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "eig_jacobi_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  eig_jacobi_kernel<<<1, EIG_THREADS, smem, as_stream(stream)>>>(G, m, k, U, S, U64, S64);
+  return check_launch("eig_jacobi_kernel");
+}
+
+int et_svd_small(const float* traj, const int64_t* offsets, int batch, int64_t max_rows, int t, int k, float* U,
+                 float* S, et_stream_t stream) {
+  ET_REQUIRE(batch >= 0 && max_rows >= 0, ET_ERR_BADARG, "et_svd_small: bad batch / max_rows");
+  ET_REQUIRE(t >= 1 && t <= ET_MAX_T, ET_ERR_UNSUPPORTED, "et_svd_small: T = %d outside [1, %d]", t, ET_MAX_T);
+  const int m = 2 * t;
+  ET_REQUIRE(k >= 1 && k <= m, ET_ERR_BADARG, "et_svd_small: k = %d outside [1, %d]", k, m);
+  if (batch == 0) return ET_OK;
+  ET_REQUIRE(traj && offsets && U && S, ET_ERR_BADARG, "et_svd_small: null pointer");
+  const int mp = (m + 1) & ~1;
+  const int ld = (int)max_rows | 1;   // odd pitch
+  const size_t smem = ((size_t)mp * ld + (size_t)mp * mp + mp) * sizeof(float) + (size_t)mp * sizeof(int);
+  ET_REQUIRE(smem <= 200 * 1024, ET_ERR_UNSUPPORTED,
+             "et_svd_small: %lld rows x %d columns do not fit shared memory (use et_gram + et_eig_jacobi)",
+             (long long)max_rows, m);
+  cudaError_t e = cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "svd_small_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  svd_small_kernel<<<batch, SVS_THREADS, smem, as_stream(stream)>>>(traj, offsets, ld, m, k, U, S);
+  return check_launch("svd_small_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+"""BatchKMeans -- drop-in for ``EigenTrajectory/kmeans.py:7-272`` running on libet_b200.so."""
+from __future__ import annotations
+
+from time import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+def _as_ldn(t):
+    """(..., d, N) -> contiguous (l, d, N) fp32 on the compute device, plus the leading shape."""
+    lead = tuple(t.shape[:-2])
+    x = ops.to_dev(t).reshape(-1, t.size(-2), t.size(-1))
+    return x, lead
+
+
+class BatchKMeans(nn.Module):
+    r"""Run multiple independent K-means algorithms in parallel.
+
+    Args:
+        n_clusters (int): Number of clusters
+        max_iter (int): Maximum number of iterations (default: 100)
+        tol (float): Tolerance (default: 0.0001)
+        n_redo (int): Number of time k-means will be run with differently initialized centroids.
+            the centroids with the lowest inertia will be selected as a final result. (default: 1)
+        init_mode (str): Initialization method.
+            'random': randomly chose initial centroids from input data.
+            'kmeans++': use the (deterministic farthest-point) k-means++ of the reference. (default: 'kmeans++')
+
+    ``sync_every``: Lloyd iterations enqueued between host checks of the device-side convergence
+    flag (the reference synchronises every iteration at kmeans.py:239; the stopping iteration is the
+    same, later launches are no-ops).
+    """
+
+    def __init__(self, n_clusters, n_redo=1, max_iter=100, tol=1e-4, init_mode="kmeans++", verbose=False):
+        super(BatchKMeans, self).__init__()
+        self.n_redo = n_redo
+        self.n_clusters = n_clusters
+        self.max_iter = max_iter
+        self.tol = tol
+        self.init_mode = init_mode
+        self.verbose = verbose
+        self.sync_every = 8
+        self.n_iter_ = None
+        self.inertia_ = None
+
+        self.register_buffer("centroids", None)
+
+    def load_state_dict(self, state_dict, **kwargs):
+        r"""Override the default load_state_dict() to load custom buffers (kmeans.py:32-43)."""
+        for k, v in state_dict.items():
+            if "." not in k:
+                assert hasattr(self, k), f"attribute {k} does not exist"
+                delattr(self, k)
+                self.register_buffer(k, v)
+
+        for name, module in self.named_children():
+            sd = {k.replace(name + ".", ""): v for k, v in state_dict.items() if k.startswith(name + ".")}
+            module.load_state_dict(sd)
+
+    # ---- small static helpers: tensor algebra on (l,d,K)-sized or already reduced data ----
+    @staticmethod
+    def calculate_error(a, b):
+        r"""Compute L2 error between a and b"""
+        diff = a - b
+        diff.pow_(2)
+        return diff.sum()
+
+    @staticmethod
+    def calculate_inertia(a):
+        r"""Compute inertia of a"""
+        return (-a).mean()
+
+    @staticmethod
+    def euc_sim(a, b):
+        r"""Batched negative squared Euclidean distance, (..., d, m) x (..., d, n) -> (..., m, n).
+
+        Utility kept for API parity (kmeans.py:59-76); it materialises the full matrix with tensor
+        algebra on whatever device its inputs live.  The clustering itself never calls it: get_labels
+        fuses similarity, arg-max and the centroid accumulation in one CUDA kernel."""
+        y = a.transpose(-2, -1) @ b
+        y.mul_(2)
+        y.sub_(a.pow(2).sum(dim=-2)[..., :, None])
+        y.sub_(b.pow(2).sum(dim=-2)[..., None, :])
+        return y
+
+    # ---- seeding (kmeans.py:78-141) ----
+    def kmeanspp(self, data):
+        r"""Initialize centroids with the reference's farthest-point 'k-means++' (..., d, N) -> (..., d, K)"""
+        x, lead = _as_ldn(data)
+        first = np.random.randint(x.size(-1))
+        cent = ops.kmeans_farthest_init(x, self.n_clusters, first)
+        return ops.back_to(cent.reshape(*lead, x.size(1), self.n_clusters), data)
+
+    def initialize_centroids(self, data):
+        r"""Initialize centroids with init_mode specified in __init__"""
+        n_data = data.size(-1)
+        if self.init_mode == "random":
+            random_index = np.random.choice(n_data, size=[self.n_clusters], replace=False)
+            centroids = data[..., torch.as_tensor(random_index, device=data.device)].clone()
+            if self.verbose:
+                print("centroids are randomly initialized.")
+        elif self.init_mode == "kmeans++":
+            centroids = self.kmeanspp(data).clone()
+            if self.verbose:
+                print("centroids are initialized with kmeans++.")
+        else:
+            raise NotImplementedError
+        return centroids
+
+    # ---- one Lloyd half-step each (kmeans.py:143-198) ----
+    def get_labels(self, data, centroids):
+        r"""Compute labels of data -> (maxsims (..., N) fp32, labels (..., N) int64)"""
+        x, lead = _as_ldn(data)
+        c, _ = _as_ldn(centroids)
+        c = c.to(x.device)
+        maxsims, labels = ops.kmeans_assign(x, c)
+        n = x.size(-1)
+        return (ops.back_to(maxsims.reshape(*lead, n), data), ops.back_to(labels.reshape(*lead, n), data))
+
+    def compute_centroids_loop(self, data, labels):
+        r"""Compute centroids of data given labels (kmeans.py:160-184): masked sum / count per cluster
+        (fp64 accumulation; an empty cluster yields NaN exactly as the reference's 0/0 does)."""
+        x, lead = _as_ldn(data)
+        l, d, n = x.shape
+        lab = labels.reshape(l, n).to(device=x.device, dtype=torch.int64).contiguous()
+        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device, 1)
+        ops.kmeans_accumulate(x, lab, acc)
+        cent = torch.empty((l, d, self.n_clusters), device=x.device)
+        ops.kmeans_finalize(acc, None, cent)
+        return ops.back_to(cent.reshape(*lead, d, self.n_clusters), data)
+
+    def compute_centroids(self, data, labels):
+        r"""Compute centroids of data"""
+        return self.compute_centroids_loop(data, labels)
+
+    # ---- fit / predict (kmeans.py:200-272) ----
+    def _lloyd(self, x, centroids, acc):
+        """Run Lloyd iterations from ``centroids`` on the device.  Returns (labels, centroids, n_iter, error, inertia)."""
+        l, d, n = x.shape
+        bufs = [centroids.contiguous().clone(), torch.empty_like(centroids)]
+        acc.status.zero_()
+        acc.sums.zero_()
+        acc.counts.zero_()
+        acc.simsum.zero_()
+        done = 0
+        n_iter = 0
+        while done < self.max_iter:
+            chunk = min(self.sync_every, self.max_iter - done)
+            for j in range(done, done + chunk):
+                cur, nxt = bufs[j % 2], bufs[(j + 1) % 2]
+                ops.kmeans_assign(x, cur, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum[j],
+                                  status=acc.status)
+                ops.kmeans_finalize(acc, cur, nxt, tol=self.tol, use_status=True)
+            done += chunk
+            converged, n_iter = (int(v) for v in acc.status.tolist())    # the only host sync per chunk
+            if self.verbose:
+                print(f"----{n_iter} iterations done, converged={bool(converged)}")
+            if converged:
+                break
+        final = bufs[n_iter % 2]
+        before = bufs[(n_iter - 1) % 2]
+        _, labels = ops.kmeans_assign(x, before, want_labels=True, want_maxsims=False)
+        inertia = -(acc.simsum[n_iter - 1] / n).mean()
+        return labels, final.clone(), n_iter, acc.err.clone(), inertia
+
+    def fit(self, data, centroids=None):
+        r"""Perform K-means clustering, and return final labels
+
+        Args:
+            data (torch.Tensor): data to be clustered, shape (l, d_vector, n_data)
+            centroids (torch.Tensor): initial centroids, shape (l, d_vector, n_clusters)
+
+        Returns:
+            best_labels (torch.Tensor): final labels, shape (l, n_data)
+        """
+        assert data.is_contiguous(), "use .contiguous()"
+        x, lead = _as_ldn(data)
+        l, d, n = x.shape
+        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device, self.max_iter)
+
+        best_centroids = best_labels = None
+        best_inertia = 1e32
+        if self.verbose:
+            tm = time()
+        for i in range(self.n_redo):
+            if self.verbose:
+                tm_i = time()
+            if centroids is None:
+                c0 = self.initialize_centroids(x)
+            else:
+                c0, _ = _as_ldn(centroids)
+                c0 = c0.to(x.device)
+            labels, cent, n_iter, error, inertia = self._lloyd(x, c0, acc)
+            inertia = float(inertia)
+            if inertia < best_inertia:
+                best_centroids, best_labels, best_inertia = cent, labels, inertia
+                self.n_iter_ = n_iter
+            centroids = None
+            if self.verbose:
+                print(f"--{i}th redo finished, error: {float(error)}, inertia: {inertia}, "
+                      f"time spent:{round(time() - tm_i, 4)} sec")
+        if best_centroids is None:          # every redo produced NaN inertia: keep the last, as a max() would not
+            best_centroids, best_labels = cent, labels
+        self.inertia_ = best_inertia
+        k = self.n_clusters
+        self.register_buffer("centroids", ops.back_to(best_centroids.reshape(*lead, d, k), data))
+        if self.verbose:
+            print(f"finished {self.n_redo} redos in {round(time() - tm, 4)} sec, final_inertia: {best_inertia}")
+        return ops.back_to(best_labels.reshape(*lead, n), data)
+
+    def predict(self, query):
+        r"""Predict the closest cluster center each sample in query belongs to."""
+        _, labels = self.get_labels(query, self.centroids)
+        return labels

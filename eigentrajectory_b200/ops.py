@@ -1,0 +1,377 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, every FLOP in libet_b200.so.
+
+All functions accept CUDA or host tensors.  Host tensors are copied to the current CUDA device,
+processed there and the results copied back (this is the end-to-end path ``bench.py`` reports as
+``e2e``); nothing here computes on the CPU.  PyTorch is used for memory, streams and autograd
+plumbing only.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ET_NORM_ORI, ET_NORM_ROT, ET_NORM_SCA, check, load, ptr, stream_of
+
+
+# ----------------------------------------------------------------------------------------
+# device plumbing
+# ----------------------------------------------------------------------------------------
+def compute_device():
+    _lib.require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_dev(t, dtype=torch.float32):
+    """Contiguous tensor of ``dtype`` on the compute device (no copy if it already is one)."""
+    if t is None:
+        return None
+    if t.is_cuda:
+        dev = t.device
+    else:
+        dev = compute_device()
+    return t.detach().to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
+
+def back_to(t, like):
+    """Return ``t`` on the device ``like`` lives on."""
+    if t is None or like is None or t.device == like.device:
+        return t
+    return t.to(like.device)
+
+
+def norm_flags(ori, rot, sca):
+    return (ET_NORM_ORI if ori else 0) | (ET_NORM_ROT if rot else 0) | (ET_NORM_SCA if sca else 0)
+
+
+def _ntc(traj):
+    assert traj.dim() == 3 and traj.size(2) == 2, f"expected (N, T, 2), got {tuple(traj.shape)}"
+    return traj.size(0), traj.size(1)
+
+
+# ----------------------------------------------------------------------------------------
+# normaliser (EigenTrajectory/normalizer.py)
+# ----------------------------------------------------------------------------------------
+def norm_params(obs, ori=True, rot=True, sca=True):
+    """TrajNorm.calculate_params: returns (ori (N,1,2)|None, rot (N,2,2)|None, sca (N,1,1)|None)."""
+    x = to_dev(obs)
+    n, t = _ntc(x)
+    o = torch.empty((n, 1, 2), device=x.device) if ori else None
+    r = torch.empty((n, 2, 2), device=x.device) if rot else None
+    s = torch.empty((n, 1, 1), device=x.device) if sca else None
+    check(load().et_norm_params(ptr(x), n, t, norm_flags(ori, rot, sca), ptr(o), ptr(r), ptr(s), stream_of(x.device)),
+          "et_norm_params")
+    return back_to(o, obs), back_to(r, obs), back_to(s, obs)
+
+
+def _apply_norm(fn_name, traj, ori, rot, sca):
+    x = to_dev(traj)
+    n, t = _ntc(x)
+    o, r, s = (to_dev(v).to(x.device) if v is not None else None for v in (ori, rot, sca))
+    for name, v, shape in (("ori", o, (n, 1, 2)), ("rot", r, (n, 2, 2)), ("sca", s, (n, 1, 1))):
+        assert v is None or tuple(v.shape) == shape, f"normaliser state {name} has shape {tuple(v.shape)}, expected {shape}"
+    out = torch.empty_like(x)
+    fn = getattr(load(), fn_name)
+    check(fn(ptr(x), n, t, norm_flags(o is not None, r is not None, s is not None), ptr(o), ptr(r), ptr(s), ptr(out),
+             stream_of(x.device)), fn_name)
+    return back_to(out, traj)
+
+
+def normalize(traj, ori, rot, sca):
+    """TrajNorm.normalize with explicit state (None = stage disabled)."""
+    return _apply_norm("et_normalize", traj, ori, rot, sca)
+
+
+def denormalize(traj, ori, rot, sca):
+    """TrajNorm.denormalize with explicit state (None = stage disabled)."""
+    return _apply_norm("et_denormalize", traj, ori, rot, sca)
+
+
+# ----------------------------------------------------------------------------------------
+# descriptor (EigenTrajectory/descriptor.py)
+# ----------------------------------------------------------------------------------------
+def to_et_space(traj, evec):
+    """C (k,N) = evec^T M,  M = traj.reshape(-1, 2T)^T."""
+    U = to_dev(evec)
+    x = to_dev(traj).to(U.device).reshape(-1, U.size(0))
+    n, k = x.size(0), U.size(1)
+    assert U.size(0) % 2 == 0
+    C = torch.empty((k, n), device=x.device)
+    check(load().et_to_et_space(ptr(x), n, U.size(0) // 2, ptr(U), k, ptr(C), stream_of(x.device)), "et_to_et_space")
+    return back_to(C, traj)
+
+
+def to_euclidean_space(C, evec, dim=2):
+    """traj (N,T,dim) = (evec C)^T; C (k,N) may be a strided view (e.g. C3[:, :, s])."""
+    assert dim == 2, "only 2-D trajectories are supported"
+    U = to_dev(evec)
+    Cd = C.detach()
+    if not Cd.is_cuda:
+        Cd = Cd.to(U.device)
+    if Cd.dtype != torch.float32:
+        Cd = Cd.float()
+    assert Cd.dim() == 2 and Cd.size(0) == U.size(1)
+    n, k = Cd.size(1), Cd.size(0)
+    out = torch.empty((n, U.size(0) // 2, 2), device=Cd.device)
+    check(load().et_to_euclidean_space(ptr(Cd), Cd.stride(0), Cd.stride(1), n, U.size(0) // 2, ptr(U), k, ptr(out),
+                                       stream_of(Cd.device)), "et_to_euclidean_space")
+    return back_to(out, C)
+
+
+def project(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True):
+    """Fused normalise + projection.  Returns (C_obs, C_pred|None, (ori, rot, sca))."""
+    x = to_dev(obs)
+    n, t_obs = _ntc(x)
+    p = to_dev(pred).to(x.device) if pred is not None else None
+    t_pred = p.size(1) if p is not None else 0
+    Uo = to_dev(U_obs).to(x.device)
+    Up = to_dev(U_pred).to(x.device) if p is not None else None
+    k = Uo.size(1)
+    C_obs = torch.empty((k, n), device=x.device)
+    C_pred = torch.empty((k, n), device=x.device) if p is not None else None
+    o = torch.empty((n, 1, 2), device=x.device) if ori else None
+    r = torch.empty((n, 2, 2), device=x.device) if rot else None
+    s = torch.empty((n, 1, 1), device=x.device) if sca else None
+    check(load().et_project(ptr(x), ptr(p), n, t_obs, t_pred, ptr(Uo), ptr(Up), k, norm_flags(ori, rot, sca), ptr(C_obs),
+                            ptr(C_pred), ptr(o), ptr(r), ptr(s), stream_of(x.device)), "et_project")
+    return (back_to(C_obs, obs), back_to(C_pred, obs), (back_to(o, obs), back_to(r, obs), back_to(s, obs)))
+
+
+def _reconstruct_raw(C, anchor, U, state, t_pred):
+    ori, rot, sca = state
+    k, n, s = C.shape
+    out = torch.empty((s, n, t_pred, 2), device=C.device)
+    flags = norm_flags(ori is not None, rot is not None, sca is not None)
+    check(load().et_reconstruct(ptr(C), ptr(anchor), n, s, k, t_pred, ptr(U), flags, ptr(ori), ptr(rot), ptr(sca),
+                                ptr(out), stream_of(C.device)), "et_reconstruct")
+    return out
+
+
+class _Reconstruct(torch.autograd.Function):
+    """out (S,N,T,2) = denormalise(U (C + anchor)); differentiable wrt C only (descriptor.py:87, anchor.py:87)."""
+
+    @staticmethod
+    def forward(ctx, C, anchor, U, ori, rot, sca):
+        ctx.save_for_backward(U, rot, sca)
+        ctx.flags = norm_flags(ori is not None, rot is not None, sca is not None)
+        return _reconstruct_raw(C, anchor, U, (ori, rot, sca), U.size(0) // 2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        U, rot, sca = ctx.saved_tensors
+        g = grad_out.contiguous()
+        s, n, t, _ = g.shape
+        k = U.size(1)
+        grad_C = torch.empty((k, n, s), device=g.device)
+        check(load().et_reconstruct_bwd(ptr(g), n, s, k, t, ptr(U), ctx.flags, ptr(rot), ptr(sca), ptr(grad_C),
+                                        stream_of(g.device)), "et_reconstruct_bwd")
+        return grad_C, None, None, None, None, None
+
+
+def reconstruct(C_pred, U_pred, state, anchor=None):
+    """ETDescriptor.reconstruction (optionally fused with ETAnchor.forward).
+
+    C_pred (k,N,S) -> (S,N,T,2); ``state`` = (ori, rot, sca) of the same batch (None = disabled).
+    Gradients flow to ``C_pred`` only.
+    """
+    assert C_pred.dim() == 3
+    like = C_pred
+    needs_grad = C_pred.requires_grad and torch.is_grad_enabled()
+    if not C_pred.is_cuda:
+        dev = compute_device()
+        Cd = C_pred.to(dev)
+    else:
+        dev, Cd = C_pred.device, C_pred
+    Cd = Cd.float().contiguous()
+    U = to_dev(U_pred).to(dev)
+    st = tuple(to_dev(v).to(dev) if v is not None else None for v in state)
+    n = Cd.size(1)
+    for name, v, shape in (("ori", st[0], (n, 1, 2)), ("rot", st[1], (n, 2, 2)), ("sca", st[2], (n, 1, 1))):
+        assert v is None or tuple(v.shape) == shape, (
+            f"normaliser state {name} has shape {tuple(v.shape)} but the coefficients hold {n} pedestrians")
+    a = to_dev(anchor).to(dev) if anchor is not None else None
+    if needs_grad:
+        out = _Reconstruct.apply(Cd, a, U, *st)
+    else:
+        out = _reconstruct_raw(Cd.detach(), a, U, st, U.size(0) // 2)
+    return back_to(out, like)
+
+
+def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, want_coeffs=True, variant=0,
+                        out=None):
+    """Headline op: rank-k round trip of obs and pred in one pass.
+
+    Returns (rec_obs, rec_pred, C_obs|None, C_pred|None).  ``out`` may supply preallocated device
+    tensors (rec_obs, rec_pred, C_obs, C_pred) to keep allocation out of a timed region.
+    """
+    x = to_dev(obs)
+    n, t_obs = _ntc(x)
+    p = to_dev(pred).to(x.device)
+    t_pred = p.size(1)
+    Uo, Up = to_dev(U_obs).to(x.device), to_dev(U_pred).to(x.device)
+    k = Uo.size(1)
+    if out is not None:
+        rec_obs, rec_pred, C_obs, C_pred = out
+    else:
+        rec_obs, rec_pred = torch.empty_like(x), torch.empty_like(p)
+        C_obs = torch.empty((k, n), device=x.device) if want_coeffs else None
+        C_pred = torch.empty((k, n), device=x.device) if want_coeffs else None
+    check(load().et_project_reconstruct(ptr(x), ptr(p), n, t_obs, t_pred, ptr(Uo), ptr(Up), k, norm_flags(ori, rot, sca),
+                                        ptr(rec_obs), ptr(rec_pred), ptr(C_obs), ptr(C_pred), variant,
+                                        stream_of(x.device)), "et_project_reconstruct")
+    return back_to(rec_obs, obs), back_to(rec_pred, obs), back_to(C_obs, obs), back_to(C_pred, obs)
+
+
+# ----------------------------------------------------------------------------------------
+# eigen-basis (ETDescriptor.truncated_SVD)
+# ----------------------------------------------------------------------------------------
+_gram_ws = {}
+
+
+def _gram_workspace(device):
+    ws = _gram_ws.get(device)
+    if ws is None:
+        ws = torch.zeros(int(load().et_gram_workspace_bytes()), dtype=torch.uint8, device=device)
+        _gram_ws[device] = ws
+    return ws
+
+
+def gram(obs, pred=None, ori=False, rot=False, sca=False, G_obs=None, G_pred=None):
+    """float64 Gram matrices of the (optionally normalised) trajectory matrices, one pass.
+
+    Returns (G_obs (2T_obs,2T_obs), G_pred (2T_pred,2T_pred)|None) on the compute device; pass
+    existing ``G_*`` to accumulate into them (row-sharded callers sum these across ranks).
+    """
+    x = to_dev(obs)
+    n, t_obs = _ntc(x)
+    p = to_dev(pred).to(x.device) if pred is not None else None
+    t_pred = p.size(1) if p is not None else 0
+    if G_obs is None:
+        G_obs = torch.zeros((2 * t_obs, 2 * t_obs), dtype=torch.float64, device=x.device)
+    if p is not None and G_pred is None:
+        G_pred = torch.zeros((2 * t_pred, 2 * t_pred), dtype=torch.float64, device=x.device)
+    check(load().et_gram(ptr(x), ptr(p), n, t_obs, t_pred, norm_flags(ori, rot, sca), ptr(G_obs), ptr(G_pred),
+                         ptr(_gram_workspace(x.device)), stream_of(x.device)), "et_gram")
+    return G_obs, (G_pred if p is not None else None)
+
+
+def eig_basis(G, k, want64=False):
+    """Leading-k eigenpairs of a float64 Gram matrix -> (U (m,k) fp32, S (k) fp32[, U64, S64])."""
+    assert G.is_cuda and G.dtype == torch.float64 and G.dim() == 2 and G.size(0) == G.size(1)
+    G = G.contiguous()
+    m = G.size(0)
+    U = torch.empty((m, k), device=G.device)
+    S = torch.empty((k,), device=G.device)
+    U64 = torch.empty((m, k), dtype=torch.float64, device=G.device) if want64 else None
+    S64 = torch.empty((k,), dtype=torch.float64, device=G.device) if want64 else None
+    check(load().et_eig_jacobi(ptr(G), m, k, ptr(U), ptr(S), ptr(U64), ptr(S64), stream_of(G.device)), "et_eig_jacobi")
+    return (U, S, U64, S64) if want64 else (U, S)
+
+
+SVD_SMALL_SMEM_BYTES = 200 * 1024
+
+
+def svd_small_fits(max_rows, t):
+    m = 2 * t
+    mp = (m + 1) & ~1
+    ld = int(max_rows) | 1
+    return (mp * ld + mp * mp + mp) * 4 + mp * 4 <= SVD_SMALL_SMEM_BYTES
+
+
+def svd_small(traj_norm, k, offsets=None):
+    """Batched shared-memory one-sided Jacobi SVD of normalised trajectories.
+
+    traj_norm (N,T,2); ``offsets`` (batch+1,) int64 row boundaries (default: one problem over all
+    rows).  Returns U (batch, 2T, k), S (batch, k).
+    """
+    x = to_dev(traj_norm)
+    n, t = _ntc(x)
+    if offsets is None:
+        offsets = torch.tensor([0, n], dtype=torch.int64)
+    off_host = offsets.detach().cpu().to(torch.int64)
+    batch = off_host.numel() - 1
+    sizes = off_host[1:] - off_host[:-1]
+    assert batch >= 1 and int(off_host[0]) >= 0 and int(off_host[-1]) <= n and bool((sizes >= 0).all())
+    max_rows = int(sizes.max())
+    if not svd_small_fits(max_rows, t):
+        raise ValueError(f"svd_small: {max_rows} rows x {2 * t} columns do not fit shared memory")
+    off = off_host.to(x.device)
+    U = torch.empty((batch, 2 * t, k), device=x.device)
+    S = torch.empty((batch, k), device=x.device)
+    check(load().et_svd_small(ptr(x), ptr(off), batch, max_rows, t, k, ptr(U), ptr(S), stream_of(x.device)),
+          "et_svd_small")
+    return U, S
+
+
+# ----------------------------------------------------------------------------------------
+# k-means (EigenTrajectory/kmeans.py)
+# ----------------------------------------------------------------------------------------
+class KMeansWorkspace:
+    """Device buffers one BatchKMeans.fit needs; allocated once per (l, d, K, device)."""
+
+    def __init__(self, l, d, k, device, max_iter):
+        nbytes = int(load().et_kmeans_workspace_bytes(l, d, k))
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.sums = torch.zeros((l, d, k), dtype=torch.float64, device=device)
+        self.counts = torch.zeros((l, k), dtype=torch.float64, device=device)
+        self.simsum = torch.zeros((max(max_iter, 1), l), dtype=torch.float64, device=device)
+        self.err = torch.zeros((1,), dtype=torch.float64, device=device)
+        self.status = torch.zeros((2,), dtype=torch.int32, device=device)
+        self.scratch = torch.zeros((l * k,), dtype=torch.int64, device=device)
+
+
+def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None, simsum=None, status=None):
+    """get_labels (+ optional accumulation for compute_centroids).  data (l,d,N), centroids (l,d,K) on the GPU."""
+    l, d, n = data.shape
+    k = centroids.size(-1)
+    labels = torch.empty((l, n), dtype=torch.int64, device=data.device) if want_labels else None
+    maxsims = torch.empty((l, n), dtype=torch.float32, device=data.device) if want_maxsims else None
+    sums = counts = ws = None
+    if acc is not None:
+        sums, counts, ws = acc.sums, acc.counts, acc.ws
+    check(load().et_kmeans_assign(ptr(data), ptr(centroids), l, d, n, k, ptr(labels), ptr(maxsims), ptr(sums), ptr(counts),
+                                  ptr(simsum), ptr(ws), ptr(status), stream_of(data.device)), "et_kmeans_assign")
+    return maxsims, labels
+
+
+def kmeans_accumulate(data, labels, acc):
+    """Masked sums / counts of compute_centroids for given labels (added into ``acc``)."""
+    l, d, n = data.shape
+    k = acc.sums.size(-1)
+    check(load().et_kmeans_accumulate(ptr(data), ptr(labels), l, d, n, k, ptr(acc.sums), ptr(acc.counts), ptr(acc.ws),
+                                      stream_of(data.device)), "et_kmeans_accumulate")
+
+
+def kmeans_finalize(acc, old_centroids, new_centroids, tol=0.0, use_status=False):
+    l, d, k = acc.sums.shape
+    check(load().et_kmeans_finalize(ptr(acc.sums), ptr(acc.counts), l, d, k, ptr(old_centroids), ptr(new_centroids),
+                                    ptr(acc.err), float(tol), ptr(acc.status) if use_status else None,
+                                    stream_of(new_centroids.device)), "et_kmeans_finalize")
+
+
+def kmeans_farthest_init(data, k, first_index, scratch=None):
+    l, d, n = data.shape
+    cent = torch.empty((l, d, k), device=data.device)
+    if scratch is None:
+        scratch = torch.empty((l * k,), dtype=torch.int64, device=data.device)
+    check(load().et_kmeans_farthest_init(ptr(data), l, d, n, k, int(first_index), ptr(cent), ptr(scratch),
+                                         stream_of(data.device)), "et_kmeans_farthest_init")
+    return cent
+
+
+# ----------------------------------------------------------------------------------------
+# metrics (utils/metrics.py)
+# ----------------------------------------------------------------------------------------
+def ade_fde(pred, gt, want_argmin=False):
+    """min-over-samples ADE and FDE per pedestrian in one pass.  pred (S,N,T,2), gt (N,T,2)|(1,N,T,2)."""
+    p = to_dev(pred)
+    g = to_dev(gt).to(p.device)
+    if g.dim() == 4:
+        assert g.size(0) == 1
+        g = g[0]
+    s, n, t, c = p.shape
+    assert c == 2 and tuple(g.shape) == (n, t, 2), f"pred {tuple(p.shape)} vs gt {tuple(g.shape)}"
+    ade = torch.empty((n,), device=p.device)
+    fde = torch.empty((n,), device=p.device)
+    arg = torch.empty((n,), dtype=torch.int32, device=p.device) if want_argmin else None
+    check(load().et_ade_fde(ptr(p), ptr(g), s, n, t, ptr(ade), ptr(fde), ptr(arg), stream_of(p.device)), "et_ade_fde")
+    return (ade, fde, arg) if want_argmin else (ade, fde)

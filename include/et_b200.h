@@ -1,0 +1,188 @@
+/*
+ * et_b200.h -- C ABI of libet_b200.so, the B200 (sm_100a) implementation of the
+ * EigenTrajectory descriptor hot path.
+ *
+ * The reference (InhwanBae/EigenTrajectory) is pure Python/PyTorch and has no FFI of
+ * its own; the entry points below are what a binding for this path attaches to.  Each
+ * one cites the reference code it replaces (path:line relative to the reference
+ * checkout).  The Python classes in eigentrajectory_b200/ (ETDescriptor, ETAnchor,
+ * TrajNorm, BatchKMeans, compute_batch_ade/fde) call these through ctypes and nothing
+ * else; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the library never
+ *    allocates, frees or synchronises: the caller owns all buffers and the stream;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *  - return value: 0 (ET_OK) or a negative ET_ERR_* code; et_last_error() returns a
+ *    thread-local, human readable message for the last failure on this thread;
+ *  - trajectories are float32, contiguous (N, T, 2) "NTC"; coefficient matrices are
+ *    float32 contiguous (k, N) / (k, N, S) exactly as the reference lays them out;
+ *  - float4-vectorised and TMA paths need 16-byte aligned base pointers (ET_ERR_ALIGN
+ *    otherwise); torch allocations always are.
+ *  - normaliser flags are a bit-or of ET_NORM_ORI | ET_NORM_ROT | ET_NORM_SCA
+ *    (TrajNorm(ori, rot, sca), EigenTrajectory/normalizer.py:13-15).
+ */
+#ifndef ET_B200_H_
+#define ET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ET_B200_VERSION 100
+
+enum {
+  ET_OK = 0,
+  ET_ERR_BADARG = -1,      /* null pointer, negative size, unsupported shape       */
+  ET_ERR_ALIGN = -2,       /* pointer not 16-byte aligned                           */
+  ET_ERR_CUDA = -3,        /* a CUDA runtime / driver call or a launch failed       */
+  ET_ERR_UNSUPPORTED = -4  /* shape outside what the kernels were built for         */
+};
+
+enum { ET_NORM_ORI = 1, ET_NORM_ROT = 2, ET_NORM_SCA = 4 };
+
+/* Limits of the generic kernels (fast paths exist for T_obs=8, T_pred=12, k=6, S=20). */
+#define ET_MAX_T 32    /* frames per trajectory segment (2T <= 64 coordinates)            */
+#define ET_MAX_K 32    /* rank of the eigen-basis                                         */
+#define ET_MAX_CLUSTERS 64
+#define ET_MAX_KM_DIM 16
+
+typedef void* et_stream_t;
+
+/* ---- library ---------------------------------------------------------------------- */
+int et_version(void);
+const char* et_last_error(void);
+/* Device the calling thread is on: SM count and compute capability. */
+int et_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Total number of kernels this library has launched from this process (all threads). */
+int64_t et_launch_count(void);
+
+/* ---- normaliser: EigenTrajectory/normalizer.py ------------------------------------- */
+/* TrajNorm.calculate_params (normalizer.py:17-28).  obs (N,T_obs,2), T_obs >= 3.
+ * ori (N,1,2), rot (N,2,2) = [[c,-s],[s,c]], sca (N,1,1) = (1/||d||)*2; outputs whose
+ * flag bit is clear may be null and are not written. */
+int et_norm_params(const float* obs, int64_t n, int t_obs, int flags,
+                   float* ori, float* rot, float* sca, et_stream_t stream);
+/* TrajNorm.normalize (normalizer.py:42-51): out = ((x - ori) @ R) * sca. */
+int et_normalize(const float* traj, int64_t n, int t, int flags, const float* ori,
+                 const float* rot, const float* sca, float* out, et_stream_t stream);
+/* TrajNorm.denormalize (normalizer.py:53-62): out = ((x / sca) @ R^T) + ori. */
+int et_denormalize(const float* traj, int64_t n, int t, int flags, const float* ori,
+                   const float* rot, const float* sca, float* out, et_stream_t stream);
+
+/* ---- descriptor: EigenTrajectory/descriptor.py -------------------------------------- */
+/* ETDescriptor.to_ET_space (descriptor.py:59-73; same body at anchor.py:22-36):
+ * C (k,N) = U^T M with M the (2T,N) view of traj (N,T,2); U (2T,k) row-major. */
+int et_to_et_space(const float* traj, int64_t n, int t, const float* U, int k, float* C,
+                   et_stream_t stream);
+/* ETDescriptor.to_Euclidean_space (descriptor.py:75-89): traj (N,T,2) = (U C)^T.
+ * C is addressed as C[j*ldc_k + i*ldc_n], so a (k,N,S) slice [:, :, s] is ldc_k=N*S,
+ * ldc_n=S with the base pointer advanced by s. */
+int et_to_euclidean_space(const float* C, int64_t ldc_k, int64_t ldc_n, int64_t n, int t,
+                          const float* U, int k, float* traj, et_stream_t stream);
+/* ETDescriptor.projection (descriptor.py:144-160) fused with normalize_trajectory
+ * (descriptor.py:29-45): derives the normaliser state from obs, writes it (ori/rot/sca,
+ * see et_norm_params), and writes C_obs (k,N) and, when pred != null, C_pred (k,N). */
+int et_project(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred,
+               const float* U_obs, const float* U_pred, int k, int flags, float* C_obs,
+               float* C_pred, float* ori, float* rot, float* sca, et_stream_t stream);
+/* ETDescriptor.reconstruction (descriptor.py:162-176) fused with ETAnchor.forward
+ * (anchor.py:76-88): out (S,N,T,2) = denormalise(U (C[:,:,s] + anchor[:,s])).
+ * C (k,N,S); anchor (k,S) or null; state as written by et_project. */
+int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k, int t,
+                   const float* U, int flags, const float* ori, const float* rot,
+                   const float* sca, float* out, et_stream_t stream);
+/* Gradient of et_reconstruct wrt C (autograd through descriptor.py:173-175; U, anchor
+ * and the state are constants, descriptor.py:87, anchor.py:87):
+ * grad_C (k,N,S) = U^T (R^T-rotate(grad_out[s,n]) / sca). */
+int et_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t, const float* U,
+                       int flags, const float* rot, const float* sca, float* grad_C,
+                       et_stream_t stream);
+/* Headline op (BASELINE.json config 2): rank-k round trip of obs and pred in one pass,
+ * the S=1 shape of script/descriptor_evaluation.py:94-107 on top of descriptor.py:144-176.
+ * rec_obs (N,T_obs,2), rec_pred (N,T_pred,2); C_obs / C_pred (k,N) are optional (null =
+ * coefficients are not materialised: 320 instead of 368 algorithmic bytes / trajectory).
+ * variant: 0 = auto, 1 = direct global access kernel, 2..4 = persistent warp-specialised
+ * TMA-tiled kernel (2: 4-stage ring, 2 blocks/SM; 3: 3-stage, 3 blocks/SM; 4: 5-stage,
+ * 2 blocks/SM); the TMA variants need (T_obs,T_pred,k) = (8,12,6) and n < 2^31. */
+int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t_obs,
+                           int t_pred, const float* U_obs, const float* U_pred, int k,
+                           int flags, float* rec_obs, float* rec_pred, float* C_obs,
+                           float* C_pred, int variant, et_stream_t stream);
+
+/* ---- eigen-basis: ETDescriptor.truncated_SVD (descriptor.py:91-114) ------------------ */
+/* One pass over the data: G_obs (2T_obs x 2T_obs) += M_obs M_obs^T and, when pred != null,
+ * G_pred += M_pred M_pred^T, in float64 (FP64 tensor-core DMMA on the (8,12) fast path), where
+ * M_* are the normalised matrices (normalisation by `flags` fused; flags = 0 and pred = null
+ * gives the plain Gram matrix of an already normalised (N,T,2) tensor).  Accumulates into G
+ * (caller zeroes it); the sum over row shards of N is what a multi-GPU caller all-reduces.
+ * workspace: et_gram_workspace_bytes() bytes, zero-filled once by the caller (the kernel leaves
+ * its ticket word zero again, so the buffer can be reused without clearing). */
+size_t et_gram_workspace_bytes(void);
+int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags,
+            double* G_obs, double* G_pred, void* workspace, et_stream_t stream);
+/* Symmetric eigen-solve of G (m x m, float64, m <= 64) by parallel-ordered cyclic Jacobi;
+ * returns the k leading left singular vectors U (m,k) row-major float32 and singular
+ * values S (k) = sqrt(lambda).  Column signs are canonical: the largest-magnitude
+ * component of each column is positive.  U64 (m,k) / S64 (k) optional float64 copies. */
+int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64,
+                  et_stream_t stream);
+/* Batched small-N SVD: one-sided (Hestenes) Jacobi on shared-memory resident tall-skinny
+ * matrices.  Problem b is the (n_b x 2T) matrix of the trajectories
+ * traj[offsets[b] .. offsets[b+1]) (already normalised).  offsets is a DEVICE int64 array
+ * of batch+1 entries; max_rows >= max_b n_b sizes shared memory (n_b*2T*4 bytes must fit
+ * 200 KB).  U (batch, 2T, k), S (batch, k). */
+int et_svd_small(const float* traj, const int64_t* offsets, int batch, int64_t max_rows, int t,
+                 int k, float* U, float* S, et_stream_t stream);
+
+/* ---- k-means: EigenTrajectory/kmeans.py ----------------------------------------------- */
+/* BatchKMeans.get_labels (kmeans.py:143-158) fused with the accumulation half of
+ * compute_centroids (kmeans.py:160-184).  data (l,d,N), centroids (l,d,K), d <= 16, K <= 64.
+ * sim = fl(fl(fl(2*dot) - |a|^2) - |b|^2), dot an ascending fp32 FMA chain from 0 and the
+ * squared norms summed in torch's CPU order (bit-equal to the reference's CPU result, see
+ * DESIGN.md), arg-max with lowest index on ties, NaN wins.
+ * Optional outputs: labels int64 (l,N), maxsims float (l,N).
+ * Optional accumulators (float64, ADDED to, caller zeroes once): sums (l,d,K), counts (l,K),
+ * simsum (l) = sum of maxsims.  workspace: et_kmeans_workspace_bytes() bytes, zero-filled once.
+ * status (optional, device int32[2]): when status[0] != 0 the call is a no-op (see finalize). */
+size_t et_kmeans_workspace_bytes(int l, int d, int k_clusters);
+int et_kmeans_assign(const float* data, const float* centroids, int l, int d, int64_t n,
+                     int k_clusters, int64_t* labels, float* maxsims, double* sums,
+                     double* counts, double* simsum, void* workspace, const int32_t* status,
+                     et_stream_t stream);
+/* Accumulation half of compute_centroids (kmeans.py:160-184) for caller-supplied labels
+ * (l,N) int64; labels outside [0,K) are ignored.  sums / counts / workspace as above. */
+int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n,
+                         int k_clusters, double* sums, double* counts, void* workspace,
+                         et_stream_t stream);
+/* Division half of compute_centroids + calculate_error (kmeans.py:45-51,183):
+ * new_centroids = float(sums / counts) (0/0 -> NaN as in the reference);
+ * err[0] = sum((old - new)^2) in float64 when err and old_centroids are given; sums / counts
+ * are cleared for the next iteration.  With status (device int32[2]): a no-op when
+ * status[0] != 0, otherwise status[1] += 1 and status[0] = (err <= tol) -- the reference's
+ * `if error <= self.tol: break` (kmeans.py:239) evaluated on the device, so that a host can
+ * enqueue several Lloyd iterations without synchronising. */
+int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_clusters,
+                       const float* old_centroids, float* new_centroids, double* err, double tol,
+                       int32_t* status, et_stream_t stream);
+/* BatchKMeans.kmeanspp (kmeans.py:78-112): deterministic farthest-point seeding.
+ * centroids (l,d,K) out; column 0 = data[..., first_index]; every later column is the point
+ * whose best similarity to the columns chosen so far is lowest (lowest index on ties),
+ * recomputed from scratch each step as the reference does.  scratch: l*K uint64. */
+int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_clusters,
+                            int64_t first_index, float* centroids, unsigned long long* scratch,
+                            et_stream_t stream);
+
+/* ---- metrics: utils/metrics.py ---------------------------------------------------------- */
+/* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass.
+ * pred (S,N,T,2), gt (N,T,2); ade (N), fde (N) float; argmin_fde (N) int32 optional. */
+int et_ade_fde(const float* pred, const float* gt, int s, int64_t n, int t, float* ade,
+               float* fde, int32_t* argmin_fde, et_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ET_B200_H_ */

@@ -1,0 +1,309 @@
+"""CPU oracle for the EigenTrajectory hot path -- TEST INFRASTRUCTURE ONLY.
+
+This module restates, op for op, the arithmetic of the reference's descriptor /
+normaliser / k-means / metric path as stateless functions on CPU torch tensors.
+It is the *checker* for the CUDA kernels in ``eigentrajectory_b200/csrc``; nothing
+in the product package imports it.  Only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may use it.
+
+Parity status: PINNED to outputs of the reference itself.  ``tests/golden/make_golden.py``
+imports the reference from ``/root/reference`` (CPU, torch 2.11) and freezes its
+outputs into ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks every
+function below against those vectors (bit-exact for everything except the SVD,
+whose LAPACK call is shared anyway).  The reference has no tests / golden vectors
+of its own, and its third-party arithmetic (LAPACK gesdd via
+``torch.linalg.svd``, MKL sgemm) is not version-pinned upstream; the pin is the
+fixtures generated in this container.
+
+All functions are dtype-generic: pass float64 tensors to obtain the fp64 "truth"
+used to decide who is closer (ours or the reference's fp32 LAPACK).
+
+Citations are ``path:line`` relative to the reference checkout.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+# --------------------------------------------------------------------------------------
+# Normaliser  (EigenTrajectory/normalizer.py)
+# --------------------------------------------------------------------------------------
+
+
+def norm_params(obs, use_ori=True, use_rot=True, use_sca=True):
+    """Per-pedestrian origin / rotation / scale from the observed track.
+
+    Follows ``EigenTrajectory/normalizer.py:17-28``: origin is the last observed
+    frame, heading is atan2 of (last - third-from-last), rotation matrix rows are
+    (cos, -sin), (sin, cos), scale is (1/||d||) * 2.
+    Returns (ori (N,1,2) | None, rot (N,2,2) | None, sca (N,1,1) | None).
+    """
+    ori = rot = sca = None
+    if use_ori:
+        ori = obs[:, [-1]]
+    if use_rot:
+        d = obs[:, -1] - obs[:, -3]
+        th = torch.atan2(d[:, 1], d[:, 0])
+        c, s = th.cos(), th.sin()
+        rot = torch.stack([torch.stack([c, -s], dim=1), torch.stack([s, c], dim=1)], dim=1)
+    if use_sca:
+        sca = 1.0 / (obs[:, -1] - obs[:, -3]).norm(p=2, dim=-1)[:, None, None] * 2
+    return ori, rot, sca
+
+
+def normalize(traj, ori, rot, sca):
+    """``normalizer.py:42-51``: ((x - ori) @ R) * sca, each stage optional."""
+    if ori is not None:
+        traj = traj - ori
+    if rot is not None:
+        traj = traj @ rot
+    if sca is not None:
+        traj = traj * sca
+    return traj
+
+
+def denormalize(traj, ori, rot, sca):
+    """``normalizer.py:53-62``: ((x / sca) @ R^T) + ori, each stage optional."""
+    if sca is not None:
+        traj = traj / sca
+    if rot is not None:
+        traj = traj @ rot.transpose(-1, -2)
+    if ori is not None:
+        traj = traj + ori
+    return traj
+
+
+def static_mask(obs, static_dist):
+    """``EigenTrajectory/model.py:46,73``: moving iff ||(last - third_last)/2|| > static_dist."""
+    return (obs[:, -1] - obs[:, -3]).div(2).norm(p=2, dim=-1) > static_dist
+
+
+# --------------------------------------------------------------------------------------
+# Descriptor  (EigenTrajectory/descriptor.py)
+# --------------------------------------------------------------------------------------
+
+
+def as_matrix(traj):
+    """(N,T,2) -> the wide strided view M (2T, N) of ``descriptor.py:109``."""
+    n = traj.shape[0]
+    return traj.reshape(n, -1).T
+
+
+def svd_basis(traj_norm, k):
+    """Thin SVD of the wide view, truncated: ``descriptor.py:91-114``.
+
+    Returns U (2T,k), S (k,), V (N,k) exactly as ``truncated_SVD`` does
+    (LAPACK gesdd through torch.linalg.svd).
+    """
+    M = as_matrix(traj_norm)
+    U, S, Vt = torch.linalg.svd(M, full_matrices=False)
+    return U[:, :k], S[:k], Vt[:k, :].T
+
+
+def project(traj_norm, U):
+    """``descriptor.py:59-73``: C (k,N) = U^T M."""
+    return U.T @ as_matrix(traj_norm)
+
+
+def unproject(C, U, dim=2):
+    """``descriptor.py:75-89``: (k,N) -> normalised trajectory (N,T,dim)."""
+    t = U.shape[0] // dim
+    return (U @ C).T.reshape(-1, t, dim)
+
+
+def descriptor_projection(obs, pred, U_obs, U_pred, use_ori=True, use_rot=True, use_sca=True):
+    """``ETDescriptor.projection`` (``descriptor.py:144-160``) as a pure function.
+
+    Returns C_obs (k,N), C_pred (k,N)|None and the normaliser state (ori, rot, sca).
+    """
+    state = norm_params(obs, use_ori, use_rot, use_sca)
+    C_obs = project(normalize(obs, *state), U_obs)
+    C_pred = project(normalize(pred, *state), U_pred) if pred is not None else None
+    return C_obs, C_pred, state
+
+
+def descriptor_reconstruction(C_pred, U_pred, state, dim=2):
+    """``ETDescriptor.reconstruction`` (``descriptor.py:162-176``).
+
+    C_pred (k,N,S) -> (S,N,T,dim); one U @ C[:,:,s] product and one denormalise per
+    sample, stacked on a new leading axis.
+    """
+    out = []
+    for s in range(C_pred.shape[2]):
+        out.append(denormalize(unproject(C_pred[:, :, s], U_pred, dim), *state))
+    return torch.stack(out, dim=0)
+
+
+def anchor_add(C_anchor, C_pred):
+    """``ETAnchor.forward`` (``anchor.py:76-88``): (k,1,S) + (k,N,S)."""
+    return C_anchor.unsqueeze(1) + C_pred
+
+
+def parameter_initialization(obs, pred, k, use_ori=True, use_rot=True, use_sca=True):
+    """``descriptor.py:116-142``: normalise, two truncated SVDs.
+
+    Returns dict(U_obs, S_obs, U_pred, S_pred, obs_norm, pred_norm, state).
+    """
+    state = norm_params(obs, use_ori, use_rot, use_sca)
+    obs_n, pred_n = normalize(obs, *state), normalize(pred, *state)
+    U_o, S_o, _ = svd_basis(obs_n, k)
+    U_p, S_p, _ = svd_basis(pred_n, k)
+    return dict(U_obs=U_o, S_obs=S_o, U_pred=U_p, S_pred=S_p, obs_norm=obs_n, pred_norm=pred_n,
+                state=state)
+
+
+def project_reconstruct(obs, pred, U_obs, U_pred, use_ori=True, use_rot=True, use_sca=True):
+    """The headline op: rank-k round trip of obs and pred with S=1.
+
+    Shape of ``script/descriptor_evaluation.py:94-107`` (project, reconstruct,
+    reshape, denormalise) on top of ``descriptor.py:144-160``.
+    Returns (rec_obs (N,To,2), rec_pred (N,Tp,2), C_obs (k,N), C_pred (k,N)).
+    """
+    C_obs, C_pred, state = descriptor_projection(obs, pred, U_obs, U_pred, use_ori, use_rot, use_sca)
+    rec_obs = denormalize(unproject(C_obs, U_obs), *state)
+    rec_pred = denormalize(unproject(C_pred, U_pred), *state)
+    return rec_obs, rec_pred, C_obs, C_pred
+
+
+def rank_k_errors(obs, pred, kmax=12):
+    """``script/descriptor_evaluation.py:87-112``: mean L2 error of the rank-k round trip.
+
+    Normaliser is ori+rot without scale (``descriptor_evaluation.py:32``).
+    Returns list of (k, obs_err, pred_err) plus the full U/S of both matrices.
+    """
+    state = norm_params(obs, True, True, False)
+    A, B = as_matrix(normalize(obs, *state)), as_matrix(normalize(pred, *state))
+    Uo, So, _ = torch.linalg.svd(A, full_matrices=False)
+    Up, Sp, _ = torch.linalg.svd(B, full_matrices=False)
+    rows = []
+    n = obs.shape[0]
+    for k in range(1, kmax + 1):
+        Ao = Uo[:, :k] @ (Uo[:, :k].T @ A)
+        Bo = Up[:, :k] @ (Up[:, :k].T @ B)
+        ro = denormalize(Ao.T.reshape(n, -1, 2), *state)
+        rp = denormalize(Bo.T.reshape(n, -1, 2), *state)
+        rows.append((k, (ro - obs).norm(p=2, dim=-1).mean().item(),
+                     (rp - pred).norm(p=2, dim=-1).mean().item()))
+    return rows, (Uo, So, Up, Sp)
+
+
+# --------------------------------------------------------------------------------------
+# k-means  (EigenTrajectory/kmeans.py)
+# --------------------------------------------------------------------------------------
+
+
+def kmeans_sim(a, b):
+    """``kmeans.py:59-76``: negative squared distance y = 2 a^T b - |a|^2 - |b|^2.
+
+    a (..., d, m), b (..., d, n) -> (..., m, n); same in-place op order.
+    """
+    y = a.transpose(-2, -1) @ b
+    y.mul_(2)
+    y.sub_(a.pow(2).sum(dim=-2)[..., :, None])
+    y.sub_(b.pow(2).sum(dim=-2)[..., None, :])
+    return y
+
+
+def kmeans_assign(data, centroids):
+    """``kmeans.py:143-158``: (maxsim, label) = max over clusters of kmeans_sim."""
+    return kmeans_sim(data, centroids).max(dim=-1)
+
+
+def kmeans_update(data, labels, n_clusters):
+    """``kmeans.py:160-184``: masked sum / count; empty cluster -> NaN (0/0)."""
+    mask = torch.stack([labels == i for i in range(n_clusters)], dim=-1)
+    return (data.unsqueeze(-1) * mask.unsqueeze(-3)).sum(dim=-2) / mask.sum(dim=-2, keepdim=True)
+
+
+def kmeans_farthest_init(data, n_clusters, first_index):
+    """``kmeans.py:78-112``: deterministic farthest-point seeding.
+
+    The first centroid is ``data[..., first_index]`` (the reference draws it from
+    ``np.random.randint(n_data)``, ``kmeans.py:93``); each next one is the point whose
+    best similarity to the chosen set is lowest.  data (l, d, N) only.
+    """
+    assert data.dim() == 3
+    l, d, _ = data.shape
+    cent = torch.zeros(l, d, n_clusters, dtype=data.dtype)
+    cent[..., 0] = data[..., first_index]
+    rows = torch.arange(l)
+    for i in range(1, n_clusters):
+        best, _ = kmeans_sim(data, cent[..., :i].contiguous()).max(dim=-1)
+        idx = best.argmin(dim=-1)
+        cent[..., i] = data[rows, :, idx]
+    return cent
+
+
+def kmeans_fit(data, n_clusters, centroids=None, first_index=None, max_iter=100, tol=1e-4,
+               trace=None):
+    """``kmeans.py:200-259`` with n_redo=1: Lloyd iterations until sum((c-c')^2) <= tol.
+
+    Returns (labels (l,N) int64, centroids (l,d,K), n_iter, inertia).  ``trace`` (a list)
+    receives (centroids_in, labels, centroids_out) per iteration for lock-step tests.
+    """
+    if centroids is None:
+        if first_index is None:
+            first_index = np.random.randint(data.shape[-1])
+        centroids = kmeans_farthest_init(data, n_clusters, first_index).clone()
+    labels = inertia = None
+    it = 0
+    for it in range(1, max_iter + 1):
+        maxsims, labels = kmeans_assign(data, centroids)
+        new_c = kmeans_update(data, labels, n_clusters)
+        err = (centroids - new_c).pow(2).sum()
+        if trace is not None:
+            trace.append((centroids.clone(), labels.clone(), new_c.clone()))
+        centroids = new_c
+        inertia = (-maxsims).mean()
+        if err <= tol:
+            break
+    return labels, centroids, it, inertia
+
+
+# --------------------------------------------------------------------------------------
+# Metrics  (utils/metrics.py)
+# --------------------------------------------------------------------------------------
+
+
+def ade_fde(pred, gt):
+    """``utils/metrics.py:73-102``: min-over-samples ADE and FDE per pedestrian.
+
+    pred (S,N,T,2), gt (N,T,2) or (1,N,T,2) -> (ade (N,), fde (N,), argmin_fde (N,)).
+    """
+    dist = (pred - gt).norm(p=2, dim=-1)            # (S,N,T)
+    ade = dist.mean(dim=2).min(dim=0)[0]
+    fde, arg = dist[:, :, -1].min(dim=0)
+    return ade, fde, arg
+
+
+def forward_losses(C_pred, C_pred_gt, recon, pred_gt):
+    """``EigenTrajectory/model.py:119-123``: the three training-loss scalars."""
+    e_c = (C_pred - C_pred_gt.unsqueeze(-1)).norm(p=2, dim=0)
+    e_d = (recon - pred_gt.unsqueeze(0)).norm(p=2, dim=-1)
+    return (e_c.min(dim=-1)[0].mean(), e_d.mean(dim=-1).min(dim=0)[0].mean(),
+            e_d[:, :, -1].min(dim=0)[0].mean())
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic workload -- shared by tests and bench's CPU leg
+# --------------------------------------------------------------------------------------
+
+
+def synthetic_trajectories(n, seed=0, t_obs=8, t_pred=12, dtype=torch.float32):
+    """Seeded pedestrian tracks: constant-turn-rate walkers with velocity noise.
+
+    p0 ~ U(-10,10)^2, heading ~ U(0,2pi), speed ~ U(0.2,0.8) m/frame (never static),
+    turn rate ~ N(0,0.05^2), per-frame velocity noise N(0,0.03^2).
+    Returns obs (n,t_obs,2), pred (n,t_pred,2), contiguous.
+    """
+    g = torch.Generator().manual_seed(seed)
+    T = t_obs + t_pred
+    p0 = (torch.rand(n, 1, 2, generator=g) * 20 - 10)
+    th0 = torch.rand(n, 1, generator=g) * (2 * np.pi)
+    v = torch.rand(n, 1, generator=g) * 0.6 + 0.2
+    om = torch.randn(n, 1, generator=g) * 0.05
+    t = torch.arange(T, dtype=torch.float32)[None, :]
+    ang = th0 + om * t
+    vel = torch.stack([v * ang.cos(), v * ang.sin()], dim=-1) + torch.randn(n, T, 2, generator=g) * 0.03
+    traj = (p0 + vel.cumsum(dim=1)).to(dtype)
+    return traj[:, :t_obs].contiguous(), traj[:, t_obs:].contiguous()

@@ -1,0 +1,348 @@
+"""GPU parity: eigen-basis (Gram + Jacobi, one-sided Jacobi), k-means, ADE/FDE and the model wrapper.
+
+SVD criteria: |S - S_ref| / S_ref <= 1e-5; projector distance
+||U U^T - U_ref U_ref^T||_F <= max(1e-5, 2 x the reference's own distance to the fp64 truth); per column
+(after sign alignment) we must be at least as close to fp64 as the reference's fp32 LAPACK is (+1e-6).
+k-means: assignment indices bit-exact vs the reference's CPU arithmetic.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import align_signs, load_golden, rel_fro, rel_max, t
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+HP = dict(obs_len=8, pred_len=12, k=6, num_samples=20, traj_dim=2, static_dist=0.419, obs_svd=True, pred_svd=True)
+
+
+@pytest.fixture(scope="module")
+def et():
+    import eigentrajectory_b200 as et
+    et.load_library()
+    return et
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import et_oracle
+    return et_oracle
+
+
+def projector(U):
+    U = torch.as_tensor(U).double()
+    return U @ U.T
+
+
+def check_basis(U, S, U_ref, S_ref, U64, S64, what):
+    U, S = U.detach().cpu(), S.detach().cpu()
+    assert rel_max(S, S_ref) <= TOL, (what, "S vs ref")
+    if S64 is not None:
+        assert rel_max(S, S64) <= TOL, (what, "S vs fp64")
+    floor = float((projector(U_ref) - projector(U64)).norm()) if U64 is not None else 0.0
+    dist = float((projector(U) - projector(U_ref)).norm())
+    assert dist <= max(TOL, 2 * floor), (what, dist, floor)
+    if U64 is not None:
+        ours, _ = align_signs(U, U64)
+        refs, _ = align_signs(U_ref, U64)
+        U64 = torch.as_tensor(U64).double()
+        e_ours = (ours - U64).norm(dim=0)
+        e_ref = (refs - U64).norm(dim=0)
+        assert bool((e_ours <= e_ref + 1e-6).all()), (what, e_ours.tolist(), e_ref.tolist())
+    # canonical sign: largest-magnitude component positive
+    idx = U.abs().argmax(dim=0)
+    assert bool((U[idx, torch.arange(U.size(1))] > 0).all()), what
+
+
+# --------------------------------------------------------------------------------------
+# eigen-basis
+# --------------------------------------------------------------------------------------
+def eth_init_groups():
+    d = load_golden("eth_init_data")
+    obs, pred = t(d["obs"]), t(d["pred"])
+    flip = torch.tensor([[[1.0, -1.0]]])
+    obs, pred = torch.cat([obs, obs * flip]), torch.cat([pred, pred * flip])        # utils/utils.py:79-81
+    mask = (obs[:, -1] - obs[:, -3]).div(2).norm(p=2, dim=-1) > HP["static_dist"]    # model.py:46
+    return obs, pred, mask
+
+
+def test_eth_init_bases_gram_path(et):
+    g = load_golden("eth_init")
+    obs, pred, mask = eth_init_groups()
+    assert obs.size(0) == int(g["n_total"]) and int(mask.sum()) == int(g["n_moving"])
+    for tag, m, sca in (("m", mask, True), ("s", ~mask, False)):
+        d = et.ETDescriptor(et.DotDict(HP), norm_sca=sca).cuda()
+        pred_norm, U_pred = d.parameter_initialization(obs[m].cuda(), pred[m].cuda())
+        tn = d.traj_normalizer
+        Go, Gp = et.ops.gram(obs[m].cuda(), pred[m].cuda(), tn.ori, tn.rot, tn.sca)
+        for side, G, Up in (("obs", Go, d.U_obs_trunc), ("pred", Gp, d.U_pred_trunc)):
+            U, S, U64, S64 = et.ops.eig_basis(G, 6, want64=True)
+            assert torch.equal(U, Up.detach())
+            check_basis(U, S, g[f"U_{side}_{tag}"], g[f"S_{side}_{tag}"], g[f"U_{side}64_{tag}"], g[f"S_{side}64_{tag}"],
+                        f"eth {tag}/{side}")
+            assert rel_max(S64.cpu(), g[f"S_{side}64_{tag}"]) < 1e-10
+        assert pred_norm.shape == pred[m].shape and U_pred.shape == (24, 6)
+
+
+def test_synthetic_basis_both_methods(et):
+    g = load_golden("descriptor_syn")
+    for tag, sca in (("sca1", True), ("sca0", False)):
+        on, pn = t(g[f"obs_norm_{tag}"]), t(g[f"pred_norm_{tag}"])
+        for method in ("gram", "jacobi", "auto"):
+            d = et.ETDescriptor(et.DotDict(HP), norm_sca=sca).cuda()
+            d.svd_method = method
+            for side, x in (("obs", on), ("pred", pn)):
+                x64 = x.double().reshape(x.size(0), -1).T
+                U64, S64, _ = torch.linalg.svd(x64, full_matrices=False)
+                U, S, V = d.truncated_SVD(x.cuda())
+                assert U.shape == (x.size(1) * 2, 6) and S.shape == (6,) and V.shape == (x.size(0), 6)
+                check_basis(U, S, g[f"U_{side}_{tag}"], g[f"S_{side}_{tag}"], U64[:, :6], S64[:6], f"{tag}/{side}/{method}")
+                # V carries the matching sign: U diag(S) V^T is the rank-k approximation of M
+                approx = (U.cpu().double() * S.cpu().double()) @ V.cpu().double().T
+                ref = (U64[:, :6] * S64[:6]) @ (U64[:, :6].T @ x64)
+                assert rel_fro(approx, ref) < 2e-5, (tag, side, method)
+            # parameter_initialization end to end (fused normalise + Gram, or normalise + one-sided Jacobi)
+            pred_norm, U_pred = d.parameter_initialization(t(g["obs"]).cuda(), t(g["pred"]).cuda())
+            assert rel_max(pred_norm.cpu(), g[f"pred_norm_{tag}"]) < TOL
+            assert float((projector(U_pred.cpu()) - projector(g[f"U_pred_{tag}"])).norm()) < 2e-5
+
+
+def test_eth_test_descriptor_evaluation(et):
+    """Config 1: script/descriptor_evaluation.py:87-112 on the ETH test split, k = 1..12."""
+    g = load_golden("eth_test")
+    obs, pred = t(g["obs"]).cuda(), t(g["pred"]).cuda()
+    n = obs.size(0)
+    tn = et.TrajNorm(ori=True, rot=True, sca=False)
+    tn.calculate_params(obs)
+    on, pn = tn.normalize(obs), tn.normalize(pred)
+    hp = et.DotDict(dict(HP, k=12))
+    d = et.ETDescriptor(hp, norm_sca=False).cuda()
+    Uo, So, _ = d.truncated_SVD(on, k=12)
+    Up, Sp, _ = d.truncated_SVD(pn, k=12)
+    assert rel_max(Sp[:6].cpu(), [184.413, 26.252, 14.566, 7.138, 4.352, 2.989]) < 1e-5
+    assert rel_max(So[:12].cpu(), g["S_obs"][:12]) < 1e-5 and rel_max(Sp.cpu(), g["S_pred"][:12]) < 1e-5
+    for k in range(1, 13):
+        Co = d.to_ET_space(on, Uo[:, :k].contiguous())
+        Cp = d.to_ET_space(pn, Up[:, :k].contiguous())
+        ro = tn.denormalize(d.to_Euclidean_space(Co, Uo[:, :k].contiguous()))
+        rp = tn.denormalize(d.to_Euclidean_space(Cp, Up[:, :k].contiguous()))
+        eo = (ro - obs).norm(p=2, dim=-1).mean().item()
+        ep = (rp - pred).norm(p=2, dim=-1).mean().item()
+        assert abs(eo - g["err_obs"][k - 1]) <= 1e-5 * max(g["err_obs"][k - 1], 1e-2) + 2e-7, (k, eo)
+        assert abs(ep - g["err_pred"][k - 1]) <= 1e-5 * max(g["err_pred"][k - 1], 1e-2) + 2e-7, (k, ep)
+
+
+def test_batched_small_svd_per_scene(et):
+    """One launch, one block per scene (ragged offsets), vs torch fp64 SVD per scene."""
+    g = load_golden("eth_test")
+    obs = t(g["obs"]).cuda()
+    tn = et.TrajNorm(True, True, False)
+    tn.calculate_params(obs)
+    pn = tn.normalize(t(g["pred"]).cuda())
+    counts = torch.as_tensor(g["num_peds_in_seq"]).long()
+    offsets = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    U, S = et.ops.svd_small(pn, 2, offsets)
+    assert U.shape == (len(counts), 24, 2)
+    for b in range(len(counts)):
+        x = pn[offsets[b]:offsets[b + 1]].cpu().double().reshape(-1, 24).T
+        S64 = torch.linalg.svdvals(x)
+        assert rel_max(S[b, :1].cpu(), S64[:1]) < 1e-5, b
+        if x.size(1) >= 2:
+            assert abs(float(S[b, 1]) - float(S64[1])) <= 1e-5 * float(S64[0]), b
+
+
+def test_gram_linearity_and_sharding_property(et, O):
+    """G(all rows) == G(shard A) + G(shard B): what the multi-GPU all-reduce relies on (N = 1e6)."""
+    obs, pred = O.synthetic_trajectories(1_000_000, seed=0)
+    obs, pred = obs.cuda(), pred.cuda()
+    Go, Gp = et.ops.gram(obs, pred, True, True, True)
+    cut = 333_337
+    Ao, Ap = et.ops.gram(obs[:cut], pred[:cut], True, True, True)
+    et.ops.gram(obs[cut:], pred[cut:], True, True, True, G_obs=Ao, G_pred=Ap)
+    assert rel_max(Ao, Go) < 1e-12 and rel_max(Ap, Gp) < 1e-12
+    assert torch.equal(Go, Go.T) and torch.equal(Gp, Gp.T)
+    # against a float64 reference on a slice
+    ref = O.parameter_initialization(obs[:20000].cpu().double(), pred[:20000].cpu().double(), 6)
+    M = ref["pred_norm"].reshape(20000, 24)
+    Gs, Gps = et.ops.gram(obs[:20000], pred[:20000], True, True, True)
+    assert rel_max(Gps.cpu(), M.T @ M) < 1e-6     # inputs normalised in fp32 on the device, fp64 in the reference
+    # deterministic: two runs are bit identical
+    Go2, Gp2 = et.ops.gram(obs, pred, True, True, True)
+    assert torch.equal(Go, Go2) and torch.equal(Gp, Gp2)
+
+
+def test_gram_generic_shapes(et, O):
+    obs, pred = O.synthetic_trajectories(3001, seed=2, t_obs=5, t_pred=7)
+    st = O.norm_params(obs.double())
+    on, pn = O.normalize(obs.double(), *st).reshape(3001, -1), O.normalize(pred.double(), *st).reshape(3001, -1)
+    Go, Gp = et.ops.gram(obs.cuda(), pred.cuda(), True, True, True)
+    assert rel_max(Go.cpu(), on.T @ on) < 1e-5 and rel_max(Gp.cpu(), pn.T @ pn) < 1e-5
+
+
+# --------------------------------------------------------------------------------------
+# k-means
+# --------------------------------------------------------------------------------------
+def test_kmeans_lockstep_trace_bit_exact(et):
+    g = load_golden("kmeans")
+    data = t(g["data"]).cuda()
+    km = et.BatchKMeans(n_clusters=20)
+    np.random.seed(0)
+    c0 = km.initialize_centroids(data)
+    assert torch.equal(c0.cpu(), t(g["init_centroids"]))
+    for it in range(12):
+        cin = t(g["trace_centroids"][it]).cuda()               # lock-step: feed the reference's centroids
+        ms, lb = km.get_labels(data, cin)
+        assert lb.dtype == torch.int64
+        assert torch.equal(lb.cpu(), t(g["trace_labels"][it]).long()), it
+        assert torch.equal(ms.cpu(), t(g["trace_maxsims"][it])), it
+        cout = km.compute_centroids(data, lb)
+        assert rel_max(cout.cpu(), g["trace_centroids"][it + 1]) < TOL, it
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 1000])
+def test_kmeans_assign_edge_sizes_bit_exact(et, n):
+    g = load_golden("kmeans")
+    km = et.BatchKMeans(n_clusters=20)
+    ms, lb = km.get_labels(t(g[f"edge{n}_data"]).cuda(), t(g[f"edge{n}_cent"]).cuda())
+    assert torch.equal(lb.cpu(), t(g[f"edge{n}_labels"]))
+    assert torch.equal(ms.cpu(), t(g[f"edge{n}_maxsims"]))
+
+
+def test_kmeans_assign_large_vs_oracle_bit_exact(et, O):
+    """Config 3 shape: (1, 6, 1e6) scale-decay Gaussians, K = 20 -- every label and similarity identical."""
+    gen = torch.Generator().manual_seed(1234)
+    data = (torch.randn(1, 6, 1_000_000, generator=gen) * torch.tensor([20., 4., 1., .8, .3, .25])[None, :, None]).contiguous()
+    cent = data[:, :, torch.randperm(1_000_000, generator=gen)[:20]].contiguous()
+    km = et.BatchKMeans(n_clusters=20)
+    ms, lb = km.get_labels(data.cuda(), cent.cuda())
+    o_ms, o_lb = O.kmeans_assign(data, cent)
+    assert int((lb.cpu() != o_lb).sum()) == 0
+    assert torch.equal(ms.cpu(), o_ms)
+    # other (d, K) shapes of the torch reduction-order rule
+    for d, k, n in ((2, 5, 1000), (3, 7, 777), (6, 40, 5000), (8, 33, 4099), (16, 64, 3000), (5, 20, 6), (6, 4, 100)):
+        x = torch.randn(2, d, n, generator=gen).contiguous()
+        c = torch.randn(2, d, k, generator=gen).contiguous()
+        ms, lb = et.BatchKMeans(n_clusters=k).get_labels(x.cuda(), c.cuda())
+        o_ms, o_lb = O.kmeans_assign(x, c)
+        assert torch.equal(lb.cpu(), o_lb), (d, k, n)
+        assert torch.equal(ms.cpu(), o_ms), (d, k, n)
+
+
+def test_kmeans_fit_free_running(et):
+    g = load_golden("kmeans")
+    data = t(g["data"]).cuda()
+    km = et.BatchKMeans(n_clusters=20)
+    np.random.seed(0)
+    labels = km.fit(data)
+    assert labels.shape == (2, 4096) and km.centroids.shape == (2, 6, 20)
+    mismatch = int((labels.cpu() != t(g["fit_labels"]).long()).sum())
+    assert mismatch <= 8, mismatch                         # fp32-vs-fp64 centroid sums: a handful of near ties at most
+    assert rel_max(km.centroids.cpu(), g["fit_centroids"]) < 1e-3
+    # predict == get_labels with the fitted centroids
+    assert torch.equal(km.predict(data), km.get_labels(data, km.centroids)[1])
+    # explicit centroids + sync_every=1 reproduces the same fit
+    km2 = et.BatchKMeans(n_clusters=20)
+    km2.sync_every = 1
+    labels2 = km2.fit(data, centroids=t(g["init_centroids"]).cuda())
+    assert km2.n_iter_ == km.n_iter_ and int((labels2 != labels).sum()) <= 8
+    sd = km.state_dict()
+    km3 = et.BatchKMeans(n_clusters=20)
+    km3.load_state_dict(sd)
+    assert torch.equal(km3.centroids, km.centroids)
+
+
+def test_kmeans_update_matches_fp64_and_empty_cluster(et, O):
+    gen = torch.Generator().manual_seed(3)
+    data = torch.randn(1, 6, 100_000, generator=gen).contiguous()
+    cent = data[:, :, :20].contiguous()
+    _, lb = O.kmeans_assign(data, cent)
+    km = et.BatchKMeans(n_clusters=20)
+    c = km.compute_centroids(data.cuda(), lb.cuda())
+    ref64 = O.kmeans_update(data.double(), lb, 20)
+    ref32 = O.kmeans_update(data, lb, 20)
+    assert rel_max(c.cpu(), ref64) < 1e-6 and rel_max(c.cpu(), ref32) < TOL
+    lb2 = torch.zeros(1, 100_000, dtype=torch.long)
+    c2 = km.compute_centroids(data.cuda(), lb2.cuda())
+    assert torch.isnan(c2[0, :, 1:]).all() and not torch.isnan(c2[0, :, 0]).any()
+
+
+# --------------------------------------------------------------------------------------
+# metrics
+# --------------------------------------------------------------------------------------
+def test_ade_fde_golden(et):
+    g = load_golden("metrics")
+    pred, gt = t(g["pred"]).cuda(), t(g["gt"]).cuda()
+    ade = et.compute_batch_ade(pred, gt)
+    fde = et.compute_batch_fde(pred, gt[None])
+    assert isinstance(ade, np.ndarray) and ade.dtype == np.float32 and ade.shape == (300,)
+    assert np.abs(ade - g["ade"]).max() <= TOL * g["ade"].max()
+    assert np.abs(fde - g["fde"]).max() <= TOL * g["fde"].max()
+    both = et.compute_batch_ade_fde(pred, gt)
+    assert np.array_equal(both[0], ade) and np.array_equal(both[1], fde)
+
+
+@pytest.mark.parametrize("n,s,tlen", [(1, 20, 12), (31, 20, 12), (32, 20, 12), (33, 1, 12), (1000, 20, 12), (257, 5, 8),
+                                      (200_000, 20, 12)])
+def test_ade_fde_vs_oracle(et, O, n, s, tlen):
+    gen = torch.Generator().manual_seed(n + s)
+    gt = torch.randn(n, tlen, 2, generator=gen).cumsum(1)
+    pred = gt[None] + torch.randn(s, n, tlen, 2, generator=gen) * 0.4
+    ade, fde, arg = et.ops.ade_fde(pred.cuda(), gt.cuda(), want_argmin=True)
+    o_ade, o_fde, o_arg = O.ade_fde(pred, gt)
+    assert rel_max(ade.cpu(), o_ade) < TOL and rel_max(fde.cpu(), o_fde) < TOL
+    assert int((arg.cpu().long() != o_arg).sum()) == 0
+    # property: FDE <= distance of any one sample; ADE of identical prediction is 0
+    z_ade, z_fde = et.ops.ade_fde(gt[None].expand(s, -1, -1, -1).contiguous().cuda(), gt.cuda())
+    assert float(z_ade.abs().max()) == 0.0 and float(z_fde.abs().max()) == 0.0
+
+
+def test_ade_fde_nan_propagates(et):
+    gt = torch.zeros(40, 12, 2)
+    pred = torch.ones(20, 40, 12, 2)
+    pred[7, 5, 3, 0] = float("nan")
+    ade, fde = et.ops.ade_fde(pred.cuda(), gt.cuda())
+    assert torch.isnan(ade[5]) and not torch.isnan(fde[5]) and not torch.isnan(ade[4])
+
+
+# --------------------------------------------------------------------------------------
+# model wrapper through the plugin seam
+# --------------------------------------------------------------------------------------
+def test_model_forward_matches_reference(et):
+    import types
+    g = load_golden("model_forward")
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.W = torch.nn.Parameter(t(g["W"]).clone())
+
+        def forward(self, x):                     # x (8,N) -> (6,N,20)
+            return (self.W @ x).reshape(6, 20, -1).permute(0, 2, 1)
+
+    hook = types.SimpleNamespace(
+        model_forward_pre_hook=lambda C, o, info=None: torch.cat([C, o], dim=0),
+        model_forward=lambda x, m: m(x),
+        model_forward_post_hook=lambda y, info=None: y)
+    hp = et.DotDict(dict(HP))
+    model = et.EigenTrajectory(Stub(), hook, hp).cuda()
+    sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd_")}
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    assert sorted(k for k in model.state_dict() if k.startswith("ET_")) == sorted(sd)
+    obs, pred = t(g["obs"]).cuda(), t(g["pred"]).cuda()
+    out = model(obs, pred)
+    assert rel_max(out["recon_traj"].detach().cpu(), g["recon"]) < TOL
+    for key, ref in (("loss_eigentraj", "loss_eigentraj"), ("loss_euclidean_ade", "loss_ade"), ("loss_euclidean_fde", "loss_fde")):
+        assert abs(float(out[key]) - float(g[ref])) <= TOL * abs(float(g[ref])), key
+    (out["loss_eigentraj"] + out["loss_euclidean_ade"] + out["loss_euclidean_fde"]).backward()
+    assert rel_max(model.baseline_model.W.grad.cpu(), g["grad_W"]) < 2e-5
+    test_out = model(obs)
+    assert rel_max(test_out["recon_traj"].detach().cpu(), g["recon_test"]) < TOL and "loss_eigentraj" not in test_out
+    # calculate_parameters runs end to end on the device and yields orthonormal bases + finite anchors
+    model2 = et.EigenTrajectory(Stub(), hook, hp).cuda()
+    model2.calculate_parameters(t(g["init_obs"]).cuda(), t(g["init_pred"]).cuda())
+    for d, key in ((model2.ET_m_descriptor, "sd_ET_m_descriptor.U_pred_trunc"), (model2.ET_s_descriptor, "sd_ET_s_descriptor.U_pred_trunc")):
+        U = d.U_pred_trunc.detach().cpu().double()
+        assert (U.T @ U - torch.eye(6, dtype=torch.float64)).abs().max() < 1e-6
+        assert float((projector(U) - projector(g[key])).norm()) < 5e-5
+    assert torch.isfinite(model2.ET_m_anchor.C_anchor).all() and model2.ET_m_anchor.C_anchor.shape == (6, 20)
