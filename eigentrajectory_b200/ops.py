@@ -7,6 +7,8 @@ plumbing only.
 """
 from __future__ import annotations
 
+from ctypes import c_void_p as C_void_p
+
 import torch
 
 from . import _lib
@@ -203,6 +205,8 @@ def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, 
     Returns (rec_obs, rec_pred, C_obs|None, C_pred|None).  ``out`` may supply preallocated device
     tensors (rec_obs, rec_pred, C_obs, C_pred) to keep allocation out of a timed region.
     """
+    if not obs.is_cuda and out is None and obs.size(0) >= 2 * HOST_CHUNK:
+        return _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coeffs, variant)
     x = to_dev(obs)
     n, t_obs = _ntc(x)
     p = to_dev(pred).to(x.device)
@@ -219,6 +223,63 @@ def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, 
                                         ptr(rec_obs), ptr(rec_pred), ptr(C_obs), ptr(C_pred), variant,
                                         stream_of(x.device)), "et_project_reconstruct")
     return back_to(rec_obs, obs), back_to(rec_pred, obs), back_to(C_obs, obs), back_to(C_pred, obs)
+
+
+HOST_CHUNK = 65536          # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
+_side_streams = {}
+
+
+def _streams(device, count=3):
+    st = _side_streams.get(device)
+    if st is None:
+        st = [torch.cuda.Stream(device=device) for _ in range(count)]
+        _side_streams[device] = st
+    return st
+
+
+def _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coeffs, variant):
+    """Host-buffer path of the headline op: the batch is cut into chunks that flow H2D -> kernel -> D2H on three
+    streams, so PCIe traffic in both directions overlaps the kernels.  Inputs should be pinned for the copies to be
+    asynchronous; results are returned in freshly allocated pinned host tensors."""
+    dev = compute_device()
+    obs_h = obs.detach().float().contiguous()
+    pred_h = pred.detach().float().contiguous()
+    n, t_obs = _ntc(obs_h)
+    t_pred = pred_h.size(1)
+    cur = torch.cuda.current_stream(dev)
+    Uo, Up = to_dev(U_obs).to(dev), to_dev(U_pred).to(dev)
+    k = Uo.size(1)
+    rec_obs = torch.empty((n, t_obs, 2), pin_memory=True)
+    rec_pred = torch.empty((n, t_pred, 2), pin_memory=True)
+    C_obs = torch.empty((k, n), pin_memory=True) if want_coeffs else None
+    C_pred = torch.empty((k, n), pin_memory=True) if want_coeffs else None
+    flags = norm_flags(ori, rot, sca)
+    streams = _streams(dev)
+    lib = load()
+    for s in streams:
+        s.wait_stream(cur)          # U_* were produced on the caller's stream
+    n_chunks = (n + HOST_CHUNK - 1) // HOST_CHUNK
+    for ci in range(n_chunks):
+        a, b = ci * HOST_CHUNK, min(n, (ci + 1) * HOST_CHUNK)
+        m = b - a
+        st = streams[ci % len(streams)]
+        with torch.cuda.stream(st):
+            xo = obs_h[a:b].to(dev, non_blocking=True)
+            xp = pred_h[a:b].to(dev, non_blocking=True)
+            ro, rp = torch.empty_like(xo), torch.empty_like(xp)
+            co = torch.empty((k, m), device=dev) if want_coeffs else None
+            cp = torch.empty((k, m), device=dev) if want_coeffs else None
+            check(lib.et_project_reconstruct(ptr(xo), ptr(xp), m, t_obs, t_pred, ptr(Uo), ptr(Up), k, flags, ptr(ro), ptr(rp),
+                                             ptr(co), ptr(cp), variant, C_void_p(st.cuda_stream)), "et_project_reconstruct")
+            rec_obs[a:b].copy_(ro, non_blocking=True)
+            rec_pred[a:b].copy_(rp, non_blocking=True)
+            if want_coeffs:
+                for j in range(k):
+                    C_obs[j, a:b].copy_(co[j], non_blocking=True)
+                    C_pred[j, a:b].copy_(cp[j], non_blocking=True)
+    for s in streams:
+        s.synchronize()             # results live in host memory: they must be complete on return
+    return rec_obs, rec_pred, C_obs, C_pred
 
 
 # ----------------------------------------------------------------------------------------
