@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="et_project_reconstruct kernel variant (0 = auto)")
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="trajectories per GPU per step")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -223,13 +223,15 @@ def main():
 
     # ---- end to end through the public API with HOST buffers (H2D + kernel + D2H every step) ----
     e2e_times = []
-    for j in range(args.e2e_steps + 1):
+    ro = rp = co = cp = None
+    for j in range(args.e2e_steps + 3):          # 3 untimed calls: pinned output buffers enter torch's host cache
+        del ro, rp, co, cp
         barrier()
         t0 = time.perf_counter()
         ro, rp, co, cp = desc.project_reconstruct(host_obs, host_pred, variant=args.variant)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if j > 0:
+        if j >= 3:
             e2e_times.append(dt)
     e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
     if world > 1:

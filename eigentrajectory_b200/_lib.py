@@ -41,8 +41,9 @@ PROTOTYPES = {
     "et_kmeans_workspace_bytes": (_sz, [_i, _i, _i]),
     "et_kmeans_assign": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "et_kmeans_accumulate": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p]),
-    "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p]),
+    "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _p]),
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),
+    "et_kmeans_seed_step": (_i, [_p, _p, _i, _i, _l, _i, _i, _p, _p]),
     "et_ade_fde": (_i, [_p, _p, _i, _l, _i, _p, _p, _p, _p]),
 }
 

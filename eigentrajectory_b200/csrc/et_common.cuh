@@ -110,4 +110,41 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- grid-wide reduction of per-block partial records (cooperative launches only) --------------
+// One-shot, self-resetting barrier over all blocks of the grid.  ctr[0] = arrivals, ctr[1] = departures; both are
+// zero on entry and zero again on exit.  Needs every block co-resident: launch with launch_cooperative().
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&ctr[0], 1u);
+    while (*reinterpret_cast<volatile unsigned*>(&ctr[0]) < nblocks) __nanosleep(20);
+    __threadfence();
+    if (atomicAdd(&ctr[1], 1u) == nblocks - 1) {   // everybody has left the spin loop
+      ctr[0] = 0u;
+      ctr[1] = 0u;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+}
+
+// Sum element e over n_part partial records (stride rec doubles) with one warp: lanes stride over the
+// partials, fixed shuffle tree => the result depends only on (n_part, data), never on timing.
+__device__ __forceinline__ double warp_fold(const double* partials, int rec, int n_part, int e, int lane) {
+  double s = 0.0;
+  for (int p = lane; p < n_part; p += 32) s += __ldcg(partials + (size_t)p * rec + e);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// Cooperative launch wrapper (guarantees co-residency or fails loudly).
+template <typename... Args>
+inline cudaError_t launch_cooperative(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args... args) {
+  void* argv[] = {(void*)&args...};
+  return cudaLaunchCooperativeKernel((const void*)kernel, grid, block, argv, smem, stream);
+}
+
 }  // namespace et

@@ -526,63 +526,68 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
 // =======================================================================================
 // 6. ETDescriptor.reconstruction fused with ETAnchor.forward, (k, T, S) = (6, 12, 20).
 //    2428 algorithmic bytes per pedestrian, 79 % of them the (S,N,T,2) output.
-//    Each warp owns 32 pedestrians: six 1-D bulk loads bring its (k, 32*S) coefficient block
-//    into warp-private shared memory, each lane reconstructs its pedestrian sample by sample into
-//    a 32 x 96 B slab which one bulk store writes to out[s, n0:n0+32] (contiguous 3 KB).
-//    No block-wide barrier after set-up.
+//    A block of four warps owns a tile of 32 pedestrians: six 1-D bulk loads bring the tile's (k, 32*S)
+//    coefficient block into shared memory once; warp w reconstructs samples w, w+4, ... -- each lane one
+//    pedestrian -- into a warp-private 32 x 96 B slab which one bulk store writes to out[s, n0:n0+32]
+//    (contiguous 3 KB).  Two slabs per warp keep a store in flight while the next sample is computed.
+//    ~41 KB of shared memory per block => five blocks (20 warps) per SM.
 // =======================================================================================
-template <int K, int T, int S, int WARPS>
+constexpr int REC_WARPS = 4;
+
+template <int K, int T, int S>
 struct RecSmem {
   static constexpr int C_FLOATS = K * 32 * S;
   static constexpr int SLAB_FLOATS = 32 * 2 * T;
-  static constexpr int WARP_FLOATS = C_FLOATS + 2 * SLAB_FLOATS;
-  static constexpr size_t bytes = 128 + (size_t)WARPS * WARP_FLOATS * 4 + 2 * T * UPITCH * 4 + K * S * 4 + WARPS * 8;
+  static constexpr int U_FLOATS = 2 * T * UPITCH;
+  static constexpr int A_FLOATS = K * S;
+  static constexpr size_t bytes =
+      128 + (size_t)(C_FLOATS + REC_WARPS * 2 * SLAB_FLOATS + U_FLOATS + A_FLOATS) * 4 + (2 * REC_WARPS + 2) * 8;
 };
 
-template <int K, int T, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) reconstruct_fast(const float* __restrict__ C,
-                                                               const float* __restrict__ anchor, int64_t n,
-                                                               int64_t n_tiles, const float* __restrict__ U, int flags,
-                                                               const float* __restrict__ ori,
-                                                               const float* __restrict__ rot,
-                                                               const float* __restrict__ sca,
-                                                               float* __restrict__ out) {
-  using L = RecSmem<K, T, S, WARPS>;
+template <int K, int T, int S>
+__global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_fast(const float* __restrict__ C,
+                                                                   const float* __restrict__ anchor, int64_t n,
+                                                                   int64_t n_tiles, const float* __restrict__ U,
+                                                                   int flags, const float* __restrict__ ori,
+                                                                   const float* __restrict__ rot,
+                                                                   const float* __restrict__ sca,
+                                                                   float* __restrict__ out) {
+  using L = RecSmem<K, T, S>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float* wbuf = reinterpret_cast<float*>(base);
-  float* Us = wbuf + (size_t)WARPS * L::WARP_FLOATS;
-  float* As = Us + 2 * T * UPITCH;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(As + K * S);
+  float* Cs = reinterpret_cast<float*>(base);
+  float* slabs = Cs + L::C_FLOATS;
+  float* Us = slabs + REC_WARPS * 2 * L::SLAB_FLOATS;
+  float* As = Us + L::U_FLOATS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(As + L::A_FLOATS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  stage_basis<2 * T, K>(Us, U, threadIdx.x, WARPS * 32);
-  for (int e = threadIdx.x; e < K * S; e += WARPS * 32) As[e] = anchor ? __ldg(anchor + e) : 0.f;
-  if (threadIdx.x < WARPS) mbar_init(&bars[threadIdx.x], 1);
-  if (threadIdx.x == 0) fence_barrier_init();
+  stage_basis<2 * T, K>(Us, U, threadIdx.x, REC_WARPS * 32);
+  for (int e = threadIdx.x; e < K * S; e += REC_WARPS * 32) As[e] = anchor ? __ldg(anchor + e) : 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
 
-  float* Cs = wbuf + (size_t)warp * L::WARP_FLOATS;
-  float* slab = Cs + L::C_FLOATS;
-  uint64_t* bar = &bars[warp];
-  const int64_t wstride = (int64_t)gridDim.x * WARPS;
+  float* slab = slabs + warp * 2 * L::SLAB_FLOATS;
   uint32_t parity = 0;
   int slab_sel = 0;
-  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += wstride) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * 32;
     const int rows = (int)((n - n0) < 32 ? (n - n0) : 32);
-    if (lane == 0) {
-      mbar_arrive_expect_tx(bar, (uint32_t)(K * rows * S * 4));
+    if (threadIdx.x == 0) {
+      mbar_arrive_expect_tx(full, (uint32_t)(K * rows * S * 4));
 #pragma unroll
       for (int j = 0; j < K; ++j)
-        bulk_load(Cs + j * 32 * S, C + ((int64_t)j * n + n0) * S, (uint32_t)(rows * S * 4), bar);
+        bulk_load(Cs + j * 32 * S, C + ((int64_t)j * n + n0) * S, (uint32_t)(rows * S * 4), full);
     }
     const int64_t i = n0 + lane;
-    NormState st = load_norm_state(ori, rot, sca, i < n ? i : n - 1, flags);
+    const NormState st = load_norm_state(ori, rot, sca, i < n ? i : n - 1, flags);
     const float inv_sca = 1.0f / st.sca;
-    mbar_wait(bar, parity);
+    mbar_wait(full, parity);
     parity ^= 1u;
-    for (int s = 0; s < S; ++s) {
+    for (int s = warp; s < S; s += REC_WARPS) {
       float c[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) c[j] = As[j * S + s] + Cs[j * 32 * S + lane * S + s];
@@ -604,66 +609,70 @@ __global__ void __launch_bounds__(WARPS * 32) reconstruct_fast(const float* __re
       }
       slab_sel ^= 1;
     }
+    __syncthreads();   // every warp has finished reading Cs before the next tile's bulk load overwrites it
   }
   if (lane == 0) bulk_wait_all<0>();
 }
 
 // Gradient wrt C.  out[s,n,t,:] = (m_t / sca) R^T + ori with m = U c, so for an upstream gradient g:
-// d m_t = (g_t R) / sca and d c = U^T d m.  Mirror image of reconstruct_fast: bulk loads bring the
-// (32 x 96 B) gradient slabs, the warp-private (k, 32*S) block is bulk-stored once per tile.
-template <int K, int T, int S, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) reconstruct_bwd_fast(const float* __restrict__ grad_out, int64_t n,
-                                                                   int64_t n_tiles, const float* __restrict__ U,
-                                                                   int flags, const float* __restrict__ rot,
-                                                                   const float* __restrict__ sca,
-                                                                   float* __restrict__ grad_C) {
-  using L = RecSmem<K, T, S, WARPS>;
+// d m_t = (g_t R) / sca and d c = U^T d m.  Mirror image of reconstruct_fast: each warp bulk-loads the
+// (32 x 96 B) gradient slabs of its samples (double-buffered), the block assembles the (k, 32*S) tile in
+// shared memory and bulk-stores it once per k.
+template <int K, int T, int S>
+__global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_bwd_fast(const float* __restrict__ grad_out, int64_t n,
+                                                                       int64_t n_tiles, const float* __restrict__ U,
+                                                                       int flags, const float* __restrict__ rot,
+                                                                       const float* __restrict__ sca,
+                                                                       float* __restrict__ grad_C) {
+  using L = RecSmem<K, T, S>;
+  static_assert((S / REC_WARPS) * REC_WARPS == S, "samples must split evenly over the warps");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float* wbuf = reinterpret_cast<float*>(base);
-  float* Us = wbuf + (size_t)WARPS * L::WARP_FLOATS;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Us + 2 * T * UPITCH + K * S);   // two per warp
+  float* Cs = reinterpret_cast<float*>(base);
+  float* slabs = Cs + L::C_FLOATS;
+  float* Us = slabs + REC_WARPS * 2 * L::SLAB_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Us + L::U_FLOATS + L::A_FLOATS) + 2;   // two per warp
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  stage_basis<2 * T, K>(Us, U, threadIdx.x, WARPS * 32);
-  if (threadIdx.x < 2 * WARPS) mbar_init(&bars[threadIdx.x], 1);
+  stage_basis<2 * T, K>(Us, U, threadIdx.x, REC_WARPS * 32);
+  if (threadIdx.x < 2 * REC_WARPS) mbar_init(&bars[threadIdx.x], 1);
   if (threadIdx.x == 0) fence_barrier_init();
   __syncthreads();
 
-  float* Cs = wbuf + (size_t)warp * L::WARP_FLOATS;
-  float* slab = Cs + L::C_FLOATS;
+  float* slab = slabs + warp * 2 * L::SLAB_FLOATS;
   uint64_t* bar = &bars[2 * warp];
-  const int64_t wstride = (int64_t)gridDim.x * WARPS;
-  uint32_t cnt = 0;   // samples consumed so far; barrier b = cnt & 1 is on its (cnt >> 1)-th phase (S is even)
-  static_assert(S % 2 == 0, "two-slab ring assumes an even number of samples");
-  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += wstride) {
+  constexpr int PER_WARP = S / REC_WARPS;
+  uint32_t cnt = 0;   // slabs consumed so far by this warp: buffer b = cnt & 1 is on its (cnt >> 1)-th phase
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * 32;
     const int rows = (int)((n - n0) < 32 ? (n - n0) : 32);
     const uint32_t slab_bytes = (uint32_t)(rows * 2 * T * 4);
     const int64_t i = n0 + lane;
-    NormState st = load_norm_state(nullptr, rot, sca, i < n ? i : n - 1, flags & ~ET_NORM_ORI);
+    const NormState st = load_norm_state(nullptr, rot, sca, i < n ? i : n - 1, flags & ~ET_NORM_ORI);
     const float inv_sca = 1.0f / st.sca;
     if (lane == 0) {
-      bulk_wait_read<0>();   // previous tile's Cs stores have left shared memory
-      mbar_arrive_expect_tx(&bar[0], slab_bytes);
-      bulk_load(slab, grad_out + n0 * 2 * T, slab_bytes, &bar[0]);
+      const uint32_t b = cnt & 1u;
+      mbar_arrive_expect_tx(&bar[b], slab_bytes);
+      bulk_load(slab + b * L::SLAB_FLOATS, grad_out + ((int64_t)warp * n + n0) * 2 * T, slab_bytes, &bar[b]);
     }
-    __syncwarp();
-    for (int s = 0; s < S; ++s) {
-      const int b = s & 1;
-      if (lane == 0 && s + 1 < S) {
-        mbar_arrive_expect_tx(&bar[b ^ 1], slab_bytes);
-        bulk_load(slab + (b ^ 1) * L::SLAB_FLOATS, grad_out + ((int64_t)(s + 1) * n + n0) * 2 * T, slab_bytes,
-                  &bar[b ^ 1]);
+    if (threadIdx.x == 0) bulk_wait_read<0>();   // the previous tile's Cs stores have left shared memory
+    __syncthreads();
+    for (int q = 0; q < PER_WARP; ++q) {
+      const int s = warp + q * REC_WARPS;
+      const uint32_t b = cnt & 1u;
+      if (lane == 0 && q + 1 < PER_WARP) {
+        mbar_arrive_expect_tx(&bar[b ^ 1u], slab_bytes);
+        bulk_load(slab + (b ^ 1u) * L::SLAB_FLOATS, grad_out + ((int64_t)(s + REC_WARPS) * n + n0) * 2 * T, slab_bytes,
+                  &bar[b ^ 1u]);
       }
       mbar_wait(&bar[b], (cnt >> 1) & 1u);
       ++cnt;
       float g[2 * T];
       const float* sl = slab + b * L::SLAB_FLOATS + lane * 2 * T;
 #pragma unroll
-      for (int q = 0; q < 2 * T / 4; ++q) {
-        const float4 v = reinterpret_cast<const float4*>(sl)[q];
-        g[4 * q] = v.x; g[4 * q + 1] = v.y; g[4 * q + 2] = v.z; g[4 * q + 3] = v.w;
+      for (int v4 = 0; v4 < 2 * T / 4; ++v4) {
+        const float4 v = reinterpret_cast<const float4*>(sl)[v4];
+        g[4 * v4] = v.x; g[4 * v4 + 1] = v.y; g[4 * v4 + 2] = v.z; g[4 * v4 + 3] = v.w;
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -679,18 +688,18 @@ __global__ void __launch_bounds__(WARPS * 32) reconstruct_bwd_fast(const float* 
       project_row<2 * T, K>(g, Us, c);
 #pragma unroll
       for (int j = 0; j < K; ++j) Cs[j * 32 * S + lane * S + s] = c[j];
-      __syncwarp();   // all lanes finished reading slab b before it is refilled next iteration
+      __syncwarp();   // all lanes finished reading slab b before it is refilled
     }
     fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
 #pragma unroll
       for (int j = 0; j < K; ++j)
         bulk_store(grad_C + ((int64_t)j * n + n0) * S, Cs + j * 32 * S, (uint32_t)(rows * S * 4));
       bulk_commit();
     }
   }
-  if (lane == 0) bulk_wait_all<0>();
+  if (threadIdx.x == 0) bulk_wait_all<0>();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -854,7 +863,6 @@ int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t
   return launch_pr_tma<5, 2>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, st);
 }
 
-constexpr int REC_WARPS = 10;
 
 int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k, int t, const float* U, int flags,
                    const float* ori, const float* rot, const float* sca, float* out, et_stream_t stream) {
@@ -869,12 +877,14 @@ int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k,
   if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (k == 6 && t == 12 && s == 20 && n >= 32) {
-    using L = RecSmem<6, 12, 20, REC_WARPS>;
-    auto kern = reconstruct_fast<6, 12, 20, REC_WARPS>;
+    using L = RecSmem<6, 12, 20>;
+    auto kern = reconstruct_fast<6, 12, 20>;
     if ((rc = ensure_smem(kern, L::bytes, "reconstruct_fast"))) return rc;
     const int64_t n_tiles = (n + 31) / 32;
-    int64_t grid = (n_tiles + REC_WARPS - 1) / REC_WARPS;
-    if (grid > sm_count()) grid = sm_count();
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_WARPS * 32, L::bytes);
+    int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
+    if (grid > n_tiles) grid = n_tiles;
     kern<<<(unsigned)grid, REC_WARPS * 32, L::bytes, st>>>(C, anchor, n, n_tiles, U, flags, ori, rot, sca, out);
     return check_launch("reconstruct_fast");
   }
@@ -895,14 +905,15 @@ int et_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t, co
   if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (k == 6 && t == 12 && s == 20 && n >= 32) {
-    using L = RecSmem<6, 12, 20, REC_WARPS>;
-    auto kern = reconstruct_bwd_fast<6, 12, 20, REC_WARPS>;
-    const size_t bytes = L::bytes + REC_WARPS * 8;   // two barriers per warp
-    if ((rc = ensure_smem(kern, bytes, "reconstruct_bwd_fast"))) return rc;
+    using L = RecSmem<6, 12, 20>;
+    auto kern = reconstruct_bwd_fast<6, 12, 20>;
+    if ((rc = ensure_smem(kern, L::bytes, "reconstruct_bwd_fast"))) return rc;
     const int64_t n_tiles = (n + 31) / 32;
-    int64_t grid = (n_tiles + REC_WARPS - 1) / REC_WARPS;
-    if (grid > sm_count()) grid = sm_count();
-    kern<<<(unsigned)grid, REC_WARPS * 32, bytes, st>>>(grad_out, n, n_tiles, U, flags, rot, sca, grad_C);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_WARPS * 32, L::bytes);
+    int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, REC_WARPS * 32, L::bytes, st>>>(grad_out, n, n_tiles, U, flags, rot, sca, grad_C);
     return check_launch("reconstruct_bwd_fast");
   }
   reconstruct_bwd_generic<<<blocks_for(n * s, 128), 128, 2 * t * k * sizeof(float), st>>>(grad_out, n, s, k, 2 * t, U,

@@ -11,8 +11,8 @@
 //           sums ((acc0 + acc1) + acc2) + acc3 where acc0 also takes the remainder rows; a tensor of 4..7
 //           columns sums its first four columns sequentially            (torch 2.11 CPU, measured)
 //   label = arg-max, lowest index on ties, NaN wins (torch.max).
-// The update half accumulates, per warp, at most 32 points in fp32 shared-memory atomics and folds them
-// into float64 registers after every batch of 32, so centroid sums carry fp64 accuracy.
+// The update half accumulates without atomics in lane-private fp32 records (<= 64 points each) that are folded into
+// float64 in a fixed order, so centroid sums carry fp64 accuracy and are run-to-run reproducible.
 #include "et_common.cuh"
 
 namespace et {
@@ -68,35 +68,39 @@ __device__ __forceinline__ void best_centroid(const float (&a)[DMAX], int d, flo
   }
 }
 
-constexpr int KM_WARPS = 8;
+constexpr int KM_WARPS = 4;                 // warps per block of the seeding kernel and the default assign kernel
 constexpr int KM_THREADS = KM_WARPS * 32;
+constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates in fp32 before folding into fp64
 
-// workspace: l tickets (uint32, zero on entry / exit) padded to 128 B, then l * gridDim.x partial records of
-// (d*K + K + 1) doubles.
-template <int DMAX, int KMAX>
-__global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
+// workspace: two uint32 barrier counters (zero on entry / exit) padded to 128 B, then gridDim.x * gridDim.y partial
+// records of (d*K + K + 1) doubles.  Cooperative launch.
+//
+// Centroid accumulation without atomics: every lane owns a private fp32 record [cluster][d sums, count] in shared
+// memory, laid out [entry][lane] so that a warp's read-modify-write hits 32 different banks.  A lane adds at most
+// KM_FLUSH_EVERY points into its record before the warp folds the 32 lane records into float64 registers
+// (rotated, conflict-free column sums in a fixed order), so totals carry fp64 accuracy and are reproducible.
+template <int DMAX, int KMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
     int64_t* __restrict__ labels, float* __restrict__ maxsims, double* __restrict__ sums, double* __restrict__ counts,
-    double* __restrict__ simsum, unsigned* __restrict__ tickets, double* __restrict__ partials,
+    double* __restrict__ simsum, unsigned* __restrict__ barrier_ctr, double* __restrict__ partials,
     const int32_t* __restrict__ status, const int64_t* __restrict__ labels_in) {
-  if (status && status[0] != 0) return;   // converged on an earlier iteration: nothing to do
-  constexpr int REC = KMAX * (DMAX + 1);       // per-warp fp32 record: [cluster][d sums..., count]
-  constexpr int NQ = (REC + 31) / 32;
-  __shared__ float cs[DMAX * KMAX];
-  __shared__ float bn[KMAX];
-  __shared__ float wrec[KM_WARPS][REC];
-  __shared__ double blk[REC + 1];
-  __shared__ unsigned is_last;
+  if (status && status[0] != 0) return;   // converged on an earlier iteration: nothing to do (uniform over the grid)
+  constexpr int RECMAX = KMAX * (DMAX + 1);
+  constexpr int NQ = (RECMAX + 31) / 32;
+  extern __shared__ __align__(16) unsigned char km_smem[];
+  float* cs = reinterpret_cast<float*>(km_smem);            // [DMAX][KMAX]
+  float* bn = cs + DMAX * KMAX;                             // [KMAX]
+  double* blk = reinterpret_cast<double*>(bn + KMAX);       // [rec + 1]
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rec = k * (d + 1);
+  float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // [rec][32]
   const bool accumulate = sums != nullptr;
 
   if (centroids)
-    for (int e = tid; e < d * k; e += KM_THREADS) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
-  for (int e = tid; e < REC; e += KM_THREADS) {
-#pragma unroll
-    for (int w = 0; w < KM_WARPS; ++w) wrec[w][e] = 0.f;
-  }
+    for (int e = tid; e < d * k; e += (WARPS * 32)) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
+  if (accumulate)
+    for (int e = lane; e < rec * 32; e += 32) lanerec[e] = 0.f;
   __syncthreads();
   if (tid < k) {
     float v[DMAX];
@@ -111,11 +115,33 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
   double sim_acc = 0.0;
-  float* mine = wrec[warp];
 
-  const int64_t stride = (int64_t)gridDim.x * KM_THREADS;
+  // fold the 32 lane records into the fp64 registers: lane i owns entries i, i+32, ...; it walks the 32 lane
+  // columns of each of its entries starting at its own column (bank = column => conflict-free)
+  auto flush = [&]() {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int e = lane + 32 * q;
+      if (e < rec) {
+        float* row = lanerec + e * 32;
+        double s = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+          const int col = (c + lane) & 31;
+          s += (double)row[col];
+          row[col] = 0.f;
+        }
+        acc[q] += s;
+      }
+    }
+    __syncwarp();
+  };
+
+  const int64_t stride = (int64_t)gridDim.x * (WARPS * 32);
+  int since_flush = 0;
   // all lanes of a warp iterate together (the loop bound is warp-uniform)
-  for (int64_t base = (int64_t)blockIdx.x * KM_THREADS + warp * 32; base < n; base += stride) {
+  for (int64_t base = (int64_t)blockIdx.x * (WARPS * 32) + warp * 32; base < n; base += stride) {
     const int64_t i = base + lane;
     if (i < n) {
       float a[DMAX];
@@ -133,79 +159,70 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_assign_kernel(
       if (labels) labels[(int64_t)l * n + i] = label;
       if (maxsims) maxsims[(int64_t)l * n + i] = best;
       if (accumulate && label >= 0) {
-        float* slot = mine + label * (d + 1);
+        float* slot = lanerec + (label * (d + 1)) * 32 + lane;
 #pragma unroll
         for (int r = 0; r < DMAX; ++r)
-          if (r < d) atomicAdd(slot + r, a[r]);
-        atomicAdd(slot + d, 1.0f);
+          if (r < d) slot[r * 32] += a[r];
+        slot[d * 32] += 1.0f;
         sim_acc += (double)best;
       }
     }
-    if (accumulate) {
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e = lane + 32 * q;
-        if (e < rec) {
-          acc[q] += (double)mine[e];
-          mine[e] = 0.f;
-        }
-      }
-      __syncwarp();
+    if (accumulate && ++since_flush == KM_FLUSH_EVERY) {
+      flush();
+      since_flush = 0;
     }
   }
   if (!accumulate) return;
+  flush();
 
   // ---- block reduction in fixed warp order ----
-  for (int e = tid; e <= REC; e += KM_THREADS) blk[e] = 0.0;
+  for (int e = tid; e <= rec; e += (WARPS * 32)) blk[e] = 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sim_acc += __shfl_xor_sync(0xffffffffu, sim_acc, o);
   __syncthreads();
-  for (int w = 0; w < KM_WARPS; ++w) {
+  for (int w = 0; w < WARPS; ++w) {
     if (warp == w) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         const int e = lane + 32 * q;
         if (e < rec) blk[e] += acc[q];
       }
-      if (lane == 0) blk[REC] += sim_acc;
+      if (lane == 0) blk[rec] += sim_acc;
     }
     __syncthreads();
   }
   const int out_rec = rec + 1;
+  const unsigned nblocks = gridDim.x * gridDim.y;
   double* part = partials + ((size_t)l * gridDim.x + blockIdx.x) * out_rec;
-  for (int e = tid; e < out_rec; e += KM_THREADS) part[e] = (e < rec) ? blk[e] : blk[REC];
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = (atomicAdd(&tickets[l], 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  // ---- the last block of this batch entry folds the partial records in block order ----
-  for (int e = tid; e < out_rec; e += KM_THREADS) {
-    double s0 = 0.0, s1 = 0.0;
-    unsigned b = 0;
-    for (; b + 2 <= gridDim.x; b += 2) {
-      s0 += __ldcg(partials + ((size_t)l * gridDim.x + b) * out_rec + e);
-      s1 += __ldcg(partials + ((size_t)l * gridDim.x + b + 1) * out_rec + e);
-    }
-    if (b < gridDim.x) s0 += __ldcg(partials + ((size_t)l * gridDim.x + b) * out_rec + e);
-    const double tot = s0 + s1;
-    if (e < rec) {
-      const int c = e / (d + 1), r = e % (d + 1);
-      if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
-      else counts[(int64_t)l * k + c] += tot;
-    } else if (simsum) {
-      simsum[l] += tot;
+  for (int e = tid; e < out_rec; e += (WARPS * 32)) part[e] = blk[e];
+  // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
+  grid_barrier(barrier_ctr, nblocks);
+  const double* lpart = partials + (size_t)l * gridDim.x * out_rec;
+  for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
+    const double tot = warp_fold(lpart, out_rec, (int)gridDim.x, e, lane);
+    if (lane == 0) {
+      if (e < rec) {
+        const int c = e / (d + 1), r = e % (d + 1);
+        if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
+        else counts[(int64_t)l * k + c] += tot;
+      } else if (simsum) {
+        simsum[l] += tot;
+      }
     }
   }
-  if (tid == 0) tickets[l] = 0u;
+}
+
+template <int DMAX, int KMAX>
+static size_t km_smem_bytes(int d, int k, int warps, bool accumulate) {
+  return (size_t)(DMAX * KMAX + KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
+         (accumulate ? (size_t)warps * k * (d + 1) * 32 * sizeof(float) : 0);
 }
 
 // new = float(sums / counts); err = sum (old - new)^2; clears the accumulators for the next iteration.
 __global__ void kmeans_finalize_kernel(double* __restrict__ sums, double* __restrict__ counts, int l, int d, int k,
                                        const float* __restrict__ old_c, float* __restrict__ new_c,
-                                       double* __restrict__ err, double tol, int32_t* __restrict__ status) {
+                                       double* __restrict__ err, double tol, int32_t* __restrict__ status,
+                                       double* __restrict__ simsum, double* __restrict__ simsum_last) {
   if (status && status[0] != 0) return;
   __shared__ double red[256];
   const int total = l * d * k;
@@ -229,6 +246,11 @@ __global__ void kmeans_finalize_kernel(double* __restrict__ sums, double* __rest
   // every thread has read what it needs from sums / counts before anyone clears them
   for (int e = threadIdx.x; e < total; e += blockDim.x) sums[e] = 0.0;
   for (int e = threadIdx.x; e < l * k; e += blockDim.x) counts[e] = 0.0;
+  if (simsum)
+    for (int e = threadIdx.x; e < l; e += blockDim.x) {
+      if (simsum_last) simsum_last[e] = simsum[e];   // sum of best similarities of the iteration just finished
+      simsum[e] = 0.0;
+    }
   if (threadIdx.x == 0) {
     if (err) err[0] = red[0];
     if (status) {
@@ -256,7 +278,9 @@ __global__ void kmeans_seed_init_kernel(unsigned long long* scratch, int l, int 
 template <int DMAX, int KMAX>
 __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const float* __restrict__ data, int d, int64_t n,
                                                                       int k, int ncols,
-                                                                      unsigned long long* __restrict__ scratch) {
+                                                                      unsigned long long* __restrict__ scratch,
+                                                                      const float* __restrict__ cent_in,
+                                                                      unsigned long long* __restrict__ key_out) {
   __shared__ float cs[DMAX * KMAX];
   __shared__ float bn[KMAX];
   __shared__ unsigned long long wmin[KM_WARPS];
@@ -264,8 +288,12 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
   const float* dl = data + (int64_t)l * d * n;
   for (int e = tid; e < d * ncols; e += KM_THREADS) {
     const int r = e / ncols, j = e % ncols;
-    const int64_t idx = (int64_t)(scratch[(int64_t)l * k + j] & 0xffffffffull);
-    cs[r * KMAX + j] = __ldg(dl + (int64_t)r * n + idx);
+    if (cent_in) {   // explicit centroids (l,d,K): the row-sharded path, where chosen points may live on another rank
+      cs[r * KMAX + j] = __ldg(cent_in + ((int64_t)l * d + r) * k + j);
+    } else {
+      const int64_t idx = (int64_t)(scratch[(int64_t)l * k + j] & 0xffffffffull);
+      cs[r * KMAX + j] = __ldg(dl + (int64_t)r * n + idx);
+    }
   }
   __syncthreads();
   if (tid < ncols) {
@@ -296,8 +324,13 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < KM_WARPS; ++w) key = wmin[w] < key ? wmin[w] : key;
-    atomicMin(&scratch[(int64_t)l * k + ncols], key);
+    atomicMin(key_out ? &key_out[l] : &scratch[(int64_t)l * k + ncols], key);
   }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, int count, unsigned long long v) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < count) p[e] = v;
 }
 
 __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l, int d, int64_t n, int k,
@@ -307,6 +340,52 @@ __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l,
   const int j = e % k, r = (e / k) % d, li = e / (d * k);
   const int64_t idx = (int64_t)(scratch[(int64_t)li * k + j] & 0xffffffffull);
   centroids[e] = __ldg(data + ((int64_t)li * d + r) * n + idx);
+}
+
+// Launch the assign kernel (cooperatively when it accumulates: the fold needs a grid barrier).
+template <int DMAX, int KMAX, int WARPS>
+static int km_launch_w(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
+                     float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
+                     const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS>;
+  constexpr int KM_THREADS_L = WARPS * 32;
+  const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, sums != nullptr);
+  if (smem > 200 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KM_THREADS_L, smem);
+  if (e != cudaSuccess || per_sm < 1) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: occupancy query failed");
+  if (per_sm > 4) per_sm = 4;
+  int64_t cap = (int64_t)sm_count() * per_sm / l;     // all l * grid.x blocks must be co-resident
+  if (cap < 1) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d exceeds the co-resident block budget", l);
+  int64_t gx = (n + KM_THREADS_L - 1) / KM_THREADS_L;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)l);
+  unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
+  double* parts = workspace ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128) : nullptr;
+  if (sums) {
+    e = launch_cooperative(kern, grid, dim3(KM_THREADS_L), smem, st, data, centroids, d, n, k, labels, maxsims, sums, counts,
+                           simsum, ctr, parts, status, labels_in);
+    if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cooperative launch: %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, KM_THREADS_L, smem, st>>>(data, centroids, d, n, k, labels, maxsims, sums, counts, simsum, ctr, parts, status,
+                                         labels_in);
+  }
+  return check_launch("kmeans_assign_kernel");
+}
+
+template <int DMAX, int KMAX>
+static int km_launch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
+                     float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
+                     const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+  // four warps per block while their lane-private records fit ~100 KB, otherwise one warp per block
+  if (km_smem_bytes<DMAX, KMAX>(d, k, KM_WARPS, sums != nullptr) <= 100 * 1024)
+    return km_launch_w<DMAX, KMAX, KM_WARPS>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
+                                             status, labels_in, st);
+  return km_launch_w<DMAX, KMAX, 1>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
+                                    labels_in, st);
 }
 
 static int km_grid(int64_t n) {
@@ -331,8 +410,8 @@ extern "C" {
 
 size_t et_kmeans_workspace_bytes(int l, int d, int k_clusters) {
   if (l < 1 || d < 1 || k_clusters < 1) return 0;
-  const size_t tickets = (((size_t)l * 4 + 127) / 128) * 128;
-  return tickets + (size_t)l * sm_count() * 4 * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
+  // 128 B of barrier counters + one partial record per co-resident block (at most 4 per SM in total)
+  return 128 + (size_t)sm_count() * 4 * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
 }
 
 int et_kmeans_assign(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
@@ -343,18 +422,12 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
   ET_REQUIRE((data && centroids) || n == 0, ET_ERR_BADARG, "et_kmeans_assign: data / centroids null");
   ET_REQUIRE(!sums || (counts && workspace), ET_ERR_BADARG, "et_kmeans_assign: sums given without counts / workspace");
   if (n == 0) return ET_OK;
-  const size_t tickets = (((size_t)l * 4 + 127) / 128) * 128;
-  unsigned* tk = reinterpret_cast<unsigned*>(workspace);
-  double* parts = workspace ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + tickets) : nullptr;
-  dim3 grid(km_grid(n), l);
   cudaStream_t st = as_stream(stream);
   if (d <= 8 && k_clusters <= 32)
-    kmeans_assign_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, centroids, d, n, k_clusters, labels, maxsims, sums,
-                                                           counts, simsum, tk, parts, status, nullptr);
-  else
-    kmeans_assign_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(
-        data, centroids, d, n, k_clusters, labels, maxsims, sums, counts, simsum, tk, parts, status, nullptr);
-  return check_launch("kmeans_assign_kernel");
+    return km_launch<8, 32>(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status,
+                            nullptr, st);
+  return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS>(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts,
+                                                   simsum, workspace, status, nullptr, st);
 }
 
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n, int k_clusters,
@@ -364,27 +437,22 @@ int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d,
   ET_REQUIRE((data && labels) || n == 0, ET_ERR_BADARG, "et_kmeans_accumulate: data / labels null");
   ET_REQUIRE(sums && counts && workspace, ET_ERR_BADARG, "et_kmeans_accumulate: sums / counts / workspace null");
   if (n == 0) return ET_OK;
-  const size_t tickets = (((size_t)l * 4 + 127) / 128) * 128;
-  unsigned* tk = reinterpret_cast<unsigned*>(workspace);
-  double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + tickets);
-  dim3 grid(km_grid(n), l);
   cudaStream_t st = as_stream(stream);
   if (d <= 8 && k_clusters <= 32)
-    kmeans_assign_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, nullptr, d, n, k_clusters, nullptr, nullptr, sums,
-                                                           counts, nullptr, tk, parts, nullptr, labels);
-  else
-    kmeans_assign_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(
-        data, nullptr, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, tk, parts, nullptr, labels);
-  return check_launch("kmeans_assign_kernel(accumulate)");
+    return km_launch<8, 32>(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr,
+                            labels, st);
+  return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS>(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr,
+                                                   workspace, nullptr, labels, st);
 }
 
 int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_clusters, const float* old_centroids,
-                       float* new_centroids, double* err, double tol, int32_t* status, et_stream_t stream) {
+                       float* new_centroids, double* err, double tol, int32_t* status, double* simsum,
+                       double* simsum_last, et_stream_t stream) {
   int rc = km_check(l, d, 0, k_clusters);
   if (rc) return rc;
   ET_REQUIRE(sums && counts && new_centroids, ET_ERR_BADARG, "et_kmeans_finalize: null pointer");
   kmeans_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, counts, l, d, k_clusters, old_centroids, new_centroids,
-                                                          err, tol, status);
+                                                          err, tol, status, simsum, simsum_last);
   return check_launch("kmeans_finalize_kernel");
 }
 
@@ -401,13 +469,33 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   dim3 grid(km_grid(n), l);
   for (int i = 1; i < k_clusters; ++i) {
     if (d <= 8 && k_clusters <= 32)
-      kmeans_seed_step_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch);
+      kmeans_seed_step_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch, nullptr, nullptr);
     else
-      kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch);
+      kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch,
+                                                                                          nullptr, nullptr);
     if ((rc = check_launch("kmeans_seed_step_kernel"))) return rc;
   }
   kmeans_seed_gather_kernel<<<(l * d * k_clusters + 255) / 256, 256, 0, st>>>(data, l, d, n, k_clusters, scratch, centroids);
   return check_launch("kmeans_seed_gather_kernel");
+}
+
+int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
+                        unsigned long long* key_out, et_stream_t stream) {
+  int rc = km_check(l, d, n, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(data && centroids && key_out, ET_ERR_BADARG, "et_kmeans_seed_step: null pointer");
+  ET_REQUIRE(ncols >= 1 && ncols < k_clusters, ET_ERR_BADARG, "et_kmeans_seed_step: ncols = %d outside [1, K)", ncols);
+  cudaStream_t st = as_stream(stream);
+  fill_u64_kernel<<<(l + 255) / 256, 256, 0, st>>>(key_out, l, ~0ull);
+  if ((rc = check_launch("fill_u64_kernel"))) return rc;
+  if (n == 0) return ET_OK;
+  dim3 grid(km_grid(n), l);
+  if (d <= 8 && k_clusters <= 32)
+    kmeans_seed_step_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, ncols, nullptr, centroids, key_out);
+  else
+    kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, ncols, nullptr,
+                                                                                        centroids, key_out);
+  return check_launch("kmeans_seed_step_kernel");
 }
 
 }  // extern "C"

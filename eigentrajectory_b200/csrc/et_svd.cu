@@ -26,15 +26,14 @@ constexpr int GR_PITCH = 40;                 // floats per staged pedestrian: 16
 constexpr int GR_NBLK_O = 3, GR_NBLK_P = 6;  // upper-triangular 8x8 blocks of the 16x16 / 24x24 Gram matrices
 constexpr int GR_GO = 16 * 16, GR_GP = 24 * 24;
 
-// workspace layout: [0] uint32 ticket (zero on entry, restored to zero on exit), then at byte 128
-// gridDim.x partial matrices of GR_GO + GR_GP doubles.
+// workspace layout: two uint32 barrier counters (zero on entry, zero again on exit), then at byte 128
+// gridDim.x partial matrices of GR_GO + GR_GP doubles.  Cooperative launch (grid barrier before the fold).
 __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restrict__ obs, const float* __restrict__ pred,
                                                            int64_t n, int flags, double* __restrict__ G_obs,
                                                            double* __restrict__ G_pred, unsigned* __restrict__ ticket,
                                                            double* __restrict__ partials) {
   __shared__ __align__(16) float xs[GR_WARPS][32 * GR_PITCH];
   __shared__ double acc_s[GR_GO + GR_GP];
-  __shared__ unsigned is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   float* xw = xs[warp];
@@ -137,29 +136,16 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
   __syncthreads();
   double* mine = partials + (size_t)blockIdx.x * (GR_GO + GR_GP);
   for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) mine[e] = acc_s[e];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!is_last) return;
-  // ---- the last block to finish folds all partials in block order and adds them to G ----
-  __threadfence();
-  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) {
-    if (e >= GR_GO && !pred) break;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    unsigned b = 0;
-    for (; b + 4 <= gridDim.x; b += 4) {
-      s0 += __ldcg(partials + (size_t)(b + 0) * (GR_GO + GR_GP) + e);
-      s1 += __ldcg(partials + (size_t)(b + 1) * (GR_GO + GR_GP) + e);
-      s2 += __ldcg(partials + (size_t)(b + 2) * (GR_GO + GR_GP) + e);
-      s3 += __ldcg(partials + (size_t)(b + 3) * (GR_GO + GR_GP) + e);
+  // ---- grid fold: after the barrier every warp of the grid sums a few elements over all block partials ----
+  grid_barrier(ticket, gridDim.x);
+  const int n_el = pred ? GR_GO + GR_GP : GR_GO;
+  for (int e = blockIdx.x * GR_WARPS + warp; e < n_el; e += gridDim.x * GR_WARPS) {
+    const double tot = warp_fold(partials, GR_GO + GR_GP, (int)gridDim.x, e, lane);
+    if (lane == 0) {
+      if (e < GR_GO) G_obs[e] += tot;
+      else G_pred[e - GR_GO] += tot;
     }
-    for (; b < gridDim.x; ++b) s0 += __ldcg(partials + (size_t)b * (GR_GO + GR_GP) + e);
-    const double tot = (s0 + s1) + (s2 + s3);
-    if (e < GR_GO) G_obs[e] += tot;
-    else G_pred[e - GR_GO] += tot;
   }
-  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // Any (T_obs, T_pred): block-wide fp64 accumulation over chunks of 64 staged pedestrians; simple and slow,
@@ -214,12 +200,19 @@ __global__ void __launch_bounds__(GG_THREADS) gram_generic(const float* __restri
 //    Per-pair threshold |g_pq| <= eps * sqrt(g_pp g_qq) (high relative accuracy on PSD matrices;
 //    exact-zero rows/columns -- the normalised last observed frame -- never rotate).
 // =======================================================================================
-constexpr int EIG_THREADS = 256;
+constexpr int EIG_MAX_THREADS = 256;
 constexpr int EIG_MAX_SWEEPS = 60;
 
-__global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
-                                                                 float* __restrict__ U, float* __restrict__ S,
-                                                                 double* __restrict__ U64, double* __restrict__ S64) {
+// The solve is latency-bound (a 24 x 24 matrix has 288 work items per phase), so the block is sized to the problem:
+// one warp up to m = 24 (phases separated by __syncwarp), more warps only for larger matrices.
+__device__ __forceinline__ void eig_sync() {
+  if (blockDim.x <= 32) __syncwarp();
+  else __syncthreads();
+}
+
+__global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
+                                                                     float* __restrict__ U, float* __restrict__ S,
+                                                                     double* __restrict__ U64, double* __restrict__ S64) {
   extern __shared__ double sm[];
   const int mp = (m + 1) & ~1;   // even size; a padding index never rotates
   double* A = sm;                // mp x mp (row-major, pitch mp)
@@ -228,23 +221,23 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* _
   int* pr = reinterpret_cast<int*>(cs + mp);   // pairs p[mp/2], q[mp/2]
   int* order = pr + mp;                         // mp
   __shared__ int n_rot;
-  const int tid = threadIdx.x, half = mp / 2;
+  const int tid = threadIdx.x, nthr = blockDim.x, half = mp / 2;
 
-  for (int e = tid; e < mp * mp; e += EIG_THREADS) {
+  for (int e = tid; e < mp * mp; e += nthr) {
     const int r = e / mp, c = e % mp;
     A[e] = (r < m && c < m) ? 0.5 * (G[r * m + c] + G[c * m + r]) : 0.0;
     V[e] = (r == c) ? 1.0 : 0.0;
   }
-  __syncthreads();
+  eig_sync();
 
   for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
     if (tid == 0) n_rot = 0;
-    __syncthreads();
+    eig_sync();
     for (int step = 0; step < mp - 1; ++step) {
       // round-robin tournament: position 0 fixed, the others rotate
-      if (tid < half) {
+      for (int pi = tid; pi < half; pi += nthr) {
         auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (mp - 1); };
-        int p = player(tid), q = player(mp - 1 - tid);
+        int p = player(pi), q = player(mp - 1 - pi);
         if (p > q) { const int t = p; p = q; q = t; }
         const double app = A[p * mp + p], aqq = A[q * mp + q], apq = A[p * mp + q];
         double c = 1.0, s = 0.0;
@@ -255,11 +248,11 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* _
           s = t * c;
           atomicAdd(&n_rot, 1);
         }
-        cs[tid] = c; cs[half + tid] = s; pr[tid] = p; pr[half + tid] = q;
+        cs[pi] = c; cs[half + pi] = s; pr[pi] = p; pr[half + pi] = q;
       }
-      __syncthreads();
+      eig_sync();
       // columns: A <- A J, V <- V J
-      for (int e = tid; e < half * mp; e += EIG_THREADS) {
+      for (int e = tid; e < half * mp; e += nthr) {
         const int pi = e / mp, r = e % mp;
         const double c = cs[pi], s = cs[half + pi];
         if (s != 0.0) {
@@ -272,28 +265,22 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* _
           V[r * mp + q] = s * vp + c * vq;
         }
       }
-      __syncthreads();
-      // rows: A <- J^T A
-      for (int e = tid; e < half * mp; e += EIG_THREADS) {
+      eig_sync();
+      // rows: A <- J^T A; the rotated off-diagonal pair is zero by construction and is stored as exactly zero
+      for (int e = tid; e < half * mp; e += nthr) {
         const int pi = e / mp, col = e % mp;
         const double c = cs[pi], s = cs[half + pi];
         if (s != 0.0) {
           const int p = pr[pi], q = pr[half + pi];
           const double ap = A[p * mp + col], aq = A[q * mp + col];
-          A[p * mp + col] = c * ap - s * aq;
-          A[q * mp + col] = s * ap + c * aq;
+          A[p * mp + col] = (col == q) ? 0.0 : c * ap - s * aq;
+          A[q * mp + col] = (col == p) ? 0.0 : s * ap + c * aq;
         }
       }
-      __syncthreads();
-      if (tid < half && cs[half + tid] != 0.0) {
-        const int p = pr[tid], q = pr[half + tid];
-        A[p * mp + q] = 0.0;
-        A[q * mp + p] = 0.0;
-      }
-      __syncthreads();
+      eig_sync();
     }
     if (n_rot == 0) break;
-    __syncthreads();
+    eig_sync();
   }
 
   // order eigenvalues descending (ties: lower index first) -- m <= 64, one thread
@@ -306,9 +293,9 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* _
       const int t = order[i]; order[i] = order[best]; order[best] = t;
     }
   }
-  __syncthreads();
-  if (tid < k) {
-    const int col = order[tid];
+  eig_sync();
+  for (int j = tid; j < k; j += nthr) {
+    const int col = order[j];
     const double lam = A[col * mp + col];
     const double sv = sqrt(lam > 0.0 ? lam : 0.0);
     // canonical sign: the largest-magnitude component (first one on ties) is positive
@@ -321,11 +308,11 @@ __global__ void __launch_bounds__(EIG_THREADS) eig_jacobi_kernel(const double* _
     const double sign = V[arg * mp + col] < 0.0 ? -1.0 : 1.0;
     for (int r = 0; r < m; ++r) {
       const double v = sign * V[r * mp + col];
-      U[r * k + tid] = (float)v;
-      if (U64) U64[r * k + tid] = v;
+      U[r * k + j] = (float)v;
+      if (U64) U64[r * k + j] = v;
     }
-    S[tid] = (float)sv;
-    if (S64) S64[tid] = sv;
+    S[j] = (float)sv;
+    if (S64) S64[j] = sv;
   }
 }
 
@@ -470,8 +457,10 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     int grid = gram_grid();
     const int64_t need = ((n + 31) / 32 + GR_WARPS - 1) / GR_WARPS;
     if (grid > need) grid = (int)need;
-    gram_fast<<<grid, GR_WARPS * 32, 0, st>>>(obs, pred, n, flags, G_obs, G_pred, reinterpret_cast<unsigned*>(workspace),
-                                             reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128));
+    cudaError_t ce = launch_cooperative(gram_fast, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred,
+                                        reinterpret_cast<unsigned*>(workspace),
+                                        reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128));
+    if (ce != cudaSuccess) return fail(ET_ERR_CUDA, "gram_fast: cooperative launch: %s", cudaGetErrorString(ce));
     return check_launch("gram_fast");
   }
   const int to2 = 2 * t_obs, tp2 = pred ? 2 * t_pred : 0;
@@ -491,7 +480,10 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   const size_t smem = (size_t)(2 * mp * mp + mp) * sizeof(double) + (size_t)2 * mp * sizeof(int);
   cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(ET_ERR_CUDA, "eig_jacobi_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  eig_jacobi_kernel<<<1, EIG_THREADS, smem, as_stream(stream)>>>(G, m, k, U, S, U64, S64);
+  int threads = ((mp / 2) * mp / 9 + 31) / 32 * 32;     // ~9 work items per thread and phase
+  if (threads < 32) threads = 32;
+  if (threads > EIG_MAX_THREADS) threads = EIG_MAX_THREADS;
+  eig_jacobi_kernel<<<1, threads, smem, as_stream(stream)>>>(G, m, k, U, S, U64, S64);
   return check_launch("eig_jacobi_kernel");
 }
 

@@ -127,7 +127,7 @@ class BatchKMeans(nn.Module):
         x, lead = _as_ldn(data)
         l, d, n = x.shape
         lab = labels.reshape(l, n).to(device=x.device, dtype=torch.int64).contiguous()
-        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device, 1)
+        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device)
         ops.kmeans_accumulate(x, lab, acc)
         cent = torch.empty((l, d, self.n_clusters), device=x.device)
         ops.kmeans_finalize(acc, None, cent)
@@ -142,17 +142,14 @@ class BatchKMeans(nn.Module):
         """Run Lloyd iterations from ``centroids`` on the device.  Returns (labels, centroids, n_iter, error, inertia)."""
         l, d, n = x.shape
         bufs = [centroids.contiguous().clone(), torch.empty_like(centroids)]
-        acc.status.zero_()
-        acc.sums.zero_()
-        acc.counts.zero_()
-        acc.simsum.zero_()
+        acc.reset()
         done = 0
         n_iter = 0
         while done < self.max_iter:
             chunk = min(self.sync_every, self.max_iter - done)
             for j in range(done, done + chunk):
                 cur, nxt = bufs[j % 2], bufs[(j + 1) % 2]
-                ops.kmeans_assign(x, cur, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum[j],
+                ops.kmeans_assign(x, cur, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum,
                                   status=acc.status)
                 ops.kmeans_finalize(acc, cur, nxt, tol=self.tol, use_status=True)
             done += chunk
@@ -164,7 +161,7 @@ class BatchKMeans(nn.Module):
         final = bufs[n_iter % 2]
         before = bufs[(n_iter - 1) % 2]
         _, labels = ops.kmeans_assign(x, before, want_labels=True, want_maxsims=False)
-        inertia = -(acc.simsum[n_iter - 1] / n).mean()
+        inertia = -(acc.simsum_last / n).mean()
         return labels, final.clone(), n_iter, acc.err.clone(), inertia
 
     def fit(self, data, centroids=None):
@@ -180,7 +177,7 @@ class BatchKMeans(nn.Module):
         assert data.is_contiguous(), "use .contiguous()"
         x, lead = _as_ldn(data)
         l, d, n = x.shape
-        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device, self.max_iter)
+        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device)
 
         best_centroids = best_labels = None
         best_inertia = 1e32

@@ -225,7 +225,7 @@ def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, 
     return back_to(rec_obs, obs), back_to(rec_pred, obs), back_to(C_obs, obs), back_to(C_pred, obs)
 
 
-HOST_CHUNK = 65536          # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
+HOST_CHUNK = 131072         # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
 _side_streams = {}
 
 
@@ -367,17 +367,27 @@ def svd_small(traj_norm, k, offsets=None):
 # k-means (EigenTrajectory/kmeans.py)
 # ----------------------------------------------------------------------------------------
 class KMeansWorkspace:
-    """Device buffers one BatchKMeans.fit needs; allocated once per (l, d, K, device)."""
+    """Device buffers one BatchKMeans.fit needs; allocated once per (l, d, K, device).
 
-    def __init__(self, l, d, k, device, max_iter):
+    ``flat`` = [sums (l,d,K) | counts (l,K) | simsum (l)] is ONE contiguous fp64 buffer so that a
+    row-sharded caller all-reduces it in place with a single collective."""
+
+    def __init__(self, l, d, k, device, max_iter=0):
         nbytes = int(load().et_kmeans_workspace_bytes(l, d, k))
         self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-        self.sums = torch.zeros((l, d, k), dtype=torch.float64, device=device)
-        self.counts = torch.zeros((l, k), dtype=torch.float64, device=device)
-        self.simsum = torch.zeros((max(max_iter, 1), l), dtype=torch.float64, device=device)
+        ns, nc = l * d * k, l * k
+        self.flat = torch.zeros((ns + nc + l,), dtype=torch.float64, device=device)
+        self.sums = self.flat[:ns].view(l, d, k)
+        self.counts = self.flat[ns:ns + nc].view(l, k)
+        self.simsum = self.flat[ns + nc:]
+        self.simsum_last = torch.zeros((l,), dtype=torch.float64, device=device)
         self.err = torch.zeros((1,), dtype=torch.float64, device=device)
         self.status = torch.zeros((2,), dtype=torch.int32, device=device)
-        self.scratch = torch.zeros((l * k,), dtype=torch.int64, device=device)
+
+    def reset(self):
+        self.flat.zero_()
+        self.simsum_last.zero_()
+        self.status.zero_()
 
 
 def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None, simsum=None, status=None):
@@ -406,7 +416,8 @@ def kmeans_finalize(acc, old_centroids, new_centroids, tol=0.0, use_status=False
     l, d, k = acc.sums.shape
     check(load().et_kmeans_finalize(ptr(acc.sums), ptr(acc.counts), l, d, k, ptr(old_centroids), ptr(new_centroids),
                                     ptr(acc.err), float(tol), ptr(acc.status) if use_status else None,
-                                    stream_of(new_centroids.device)), "et_kmeans_finalize")
+                                    ptr(acc.simsum), ptr(acc.simsum_last), stream_of(new_centroids.device)),
+          "et_kmeans_finalize")
 
 
 def kmeans_farthest_init(data, k, first_index, scratch=None):
@@ -417,6 +428,20 @@ def kmeans_farthest_init(data, k, first_index, scratch=None):
     check(load().et_kmeans_farthest_init(ptr(data), l, d, n, k, int(first_index), ptr(cent), ptr(scratch),
                                          stream_of(data.device)), "et_kmeans_farthest_init")
     return cent
+
+
+def kmeans_seed_step(data, centroids, ncols):
+    """Local farthest-point candidate of a row shard: returns (best similarity (l,) fp32, local index (l,) int64)."""
+    l, d, n = data.shape
+    k = centroids.size(-1)
+    key = torch.empty((l,), dtype=torch.int64, device=data.device)
+    check(load().et_kmeans_seed_step(ptr(data), ptr(centroids), l, d, n, k, int(ncols), ptr(key), stream_of(data.device)),
+          "et_kmeans_seed_step")
+    idx = key & 0xFFFFFFFF
+    bits = (key >> 32) & 0xFFFFFFFF
+    # undo the order-preserving map: keys with the top bit set were non-negative floats
+    raw = torch.where(bits >= 0x80000000, bits - 0x80000000, 0xFFFFFFFF - bits)
+    return raw.to(torch.uint32).view(torch.float32), idx
 
 
 # ----------------------------------------------------------------------------------------

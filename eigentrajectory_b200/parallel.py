@@ -1,0 +1,166 @@
+"""Row-sharded (one process per GPU) versions of the two stages that need an exchange.
+
+Trajectories are partitioned into contiguous row blocks, one per rank.  Projection, reconstruction
+and ADE/FDE need no communication at all.  The eigen-basis needs ONE all-reduce (the fp64 Gram
+accumulators, 832 doubles); k-means needs one all-reduce of ``l * (d*K + K + 1)`` doubles per Lloyd
+iteration plus, for the reference's farthest-point seeding, one (value, index) exchange and one
+broadcast per step.  All of them are a few KB: latency-bound, enqueued on the compute stream through
+``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU unit tests).
+
+The numerical work is injected through a small ``backend`` object so that the host-side logic
+(partitioning, packing, collectives, tie-breaking) is unit-testable without a GPU; the default
+backend is the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous, balanced row block [start, end) of rank ``rank`` out of ``world``."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class CudaBackend:
+    """Default compute backend: libet_b200.so through ``ops``."""
+
+    def gram(self, obs, pred, ori, rot, sca):
+        return ops.gram(obs, pred, ori, rot, sca)
+
+    def eig(self, G, k):
+        return ops.eig_basis(G, k)
+
+    def new_workspace(self, l, d, k, device):
+        return ops.KMeansWorkspace(l, d, k, device)
+
+    def assign_accumulate(self, data, cent, acc):
+        ops.kmeans_assign(data, cent, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum, status=acc.status)
+
+    def finalize(self, acc, old, new, tol):
+        ops.kmeans_finalize(acc, old, new, tol=tol, use_status=True)
+
+    def labels(self, data, cent):
+        return ops.kmeans_assign(data, cent, want_labels=True, want_maxsims=False)[1]
+
+    def seed_step(self, data, cent, ncols):
+        return ops.kmeans_seed_step(data, cent, ncols)
+
+
+def _all_reduce(t, group):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def sharded_basis(obs_shard, pred_shard, k, ori=True, rot=True, sca=True, group=None, backend=None):
+    """Eigen-bases of the row-sharded init set: local fused Gram pass, ONE all-reduce, replicated eigen-solve.
+
+    Every rank returns the same (U_obs (2T_obs,k), S_obs, U_pred (2T_pred,k), S_pred): the Jacobi solve is
+    deterministic, so no broadcast is needed."""
+    backend = backend or CudaBackend()
+    G_obs, G_pred = backend.gram(obs_shard, pred_shard, ori, rot, sca)
+    no, np_ = G_obs.numel(), G_pred.numel()
+    packed = torch.cat([G_obs.reshape(-1), G_pred.reshape(-1)])        # one buffer => one collective
+    _all_reduce(packed, group)
+    G_obs = packed[:no].reshape(G_obs.shape).contiguous()
+    G_pred = packed[no:no + np_].reshape(G_pred.shape).contiguous()
+    U_obs, S_obs = backend.eig(G_obs, k)
+    U_pred, S_pred = backend.eig(G_pred, k)
+    return U_obs, S_obs, U_pred, S_pred
+
+
+def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset, group=None, backend=None):
+    """The reference's farthest-point seeding (kmeans.py:78-112) over row shards.
+
+    ``data_shard`` (l,d,n_local) holds global columns [row_offset, row_offset + n_local).  Per step: local
+    candidate (lowest best-similarity, lowest index on ties) -> all-gather of (value, global index) -> the
+    global winner (lowest value, then lowest global index) -> its coordinates summed in from the owner."""
+    backend = backend or CudaBackend()
+    rank, world = _world(group)
+    l, d, n_local = data_shard.shape
+    dev = data_shard.device
+    cent = torch.zeros((l, d, n_clusters), device=dev, dtype=data_shard.dtype)
+
+    def fetch(global_idx):
+        """(l,d) coordinates of global column ``global_idx`` (l,) from whichever rank owns each."""
+        local = global_idx - row_offset
+        mine = (local >= 0) & (local < n_local)
+        safe = local.clamp(0, max(n_local - 1, 0))
+        pts = data_shard[torch.arange(l, device=dev), :, safe] if n_local > 0 else torch.zeros((l, d), device=dev)
+        pts = torch.where(mine[:, None], pts, torch.zeros_like(pts)).double()
+        _all_reduce(pts, group)                     # exactly one rank contributes a non-zero row
+        return pts.to(data_shard.dtype)
+
+    first = torch.full((l,), int(first_global_index), dtype=torch.int64, device=dev)
+    cent[:, :, 0] = fetch(first)
+    big = torch.iinfo(torch.int64).max
+    for i in range(1, n_clusters):
+        if n_local > 0:
+            val, idx = backend.seed_step(data_shard, cent, i)
+            gidx = idx + row_offset
+        else:
+            val = torch.full((l,), float("inf"), device=dev)
+            gidx = torch.full((l,), big, dtype=torch.int64, device=dev)
+        if world > 1:
+            vals = [torch.empty_like(val) for _ in range(world)]
+            idxs = [torch.empty_like(gidx) for _ in range(world)]
+            dist.all_gather(vals, val, group=group)
+            dist.all_gather(idxs, gidx, group=group)
+            vals, idxs = torch.stack(vals), torch.stack(idxs)            # (world, l)
+            best = vals.min(dim=0, keepdim=True)[0]
+            cand = torch.where(vals == best, idxs, torch.full_like(idxs, big))
+            gidx = cand.min(dim=0)[0]
+        cent[:, :, i] = fetch(gidx)
+    return cent
+
+
+def sharded_kmeans_fit(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, sync_every=8, group=None,
+                       backend=None):
+    """Lloyd iterations (kmeans.py:200-259, n_redo = 1) over row shards: per iteration one fused
+    assign+accumulate pass on local rows and ONE all-reduce of the packed (sums, counts, sum of similarities).
+
+    Returns (labels of the local rows (l,n_local) int64, centroids (l,d,K) -- identical on all ranks --,
+    iterations executed, inertia)."""
+    backend = backend or CudaBackend()
+    l, d, n_local = data_shard.shape
+    dev = data_shard.device
+    acc = backend.new_workspace(l, d, n_clusters, dev)
+    bufs = [centroids.contiguous().clone(), torch.empty_like(centroids)]
+    acc.reset()
+    done = n_iter = 0
+    while done < max_iter:
+        chunk = min(sync_every, max_iter - done)
+        for j in range(done, done + chunk):
+            cur, nxt = bufs[j % 2], bufs[(j + 1) % 2]
+            backend.assign_accumulate(data_shard, cur, acc)
+            _all_reduce(acc.flat, group)            # sums | counts | sum of similarities: one in-place collective
+            backend.finalize(acc, cur, nxt, tol)
+        done += chunk
+        converged, n_iter = (int(v) for v in acc.status.tolist())
+        if converged:
+            break
+    final, before = bufs[n_iter % 2], bufs[(n_iter - 1) % 2]
+    labels = backend.labels(data_shard, before) if n_local > 0 else torch.zeros((l, 0), dtype=torch.int64, device=dev)
+    inertia = float(-(acc.simsum_last / n_total).mean())
+    return labels, final.clone(), n_iter, inertia
+
+
+def sharded_mean(values, group=None):
+    """Mean of a per-pedestrian metric over all ranks: one 2-scalar all-reduce (sum, count)."""
+    v = torch.as_tensor(values)
+    pair = torch.tensor([float(v.double().sum()), float(v.numel())], dtype=torch.float64,
+                        device=v.device if v.is_cuda else "cpu")
+    _all_reduce(pair, group)
+    return float(pair[0] / pair[1])

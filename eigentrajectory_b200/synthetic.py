@@ -1,7 +1,7 @@
 """Seeded synthetic pedestrian tracks for benchmarks and examples.
 
 Generated on the CPU with a ``torch.Generator`` so that a CPU baseline and the GPU see identical
-bits.  (The oracle keeps its own copy of this recipe; tests check that the two agree.)
+bits.  (The test-side checker keeps its own copy of this recipe; tests check that the two agree.)
 """
 import math
 

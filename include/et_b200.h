@@ -161,13 +161,14 @@ int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d,
 /* Division half of compute_centroids + calculate_error (kmeans.py:45-51,183):
  * new_centroids = float(sums / counts) (0/0 -> NaN as in the reference);
  * err[0] = sum((old - new)^2) in float64 when err and old_centroids are given; sums / counts
- * are cleared for the next iteration.  With status (device int32[2]): a no-op when
- * status[0] != 0, otherwise status[1] += 1 and status[0] = (err <= tol) -- the reference's
- * `if error <= self.tol: break` (kmeans.py:239) evaluated on the device, so that a host can
- * enqueue several Lloyd iterations without synchronising. */
+ * are cleared for the next iteration, and so is simsum (l) after being copied to simsum_last (l)
+ * (both optional).  With status (device int32[2]): a no-op when status[0] != 0, otherwise
+ * status[1] += 1 and status[0] = (err <= tol) -- the reference's `if error <= self.tol: break`
+ * (kmeans.py:239) evaluated on the device, so that a host can enqueue several Lloyd iterations
+ * without synchronising. */
 int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_clusters,
                        const float* old_centroids, float* new_centroids, double* err, double tol,
-                       int32_t* status, et_stream_t stream);
+                       int32_t* status, double* simsum, double* simsum_last, et_stream_t stream);
 /* BatchKMeans.kmeanspp (kmeans.py:78-112): deterministic farthest-point seeding.
  * centroids (l,d,K) out; column 0 = data[..., first_index]; every later column is the point
  * whose best similarity to the columns chosen so far is lowest (lowest index on ties),
@@ -175,6 +176,13 @@ int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_cluster
 int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_clusters,
                             int64_t first_index, float* centroids, unsigned long long* scratch,
                             et_stream_t stream);
+
+/* One farthest-point step on a ROW SHARD (kmeans.py:95-98 evaluated on local rows): with the first
+ * ncols columns of centroids (l,d,K) given, key_out[l] = min over local points of
+ * (order-preserving bits of the point's best similarity) << 32 | local index.  A multi-GPU caller
+ * takes the minimum over ranks of (value, global index) and broadcasts the winner's coordinates. */
+int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d, int64_t n,
+                        int k_clusters, int ncols, unsigned long long* key_out, et_stream_t stream);
 
 /* ---- metrics: utils/metrics.py ---------------------------------------------------------- */
 /* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass.

@@ -151,11 +151,11 @@ def main():
     km = et.BatchKMeans(n_clusters=20)
     np.random.seed(0)
     cent = km.initialize_centroids(data)
-    acc = ops.KMeansWorkspace(1, 6, 20, dev, 100)
+    acc = ops.KMeansWorkspace(1, 6, 20, dev)
     nxt = torch.empty_like(cent)
 
     def km_iter():
-        ops.kmeans_assign(data, cent, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum[0])
+        ops.kmeans_assign(data, cent, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum)
         ops.kmeans_finalize(acc, cent, nxt)
     a, m = time_op(km_iter)
     add("kmeans assign+update iteration (HBM-cold)", n, 24, a, m, "point", "2 launches", launches=2)

@@ -1,0 +1,79 @@
+"""GPU: the row-sharded paths with the CUDA backend, world_size = 2.  With two or more GPUs the ranks use NCCL on
+separate devices; on a single-GPU box both ranks share cuda:0 and the collectives go through gloo (CUDA tensors),
+which still exercises every kernel and the whole sharded control flow."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, use_nccl, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank if use_nccl else 0)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
+    try:
+        import eigentrajectory_b200 as et
+        from eigentrajectory_b200 import ops, parallel as P
+        from oracle import et_oracle as O
+        n = 200_003
+        obs, pred = O.synthetic_trajectories(n, seed=3)
+        a, b = P.shard_bounds(n, rank, world)
+        res = {}
+        Uo, So, Up, Sp = P.sharded_basis(obs[a:b].to(dev), pred[a:b].to(dev), 6)
+        G_o, G_p = ops.gram(obs.to(dev), pred.to(dev), True, True, True)          # unsharded, same device code
+        U1, S1 = ops.eig_basis(G_p, 6)
+        res["S_err"] = float((Sp - S1).abs().max() / S1.max())
+        res["P_err"] = float((Up.double() @ Up.double().T - U1.double() @ U1.double().T).norm())
+        res["U_pred"] = Up.cpu()
+        # k-means on the pred coefficients of this data, sharded vs single device
+        C = ops.to_et_space(ops.normalize(pred.to(dev), *ops.norm_params(obs.to(dev))), Up).unsqueeze(0).contiguous()
+        first = 4242
+        cent0 = P.sharded_farthest_init(C[:, :, a:b].contiguous(), 20, first, a)
+        ref0 = ops.kmeans_farthest_init(C, 20, first)
+        res["init_equal"] = bool(torch.equal(cent0, ref0))
+        labels, cent, n_iter, inertia = P.sharded_kmeans_fit(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25)
+        km = et.BatchKMeans(n_clusters=20, max_iter=25)
+        ref_labels = km.fit(C, centroids=ref0)
+        res["label_mismatch"] = int((labels != ref_labels[:, a:b]).sum())
+        res["cent_err"] = float((cent - km.centroids).abs().max() / km.centroids.abs().max())
+        res["iters"] = (n_iter, km.n_iter_)
+        res["cent"] = cent.cpu()
+        # sharded metric mean
+        rec = ops.reconstruct(torch.zeros(6, b - a, 20, device=dev), Up, ops.norm_params(obs[a:b].to(dev)))
+        ade, fde = ops.ade_fde(rec, pred[a:b].to(dev))
+        res["ade_mean"] = P.sharded_mean(ade)
+        if rank == 0:
+            rec_all = ops.reconstruct(torch.zeros(6, n, 20, device=dev), Up, ops.norm_params(obs.to(dev)))
+            res["ade_mean_ref"] = float(ops.ade_fde(rec_all, pred.to(dev))[0].double().mean())
+        out[rank] = res
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_basis_kmeans_metrics_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    use_nccl = torch.cuda.device_count() >= 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
+    r0, r1 = out[0], out[1]
+    for r in (r0, r1):
+        assert r["S_err"] < 1e-6 and r["P_err"] < 1e-6
+        assert r["init_equal"]
+        assert r["label_mismatch"] <= 4 and r["cent_err"] < 1e-4
+        assert r["iters"][0] == r["iters"][1]
+    assert torch.equal(r0["U_pred"], r1["U_pred"]) and torch.equal(r0["cent"], r1["cent"])
+    assert abs(r0["ade_mean"] - r1["ade_mean"]) < 1e-12
+    assert abs(r0["ade_mean"] - r0["ade_mean_ref"]) < 1e-6 * abs(r0["ade_mean_ref"])
