@@ -396,8 +396,6 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
   uint64_t* done = full + NS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  stage_basis<16, 6>(Uo, U_obs, threadIdx.x, PR_THREADS);
-  stage_basis<24, 6>(Up, U_pred, threadIdx.x, PR_THREADS);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -406,7 +404,12 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
     }
     fence_barrier_init();
   }
-  __syncthreads();
+  __syncthreads();   // barriers are live: the producer starts loading while the consumers stage the bases
+  if (warp < PR_CONSUMER_WARPS) {
+    stage_basis<16, 6>(Uo, U_obs, threadIdx.x, PR_CONSUMER_WARPS * 32);
+    stage_basis<24, 6>(Up, U_pred, threadIdx.x, PR_CONSUMER_WARPS * 32);
+    asm volatile("bar.sync 1, %0;" ::"n"(PR_CONSUMER_WARPS * 32) : "memory");   // consumers only
+  }
 
   const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 

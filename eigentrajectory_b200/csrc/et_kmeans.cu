@@ -52,20 +52,54 @@ __device__ __forceinline__ float sumsq_torch_order(const float (&v)[DMAX], int d
   return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
 }
 
-// best similarity / label of one point against ncols staged centroids (cs: [d][kpitch], bn: [ncols])
-template <int DMAX>
+// best similarity / label of one point against the staged centroids (cs: [d][kpitch], bn: [kpad]).
+// Four centroids are evaluated at a time (four independent FMA chains, one broadcast LDS.128 per data row); each
+// similarity is still the reference's exact op sequence and the arg-max scan stays in ascending j.  Columns
+// ncols..kpad-1 are padding (centroid 0, |b|^2 = +inf => similarity -inf, never selected).
+// EXACT: d == DMAX is known at compile time (no per-row guards).  NANAWARE: torch.max semantics when a similarity
+// can be NaN (a NaN centroid from an empty cluster, or non-finite data); the common finite case skips those tests.
+template <int DMAX, bool EXACT, bool NANAWARE>
 __device__ __forceinline__ void best_centroid(const float (&a)[DMAX], int d, float anorm, const float* cs, int kpitch,
-                                              const float* bn, int ncols, float& best, int& label) {
-  best = 0.f;
+                                              const float* bn, int ncols, int kpad, float& best, int& label) {
+  best = NANAWARE ? 0.f : -INFINITY;
   label = 0;
-  for (int j = 0; j < ncols; ++j) {
-    float dot = 0.f;
+  bool first = true;
+  for (int j0 = 0; j0 < kpad; j0 += 4) {
+    float dot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < DMAX; ++i)
-      if (i < d) dot = fmaf(a[i], cs[i * kpitch + j], dot);
-    const float y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.0f), anorm), bn[j]);
-    if (j == 0 || y > best || (y != y && best == best)) { best = y; label = j; }
+    for (int i = 0; i < DMAX; ++i) {
+      if (EXACT || i < d) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + i * kpitch + j0);
+        dot[0] = fmaf(a[i], c4.x, dot[0]);
+        dot[1] = fmaf(a[i], c4.y, dot[1]);
+        dot[2] = fmaf(a[i], c4.z, dot[2]);
+        dot[3] = fmaf(a[i], c4.w, dot[3]);
+      }
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(bn + j0);
+    const float bnv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float y = __fsub_rn(__fsub_rn(__fmul_rn(dot[u], 2.0f), anorm), bnv[u]);
+      if (NANAWARE) {
+        if (j0 + u < ncols && (first || y > best || (y != y && best == best))) { best = y; label = j0 + u; }
+        first = false;
+      } else {
+        if (y > best) { best = y; label = j0 + u; }
+      }
+    }
   }
+}
+
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ void best_centroid_any(const float (&a)[DMAX], int d, float anorm, const float* cs, int kpitch,
+                                                  const float* bn, int ncols, int kpad, bool nan_possible, float& best,
+                                                  int& label) {
+  // anorm is finite iff every coordinate is (squares are non-negative): one test covers the point
+  if (nan_possible || !(fabsf(anorm) <= 3.0e38f))
+    best_centroid<DMAX, EXACT, true>(a, d, anorm, cs, kpitch, bn, ncols, kpad, best, label);
+  else
+    best_centroid<DMAX, EXACT, false>(a, d, anorm, cs, kpitch, bn, ncols, kpad, best, label);
 }
 
 constexpr int KM_WARPS = 4;                 // warps per block of the seeding kernel and the default assign kernel
@@ -79,7 +113,7 @@ constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates 
 // memory, laid out [entry][lane] so that a warp's read-modify-write hits 32 different banks.  A lane adds at most
 // KM_FLUSH_EVERY points into its record before the warp folds the 32 lane records into float64 registers
 // (rotated, conflict-free column sums in a fixed order), so totals carry fp64 accuracy and are reproducible.
-template <int DMAX, int KMAX, int WARPS>
+template <int DMAX, int KMAX, int WARPS, bool EXACT>
 __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
     int64_t* __restrict__ labels, float* __restrict__ maxsims, double* __restrict__ sums, double* __restrict__ counts,
@@ -97,18 +131,30 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
   float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // [rec][32]
   const bool accumulate = sums != nullptr;
 
+  for (int e = tid; e < DMAX * KMAX + KMAX; e += (WARPS * 32)) cs[e] = 0.f;   // cs and bn (contiguous), padding included
+  __syncthreads();
   if (centroids)
     for (int e = tid; e < d * k; e += (WARPS * 32)) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
   if (accumulate)
     for (int e = lane; e < rec * 32; e += 32) lanerec[e] = 0.f;
   __syncthreads();
-  if (tid < k) {
-    float v[DMAX];
+  __shared__ int nan_centroid;
+  if (tid == 0) nan_centroid = 0;
+  __syncthreads();
+  const int kpad = (k + 3) & ~3;
+  if (tid < kpad) {
+    float bnorm = INFINITY;           // padding columns: similarity -inf
+    if (tid < k) {
+      float v[DMAX];
 #pragma unroll
-    for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
-    bn[tid] = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, k));
+      for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
+      bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, k));
+      if (!(bnorm <= 3.0e38f)) nan_centroid = 1;      // NaN or inf centroid: take the torch.max-exact path
+    }
+    bn[tid] = bnorm;
   }
   __syncthreads();
+  const bool nan_possible = nan_centroid != 0;
 
   const float* dl = data + (int64_t)l * d * n;
   double acc[NQ];
@@ -141,12 +187,23 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
   const int64_t stride = (int64_t)gridDim.x * (WARPS * 32);
   int since_flush = 0;
   // all lanes of a warp iterate together (the loop bound is warp-uniform)
+  float a_next[DMAX];
+  {
+    const int64_t i0 = (int64_t)blockIdx.x * (WARPS * 32) + warp * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
+  }
   for (int64_t base = (int64_t)blockIdx.x * (WARPS * 32) + warp * 32; base < n; base += stride) {
     const int64_t i = base + lane;
-    if (i < n) {
-      float a[DMAX];
+    float a[DMAX];
 #pragma unroll
-      for (int r = 0; r < DMAX; ++r) a[r] = (r < d) ? __ldg(dl + (int64_t)r * n + i) : 0.f;
+    for (int r = 0; r < DMAX; ++r) a[r] = a_next[r];
+    {   // software prefetch of the next point: its loads are in flight while this one is scored
+      const int64_t in = i + stride;
+#pragma unroll
+      for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
+    }
+    if (i < n) {
       float best = 0.f;
       int label;
       if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
@@ -154,7 +211,7 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
         label = (li >= 0 && li < k) ? (int)li : -1;
       } else {
         const float anorm = sumsq_torch_order<DMAX>(a, d, col_is_sequential(i, n));
-        best_centroid<DMAX>(a, d, anorm, cs, KMAX, bn, k, best, label);
+        best_centroid_any<DMAX, EXACT>(a, d, anorm, cs, KMAX, bn, k, kpad, nan_possible, best, label);
       }
       if (labels) labels[(int64_t)l * n + i] = label;
       if (maxsims) maxsims[(int64_t)l * n + i] = best;
@@ -162,7 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
         float* slot = lanerec + (label * (d + 1)) * 32 + lane;
 #pragma unroll
         for (int r = 0; r < DMAX; ++r)
-          if (r < d) slot[r * 32] += a[r];
+          if (EXACT || r < d) slot[r * 32] += a[r];
         slot[d * 32] += 1.0f;
         sim_acc += (double)best;
       }
@@ -275,15 +332,18 @@ __global__ void kmeans_seed_init_kernel(unsigned long long* scratch, int l, int 
 // Step `ncols` (1 <= ncols < K): the chosen points scratch[l*K + 0 .. ncols) are the current centroids; every
 // point takes its best similarity against them exactly as the reference recomputes it, and the point with the
 // lowest best similarity (lowest index on ties) is recorded in scratch[l*K + ncols].
-template <int DMAX, int KMAX>
+template <int DMAX, int KMAX, bool EXACT>
 __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const float* __restrict__ data, int d, int64_t n,
                                                                       int k, int ncols,
                                                                       unsigned long long* __restrict__ scratch,
                                                                       const float* __restrict__ cent_in,
                                                                       unsigned long long* __restrict__ key_out) {
-  __shared__ float cs[DMAX * KMAX];
-  __shared__ float bn[KMAX];
+  __shared__ __align__(16) float cs[DMAX * KMAX];
+  __shared__ __align__(16) float bn[KMAX];
   __shared__ unsigned long long wmin[KM_WARPS];
+  for (int e = threadIdx.x; e < DMAX * KMAX; e += KM_THREADS) cs[e] = 0.f;
+  if (threadIdx.x < KMAX) bn[threadIdx.x] = 0.f;
+  __syncthreads();
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* dl = data + (int64_t)l * d * n;
   for (int e = tid; e < d * ncols; e += KM_THREADS) {
@@ -296,22 +356,39 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
     }
   }
   __syncthreads();
-  if (tid < ncols) {
-    float v[DMAX];
+  const int kpad = (ncols + 3) & ~3;
+  if (tid < kpad) {
+    float bnorm = INFINITY;
+    if (tid < ncols) {
+      float v[DMAX];
 #pragma unroll
-    for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
-    bn[tid] = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, ncols));
+      for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
+      bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, ncols));
+    }
+    bn[tid] = bnorm;
   }
   __syncthreads();
   unsigned long long key = ~0ull;
-  for (int64_t i = (int64_t)blockIdx.x * KM_THREADS + tid; i < n; i += (int64_t)gridDim.x * KM_THREADS) {
+  const int64_t sstride = (int64_t)gridDim.x * KM_THREADS;
+  float a_next[DMAX];
+  {
+    const int64_t i0 = (int64_t)blockIdx.x * KM_THREADS + tid;
+#pragma unroll
+    for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * KM_THREADS + tid; i < n; i += sstride) {
     float a[DMAX];
 #pragma unroll
-    for (int r = 0; r < DMAX; ++r) a[r] = (r < d) ? __ldg(dl + (int64_t)r * n + i) : 0.f;
+    for (int r = 0; r < DMAX; ++r) a[r] = a_next[r];
+    {
+      const int64_t in = i + sstride;
+#pragma unroll
+      for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
+    }
     const float anorm = sumsq_torch_order<DMAX>(a, d, col_is_sequential(i, n));
     float best;
     int label;
-    best_centroid<DMAX>(a, d, anorm, cs, KMAX, bn, ncols, best, label);
+    best_centroid<DMAX, EXACT, false>(a, d, anorm, cs, KMAX, bn, ncols, kpad, best, label);
     const unsigned long long kk = pack_min_key(best, i);
     key = kk < key ? kk : key;
   }
@@ -343,11 +420,11 @@ __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l,
 }
 
 // Launch the assign kernel (cooperatively when it accumulates: the fold needs a grid barrier).
-template <int DMAX, int KMAX, int WARPS>
+template <int DMAX, int KMAX, int WARPS, bool EXACT>
 static int km_launch_w(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
                      const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
-  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS>;
+  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT>;
   constexpr int KM_THREADS_L = WARPS * 32;
   const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, sums != nullptr);
   if (smem > 200 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
@@ -356,7 +433,7 @@ static int km_launch_w(const float* data, const float* centroids, int l, int d, 
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, KM_THREADS_L, smem);
   if (e != cudaSuccess || per_sm < 1) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: occupancy query failed");
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 8) per_sm = 8;
   int64_t cap = (int64_t)sm_count() * per_sm / l;     // all l * grid.x blocks must be co-resident
   if (cap < 1) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d exceeds the co-resident block budget", l);
   int64_t gx = (n + KM_THREADS_L - 1) / KM_THREADS_L;
@@ -376,22 +453,47 @@ static int km_launch_w(const float* data, const float* centroids, int l, int d, 
   return check_launch("kmeans_assign_kernel");
 }
 
-template <int DMAX, int KMAX>
+template <int DMAX, int KMAX, bool EXACT>
 static int km_launch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
                      const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
   // four warps per block while their lane-private records fit ~100 KB, otherwise one warp per block
   if (km_smem_bytes<DMAX, KMAX>(d, k, KM_WARPS, sums != nullptr) <= 100 * 1024)
-    return km_launch_w<DMAX, KMAX, KM_WARPS>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
-                                             status, labels_in, st);
-  return km_launch_w<DMAX, KMAX, 1>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
-                                    labels_in, st);
+    return km_launch_w<DMAX, KMAX, KM_WARPS, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
+                                                    workspace, status, labels_in, st);
+  return km_launch_w<DMAX, KMAX, 1, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
+                                           status, labels_in, st);
+}
+
+// (6, <=32) is the reference configuration (k = 6 coefficients, 20 anchors): compile-time d.
+static int km_dispatch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
+                       float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
+                       const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+  if (d == 6 && k <= 32)
+    return km_launch<6, 32, true>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
+                                  labels_in, st);
+  if (d <= 8 && k <= 32)
+    return km_launch<8, 32, false>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
+                                   labels_in, st);
+  return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
+                                                          workspace, status, labels_in, st);
 }
 
 static int km_grid(int64_t n) {
   int64_t g = (n + KM_THREADS - 1) / KM_THREADS;
-  const int64_t cap = (int64_t)sm_count() * 4;
+  const int64_t cap = (int64_t)sm_count() * 8;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+static void launch_seed_step(dim3 grid, cudaStream_t st, const float* data, int d, int64_t n, int k, int ncols,
+                             unsigned long long* scratch, const float* cent_in, unsigned long long* key_out) {
+  if (d == 6 && k <= 32)
+    kmeans_seed_step_kernel<6, 32, true><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out);
+  else if (d <= 8 && k <= 32)
+    kmeans_seed_step_kernel<8, 32, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out);
+  else
+    kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch,
+                                                                                               cent_in, key_out);
 }
 
 static int km_check(int l, int d, int64_t n, int k) {
@@ -410,8 +512,8 @@ extern "C" {
 
 size_t et_kmeans_workspace_bytes(int l, int d, int k_clusters) {
   if (l < 1 || d < 1 || k_clusters < 1) return 0;
-  // 128 B of barrier counters + one partial record per co-resident block (at most 4 per SM in total)
-  return 128 + (size_t)sm_count() * 4 * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
+  // 128 B of barrier counters + one partial record per co-resident block (at most 8 per SM in total)
+  return 128 + (size_t)sm_count() * 8 * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
 }
 
 int et_kmeans_assign(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
@@ -423,11 +525,7 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
   ET_REQUIRE(!sums || (counts && workspace), ET_ERR_BADARG, "et_kmeans_assign: sums given without counts / workspace");
   if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
-  if (d <= 8 && k_clusters <= 32)
-    return km_launch<8, 32>(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status,
-                            nullptr, st);
-  return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS>(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts,
-                                                   simsum, workspace, status, nullptr, st);
+  return km_dispatch(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status, nullptr, st);
 }
 
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n, int k_clusters,
@@ -438,11 +536,7 @@ int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d,
   ET_REQUIRE(sums && counts && workspace, ET_ERR_BADARG, "et_kmeans_accumulate: sums / counts / workspace null");
   if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
-  if (d <= 8 && k_clusters <= 32)
-    return km_launch<8, 32>(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr,
-                            labels, st);
-  return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS>(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr,
-                                                   workspace, nullptr, labels, st);
+  return km_dispatch(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr, labels, st);
 }
 
 int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_clusters, const float* old_centroids,
@@ -468,11 +562,7 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   if ((rc = check_launch("kmeans_seed_init_kernel"))) return rc;
   dim3 grid(km_grid(n), l);
   for (int i = 1; i < k_clusters; ++i) {
-    if (d <= 8 && k_clusters <= 32)
-      kmeans_seed_step_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch, nullptr, nullptr);
-    else
-      kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, i, scratch,
-                                                                                          nullptr, nullptr);
+    launch_seed_step(grid, st, data, d, n, k_clusters, i, scratch, nullptr, nullptr);
     if ((rc = check_launch("kmeans_seed_step_kernel"))) return rc;
   }
   kmeans_seed_gather_kernel<<<(l * d * k_clusters + 255) / 256, 256, 0, st>>>(data, l, d, n, k_clusters, scratch, centroids);
@@ -490,11 +580,7 @@ int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d,
   if ((rc = check_launch("fill_u64_kernel"))) return rc;
   if (n == 0) return ET_OK;
   dim3 grid(km_grid(n), l);
-  if (d <= 8 && k_clusters <= 32)
-    kmeans_seed_step_kernel<8, 32><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, ncols, nullptr, centroids, key_out);
-  else
-    kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS><<<grid, KM_THREADS, 0, st>>>(data, d, n, k_clusters, ncols, nullptr,
-                                                                                        centroids, key_out);
+  launch_seed_step(grid, st, data, d, n, k_clusters, ncols, nullptr, centroids, key_out);
   return check_launch("kmeans_seed_step_kernel");
 }
 

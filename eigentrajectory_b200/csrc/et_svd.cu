@@ -21,13 +21,16 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-constexpr int GR_WARPS = 8;
+constexpr int GR_WARPS = 4;
 constexpr int GR_PITCH = 40;                 // floats per staged pedestrian: 16 obs + 24 pred, conflict-free
 constexpr int GR_NBLK_O = 3, GR_NBLK_P = 6;  // upper-triangular 8x8 blocks of the 16x16 / 24x24 Gram matrices
 constexpr int GR_GO = 16 * 16, GR_GP = 24 * 24;
 
 // workspace layout: two uint32 barrier counters (zero on entry, zero again on exit), then at byte 128
 // gridDim.x partial matrices of GR_GO + GR_GP doubles.  Cooperative launch (grid barrier before the fold).
+//
+// Each warp walks its tiles of 32 pedestrians with a one-tile register prefetch: the global loads of tile i+1 are in
+// flight while the DMMA phase of tile i runs, so the fp64 tensor pipe is not left idle behind HBM latency.
 __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restrict__ obs, const float* __restrict__ pred,
                                                            int64_t n, int flags, double* __restrict__ G_obs,
                                                            double* __restrict__ G_pred, unsigned* __restrict__ ticket,
@@ -46,39 +49,45 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
 
   const int64_t n_tiles = (n + 31) / 32;
   const int64_t wstride = (int64_t)gridDim.x * GR_WARPS;
-  for (int64_t tile = (int64_t)blockIdx.x * GR_WARPS + warp; tile < n_tiles; tile += wstride) {
+  float4 raw[10];
+  auto fetch = [&](int64_t tile) {
     const int64_t i = tile * 32 + lane;
-    float4* row = reinterpret_cast<float4*>(xw + lane * GR_PITCH);
-    if (i < n) {
-      float x[40];
+    if (tile < n_tiles && i < n) {
       const float4* po = reinterpret_cast<const float4*>(obs + i * 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 v = __ldg(po + c);
-        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
-      }
+      for (int c = 0; c < 4; ++c) raw[c] = __ldg(po + c);
       if (pred) {
         const float4* pp = reinterpret_cast<const float4*>(pred + i * 24);
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const float4 v = __ldg(pp + c);
-          x[16 + 4 * c] = v.x; x[17 + 4 * c] = v.y; x[18 + 4 * c] = v.z; x[19 + 4 * c] = v.w;
-        }
+        for (int c = 0; c < 6; ++c) raw[4 + c] = __ldg(pp + c);
       } else {
 #pragma unroll
-        for (int c = 16; c < 40; ++c) x[c] = 0.f;
+        for (int c = 4; c < 10; ++c) raw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (flags) {
+    } else {
+#pragma unroll
+      for (int c = 0; c < 10; ++c) raw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int64_t tile = (int64_t)blockIdx.x * GR_WARPS + warp;
+  fetch(tile);
+  for (; tile < n_tiles; tile += wstride) {
+    {
+      float x[40];
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {
+        x[4 * c] = raw[c].x; x[4 * c + 1] = raw[c].y; x[4 * c + 2] = raw[c].z; x[4 * c + 3] = raw[c].w;
+      }
+      if (flags && tile * 32 + lane < n) {
         const NormState st = make_norm_state(x[14], x[15], x[10], x[11]);
 #pragma unroll
         for (int t = 0; t < 20; ++t) norm_fwd(x[2 * t], x[2 * t + 1], st, flags);
       }
+      float4* row = reinterpret_cast<float4*>(xw + lane * GR_PITCH);
 #pragma unroll
       for (int c = 0; c < 10; ++c) row[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 10; ++c) row[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    fetch(tile + wstride);   // next tile's loads fly during the DMMA phase below
     __syncwarp();
     // 8 k-steps of 4 pedestrians; fragment f holds x[ped 4*ks + t4][8 f + g] (serves as A and as B)
 #pragma unroll 2
@@ -210,78 +219,108 @@ __device__ __forceinline__ void eig_sync() {
   else __syncthreads();
 }
 
+// MP != 0: the padded size is a compile-time constant and the block is one warp, so every index computation and the
+// item loops (9 items per lane for 24 x 24) unroll completely.
+template <int MP>
 __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
                                                                      float* __restrict__ U, float* __restrict__ S,
-                                                                     double* __restrict__ U64, double* __restrict__ S64) {
+                                                                     double* __restrict__ U64, double* __restrict__ S64,
+                                                                     int* __restrict__ info) {
   extern __shared__ double sm[];
-  const int mp = (m + 1) & ~1;   // even size; a padding index never rotates
-  double* A = sm;                // mp x mp (row-major, pitch mp)
-  double* V = A + mp * mp;       // mp x mp
-  double* cs = V + mp * mp;      // mp/2 cosines, mp/2 sines
+  const int mp = MP ? MP : ((m + 1) & ~1);   // even size; a padding index never rotates
+  const int ld = mp + 1;         // odd pitch: column walks (stride ld doubles) are bank-conflict free
+  double* A = sm;                // mp x mp, row-major with pitch ld
+  double* V = A + mp * ld;       // mp x mp, same pitch
+  double* cs = V + mp * ld;      // mp/2 cosines, mp/2 sines
   int* pr = reinterpret_cast<int*>(cs + mp);   // pairs p[mp/2], q[mp/2]
   int* order = pr + mp;                         // mp
-  __shared__ int n_rot;
-  const int tid = threadIdx.x, nthr = blockDim.x, half = mp / 2;
+  __shared__ int n_rot, step_rot[2];   // step_rot is double-buffered by step parity (reset one step ahead)
+  __shared__ double floor2;            // (1e-18 * largest diagonal entry)^2: rotations below it cannot matter
+  int sweeps_done = 0, total_rot = 0;
+  const int tid = threadIdx.x, nthr = MP ? 32 : (int)blockDim.x, half = mp / 2;
 
   for (int e = tid; e < mp * mp; e += nthr) {
     const int r = e / mp, c = e % mp;
-    A[e] = (r < m && c < m) ? 0.5 * (G[r * m + c] + G[c * m + r]) : 0.0;
-    V[e] = (r == c) ? 1.0 : 0.0;
+    A[r * ld + c] = (r < m && c < m) ? 0.5 * (G[r * m + c] + G[c * m + r]) : 0.0;
+    V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  if (tid == 0) step_rot[0] = step_rot[1] = 0;
+  int gstep = 0;
+  eig_sync();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
+    floor2 = (1e-18 * mx) * (1e-18 * mx);
   }
   eig_sync();
 
   for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
     if (tid == 0) n_rot = 0;
     eig_sync();
-    for (int step = 0; step < mp - 1; ++step) {
+    for (int step = 0; step < mp - 1; ++step, ++gstep) {
       // round-robin tournament: position 0 fixed, the others rotate
       for (int pi = tid; pi < half; pi += nthr) {
         auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (mp - 1); };
         int p = player(pi), q = player(mp - 1 - pi);
         if (p > q) { const int t = p; p = q; q = t; }
-        const double app = A[p * mp + p], aqq = A[q * mp + q], apq = A[p * mp + q];
+        const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
         double c = 1.0, s = 0.0;
-        if (q < m && fabs(apq) > 1e-300 && fabs(apq) > 2.2e-16 * sqrt(fabs(app) * fabs(aqq))) {
-          const double tau = (aqq - app) / (2.0 * apq);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
+        // rotate iff |a_pq| > 1e-14 sqrt(a_pp a_qq)  (compared squared: no square root on the critical path)
+        // and |a_pq| above an absolute floor 1e-18 max_i a_ii that keeps the solve from polishing the numerical null space
+        if (q < m && apq * apq > floor2 && apq * apq > 1e-28 * fabs(app * aqq)) {
+          // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (a_qq - a_pp) / (2 a_pq), written with one sqrt and
+          // one division: t = o / (dd + sign(dd) sqrt(dd^2 + o^2)), o = 2 a_pq, dd = a_qq - a_pp
+          const double o = 2.0 * apq, dd = aqq - app;
+          const double h = sqrt(fma(dd, dd, o * o));
+          const double t = o / (dd + (dd >= 0.0 ? h : -h));
+          c = rsqrt(fma(t, t, 1.0));
           s = t * c;
-          atomicAdd(&n_rot, 1);
+          atomicAdd(&step_rot[gstep & 1], 1);
         }
         cs[pi] = c; cs[half + pi] = s; pr[pi] = p; pr[half + pi] = q;
       }
       eig_sync();
+      const int rotated = step_rot[gstep & 1];     // block-uniform
+      if (tid == 0) { n_rot += rotated; step_rot[(gstep + 1) & 1] = 0; }
+      eig_sync();
+      if (rotated == 0) continue;       // nothing to do in this step (typical for the last, confirming sweep)
       // columns: A <- A J, V <- V J
+#pragma unroll
       for (int e = tid; e < half * mp; e += nthr) {
         const int pi = e / mp, r = e % mp;
         const double c = cs[pi], s = cs[half + pi];
         if (s != 0.0) {
           const int p = pr[pi], q = pr[half + pi];
-          const double ap = A[r * mp + p], aq = A[r * mp + q];
-          A[r * mp + p] = c * ap - s * aq;
-          A[r * mp + q] = s * ap + c * aq;
-          const double vp = V[r * mp + p], vq = V[r * mp + q];
-          V[r * mp + p] = c * vp - s * vq;
-          V[r * mp + q] = s * vp + c * vq;
+          const double ap = A[r * ld + p], aq = A[r * ld + q];
+          A[r * ld + p] = c * ap - s * aq;
+          A[r * ld + q] = s * ap + c * aq;
+          const double vp = V[r * ld + p], vq = V[r * ld + q];
+          V[r * ld + p] = c * vp - s * vq;
+          V[r * ld + q] = s * vp + c * vq;
         }
       }
       eig_sync();
       // rows: A <- J^T A; the rotated off-diagonal pair is zero by construction and is stored as exactly zero
+#pragma unroll
       for (int e = tid; e < half * mp; e += nthr) {
         const int pi = e / mp, col = e % mp;
         const double c = cs[pi], s = cs[half + pi];
         if (s != 0.0) {
           const int p = pr[pi], q = pr[half + pi];
-          const double ap = A[p * mp + col], aq = A[q * mp + col];
-          A[p * mp + col] = (col == q) ? 0.0 : c * ap - s * aq;
-          A[q * mp + col] = (col == p) ? 0.0 : s * ap + c * aq;
+          const double ap = A[p * ld + col], aq = A[q * ld + col];
+          A[p * ld + col] = (col == q) ? 0.0 : c * ap - s * aq;
+          A[q * ld + col] = (col == p) ? 0.0 : s * ap + c * aq;
         }
       }
       eig_sync();
     }
+    eig_sync();
+    ++sweeps_done;
+    total_rot += n_rot;
     if (n_rot == 0) break;
     eig_sync();
   }
+  if (info && tid == 0) { info[0] = sweeps_done; info[1] = total_rot; }
 
   // order eigenvalues descending (ties: lower index first) -- m <= 64, one thread
   if (tid == 0) {
@@ -289,25 +328,25 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
     for (int i = 0; i < m; ++i) {
       int best = i;
       for (int j = i + 1; j < m; ++j)
-        if (A[order[j] * mp + order[j]] > A[order[best] * mp + order[best]]) best = j;
+        if (A[order[j] * ld + order[j]] > A[order[best] * ld + order[best]]) best = j;
       const int t = order[i]; order[i] = order[best]; order[best] = t;
     }
   }
   eig_sync();
   for (int j = tid; j < k; j += nthr) {
     const int col = order[j];
-    const double lam = A[col * mp + col];
+    const double lam = A[col * ld + col];
     const double sv = sqrt(lam > 0.0 ? lam : 0.0);
     // canonical sign: the largest-magnitude component (first one on ties) is positive
     int arg = 0;
     double big = -1.0;
     for (int r = 0; r < m; ++r) {
-      const double a = fabs(V[r * mp + col]);
+      const double a = fabs(V[r * ld + col]);
       if (a > big) { big = a; arg = r; }
     }
-    const double sign = V[arg * mp + col] < 0.0 ? -1.0 : 1.0;
+    const double sign = V[arg * ld + col] < 0.0 ? -1.0 : 1.0;
     for (int r = 0; r < m; ++r) {
-      const double v = sign * V[r * mp + col];
+      const double v = sign * V[r * ld + col];
       U[r * k + j] = (float)v;
       if (U64) U64[r * k + j] = v;
     }
@@ -373,10 +412,11 @@ __global__ void __launch_bounds__(SVS_THREADS) svd_small_kernel(const float* __r
           b += __shfl_xor_sync(0xffffffffu, b, o);
           g += __shfl_xor_sync(0xffffffffu, g, o);
         }
-        if (fabs(g) > 1e-7 * sqrt(a * b) && fabs(g) > 1e-30) {
-          const double tau = (b - a) / (2.0 * g);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          const double cd = 1.0 / sqrt(1.0 + t * t);
+        if (g * g > 1e-14 * (a * b) && fabs(g) > 1e-30) {
+          const double o = 2.0 * g, dd = b - a;
+          const double h = sqrt(fma(dd, dd, o * o));
+          const double t = o / (dd + (dd >= 0.0 ? h : -h));
+          const double cd = rsqrt(fma(t, t, 1.0));
           const float c = (float)cd, s = (float)(t * cd);
           for (int r = lane; r < nb; r += 32) {
             const float vp = xp[r], vq = xq[r];
@@ -430,7 +470,7 @@ __global__ void __launch_bounds__(SVS_THREADS) svd_small_kernel(const float* __r
   }
 }
 
-static int gram_grid() { return sm_count() * 2; }
+static int gram_grid() { return sm_count() * 4; }
 
 }  // namespace et
 
@@ -472,18 +512,28 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
   return check_launch("gram_generic");
 }
 
-int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64, et_stream_t stream) {
+int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64, int* info,
+                  et_stream_t stream) {
   ET_REQUIRE(G && U && S, ET_ERR_BADARG, "et_eig_jacobi: null pointer");
   ET_REQUIRE(m >= 1 && m <= 2 * ET_MAX_T, ET_ERR_UNSUPPORTED, "et_eig_jacobi: m = %d outside [1, %d]", m, 2 * ET_MAX_T);
   ET_REQUIRE(k >= 1 && k <= m, ET_ERR_BADARG, "et_eig_jacobi: k = %d outside [1, m = %d]", k, m);
   const int mp = (m + 1) & ~1;
-  const size_t smem = (size_t)(2 * mp * mp + mp) * sizeof(double) + (size_t)2 * mp * sizeof(int);
-  cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "eig_jacobi_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  int threads = ((mp / 2) * mp / 9 + 31) / 32 * 32;     // ~9 work items per thread and phase
-  if (threads < 32) threads = 32;
-  if (threads > EIG_MAX_THREADS) threads = EIG_MAX_THREADS;
-  eig_jacobi_kernel<<<1, threads, smem, as_stream(stream)>>>(G, m, k, U, S, U64, S64);
+  const size_t smem = (size_t)(2 * mp * (mp + 1) + mp) * sizeof(double) + (size_t)2 * mp * sizeof(int);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(ET_ERR_CUDA, "eig_jacobi_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  cudaStream_t st = as_stream(stream);
+  if (mp == 16) {
+    eig_jacobi_kernel<16><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+  } else if (mp == 24) {
+    eig_jacobi_kernel<24><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+  } else {
+    int threads = ((mp / 2) * mp / 9 + 31) / 32 * 32;     // ~9 work items per thread and phase
+    if (threads < 32) threads = 32;
+    if (threads > EIG_MAX_THREADS) threads = EIG_MAX_THREADS;
+    eig_jacobi_kernel<0><<<1, threads, smem, st>>>(G, m, k, U, S, U64, S64, info);
+  }
   return check_launch("eig_jacobi_kernel");
 }
 

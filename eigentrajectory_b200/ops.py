@@ -315,8 +315,10 @@ def gram(obs, pred=None, ori=False, rot=False, sca=False, G_obs=None, G_pred=Non
     return G_obs, (G_pred if p is not None else None)
 
 
-def eig_basis(G, k, want64=False):
-    """Leading-k eigenpairs of a float64 Gram matrix -> (U (m,k) fp32, S (k) fp32[, U64, S64])."""
+def eig_basis(G, k, want64=False, info=None):
+    """Leading-k eigenpairs of a float64 Gram matrix -> (U (m,k) fp32, S (k) fp32[, U64, S64]).
+
+    ``info``: optional device int32[2] tensor that receives (sweeps, rotations)."""
     assert G.is_cuda and G.dtype == torch.float64 and G.dim() == 2 and G.size(0) == G.size(1)
     G = G.contiguous()
     m = G.size(0)
@@ -324,7 +326,8 @@ def eig_basis(G, k, want64=False):
     S = torch.empty((k,), device=G.device)
     U64 = torch.empty((m, k), dtype=torch.float64, device=G.device) if want64 else None
     S64 = torch.empty((k,), dtype=torch.float64, device=G.device) if want64 else None
-    check(load().et_eig_jacobi(ptr(G), m, k, ptr(U), ptr(S), ptr(U64), ptr(S64), stream_of(G.device)), "et_eig_jacobi")
+    check(load().et_eig_jacobi(ptr(G), m, k, ptr(U), ptr(S), ptr(U64), ptr(S64), ptr(info), stream_of(G.device)),
+          "et_eig_jacobi")
     return (U, S, U64, S64) if want64 else (U, S)
 
 

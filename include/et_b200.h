@@ -127,9 +127,10 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
 /* Symmetric eigen-solve of G (m x m, float64, m <= 64) by parallel-ordered cyclic Jacobi;
  * returns the k leading left singular vectors U (m,k) row-major float32 and singular
  * values S (k) = sqrt(lambda).  Column signs are canonical: the largest-magnitude
- * component of each column is positive.  U64 (m,k) / S64 (k) optional float64 copies. */
+ * component of each column is positive.  U64 (m,k) / S64 (k) optional float64 copies;
+ * info (optional, device int32[2]) receives {sweeps executed, rotations applied}. */
 int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64,
-                  et_stream_t stream);
+                  int* info, et_stream_t stream);
 /* Batched small-N SVD: one-sided (Hestenes) Jacobi on shared-memory resident tall-skinny
  * matrices.  Problem b is the (n_b x 2T) matrix of the trajectories
  * traj[offsets[b] .. offsets[b+1]) (already normalised).  offsets is a DEVICE int64 array
