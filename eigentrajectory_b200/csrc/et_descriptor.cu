@@ -369,25 +369,31 @@ constexpr int PR_TILE = 128;
 constexpr int PR_OBS_BYTES = PR_TILE * 64;
 constexpr int PR_PA_BYTES = PR_TILE * 64;
 constexpr int PR_PB_BYTES = PR_TILE * 32;
-constexpr int PR_STAGE_BYTES = PR_OBS_BYTES + PR_PA_BYTES + PR_PB_BYTES;   // 20480
+constexpr int PR_LOAD_BYTES = PR_OBS_BYTES + PR_PA_BYTES + PR_PB_BYTES;    // 20480: what one tile's TMA loads bring
+constexpr int PR_C_BYTES = 6 * PR_TILE * 4;                                  // 3072: one (k, 128) coefficient box
+template <bool TMAC>
+struct PRStage { static constexpr int bytes = PR_LOAD_BYTES + (TMAC ? 2 * PR_C_BYTES : 0); };   // 20480 / 26624
 constexpr int PR_CONSUMER_WARPS = PR_TILE / 32;
 constexpr int PR_THREADS = (PR_CONSUMER_WARPS + 1) * 32;
 
 struct PRMaps {
-  CUtensorMap in_obs, in_pa, in_pb, out_obs, out_pa, out_pb;
+  CUtensorMap in_obs, in_pa, in_pb, out_obs, out_pa, out_pb, out_cobs, out_cpred;
 };
 
-template <int NS>
+template <int NS, bool TMAC>
 constexpr size_t pr_smem_bytes() {
-  return 1024 /* alignment slack */ + (size_t)NS * PR_STAGE_BYTES + (16 + 24) * UPITCH * 4 + 2 * NS * 8;
+  return 1024 /* alignment slack */ + (size_t)NS * PRStage<TMAC>::bytes + (16 + 24) * UPITCH * 4 + 2 * NS * 8;
 }
 
-template <int NS, int MINB>
+// TMAC: the coefficient rows of a tile are staged in shared memory as two (k, 128) boxes and written by the producer
+// with tensor stores as well (needs N % 4 == 0 for the (k, N) tensor map); otherwise consumers store them directly.
+template <int NS, int MINB, bool TMAC>
 __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(const __grid_constant__ PRMaps maps, int64_t n,
                                                                        int n_tiles, const float* __restrict__ U_obs,
                                                                        const float* __restrict__ U_pred, int flags,
                                                                        float* __restrict__ C_obs,
                                                                        float* __restrict__ C_pred) {
+  constexpr int PR_STAGE_BYTES = PRStage<TMAC>::bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* Uo = reinterpret_cast<float*>(stages + (size_t)NS * PR_STAGE_BYTES);
@@ -418,11 +424,13 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
     if (lane == 0 && my_tiles > 0) {
       prefetch_tensormap(&maps.in_obs);  prefetch_tensormap(&maps.in_pa);  prefetch_tensormap(&maps.in_pb);
       prefetch_tensormap(&maps.out_obs); prefetch_tensormap(&maps.out_pa); prefetch_tensormap(&maps.out_pb);
+      if (TMAC && C_obs) prefetch_tensormap(&maps.out_cobs);
+      if (TMAC && C_pred) prefetch_tensormap(&maps.out_cpred);
       auto issue_load = [&](int it) {
         const int s = it % NS;
         const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * PR_TILE;
         uint8_t* st = stages + (size_t)s * PR_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], PR_STAGE_BYTES);
+        mbar_arrive_expect_tx(&full[s], PR_LOAD_BYTES);
         tma_load_2d(st, &maps.in_obs, 0, row0, &full[s]);
         tma_load_2d(st + PR_OBS_BYTES, &maps.in_pa, 0, row0, &full[s]);
         tma_load_2d(st + PR_OBS_BYTES + PR_PA_BYTES, &maps.in_pb, 16, row0, &full[s]);
@@ -437,6 +445,10 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
         tma_store_2d(&maps.out_obs, 0, row0, st);
         tma_store_2d(&maps.out_pa, 0, row0, st + PR_OBS_BYTES);
         tma_store_2d(&maps.out_pb, 16, row0, st + PR_OBS_BYTES + PR_PA_BYTES);
+        if (TMAC) {
+          if (C_obs) tma_store_2d(&maps.out_cobs, row0, 0, st + PR_LOAD_BYTES);
+          if (C_pred) tma_store_2d(&maps.out_cpred, row0, 0, st + PR_LOAD_BYTES + PR_C_BYTES);
+        }
         bulk_commit();
         // refill the stage whose store was issued one iteration ago
         if (it >= 1 && it - 1 + NS < my_tiles) {
@@ -509,11 +521,19 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
             make_float4(xp[16 + 4 * c], xp[17 + 4 * c], xp[18 + 4 * c], xp[19 + 4 * c]);
     }
 
+    if (TMAC) {
+      float* cb = reinterpret_cast<float*>(st + PR_LOAD_BYTES);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        cb[j * PR_TILE + r] = co[j];
+        cb[6 * PR_TILE + j * PR_TILE + r] = cp[j];
+      }
+    }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(&done[s]);
 
-    if (i < n) {
+    if (!TMAC && i < n) {
       if (C_obs) {
 #pragma unroll
         for (int j = 0; j < 6; ++j) C_obs[(int64_t)j * n + i] = co[j];
@@ -722,10 +742,10 @@ static int ensure_smem(F kernel, size_t bytes, const char* what) {
   return ET_OK;
 }
 
-template <int NS, int MINB>
-static int launch_pr_tma(const float* obs, const float* pred, int64_t n, const float* U_obs, const float* U_pred,
-                         int flags, float* rec_obs, float* rec_pred, float* C_obs, float* C_pred,
-                         cudaStream_t stream) {
+template <int NS, int MINB, bool TMAC>
+static int launch_pr_tma_c(const float* obs, const float* pred, int64_t n, const float* U_obs, const float* U_pred,
+                           int flags, float* rec_obs, float* rec_pred, float* C_obs, float* C_pred,
+                           cudaStream_t stream) {
   PRMaps maps;
   int rc;
   if ((rc = make_tensor_map_2d(&maps.in_obs, obs, (uint64_t)n, 16, 64, 16, PR_TILE, 64))) return rc;
@@ -734,16 +754,31 @@ static int launch_pr_tma(const float* obs, const float* pred, int64_t n, const f
   if ((rc = make_tensor_map_2d(&maps.out_obs, rec_obs, (uint64_t)n, 16, 64, 16, PR_TILE, 64))) return rc;
   if ((rc = make_tensor_map_2d(&maps.out_pa, rec_pred, (uint64_t)n, 24, 96, 16, PR_TILE, 64))) return rc;
   if ((rc = make_tensor_map_2d(&maps.out_pb, rec_pred, (uint64_t)n, 24, 96, 8, PR_TILE, 32))) return rc;
-  constexpr size_t smem = pr_smem_bytes<NS>();
-  if ((rc = ensure_smem(project_reconstruct_tma<NS, MINB>, smem, "project_reconstruct_tma"))) return rc;
+  if (TMAC) {   // (k, N) row-major coefficient matrices, box = 128 pedestrians x 6 rows
+    if (C_obs && (rc = make_tensor_map_2d(&maps.out_cobs, C_obs, 6, (uint32_t)n, (uint64_t)n * 4, PR_TILE, 6, 0))) return rc;
+    if (C_pred && (rc = make_tensor_map_2d(&maps.out_cpred, C_pred, 6, (uint32_t)n, (uint64_t)n * 4, PR_TILE, 6, 0))) return rc;
+  }
+  constexpr size_t smem = pr_smem_bytes<NS, TMAC>();
+  auto kern = project_reconstruct_tma<NS, MINB, TMAC>;
+  if ((rc = ensure_smem(kern, smem, "project_reconstruct_tma"))) return rc;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, project_reconstruct_tma<NS, MINB>, PR_THREADS, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PR_THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   const int n_tiles = (int)((n + PR_TILE - 1) / PR_TILE);
   int grid = sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  project_reconstruct_tma<NS, MINB><<<grid, PR_THREADS, smem, stream>>>(maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred);
+  kern<<<grid, PR_THREADS, smem, stream>>>(maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred);
   return check_launch("project_reconstruct_tma");
+}
+
+template <int NS, int MINB>
+static int launch_pr_tma(const float* obs, const float* pred, int64_t n, const float* U_obs, const float* U_pred,
+                         int flags, float* rec_obs, float* rec_pred, float* C_obs, float* C_pred, bool tma_c,
+                         cudaStream_t stream) {
+  // tensor stores for the coefficients need a 16-byte row pitch (N % 4 == 0) and aligned bases
+  const bool ok = tma_c && (C_obs || C_pred) && n % 4 == 0 && aligned16(C_obs) && aligned16(C_pred);
+  if (ok) return launch_pr_tma_c<NS, MINB, true>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, stream);
+  return launch_pr_tma_c<NS, MINB, false>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, stream);
 }
 
 }  // namespace et
@@ -860,12 +895,12 @@ int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t
     return check_launch("project_reconstruct_direct");
   }
   ET_REQUIRE(n < (int64_t)1 << 31, ET_ERR_UNSUPPORTED, "et_project_reconstruct: TMA variants need n < 2^31");
-  // 2: 4 stages, 2 blocks / SM (no register cap)   3: 3 stages, 3 blocks / SM   4: 5 stages, 2 blocks / SM
-  if (variant == 2) return launch_pr_tma<4, 2>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, st);
-  if (variant == 3) return launch_pr_tma<3, 3>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, st);
-  return launch_pr_tma<5, 2>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, st);
+  // 2: 4 stages, 2 blocks/SM, coefficients through TMA stores   3: 3 stages, 3 blocks/SM   4: 4 stages, 2 blocks/SM,
+  // coefficients stored directly by the consumer warps
+  if (variant == 2) return launch_pr_tma<4, 2>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, true, st);
+  if (variant == 3) return launch_pr_tma<3, 3>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, false, st);
+  return launch_pr_tma<4, 2>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, false, st);
 }
-
 
 int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k, int t, const float* U, int flags,
                    const float* ori, const float* rot, const float* sca, float* out, et_stream_t stream) {

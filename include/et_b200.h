@@ -106,8 +106,9 @@ int et_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t, co
  * rec_obs (N,T_obs,2), rec_pred (N,T_pred,2); C_obs / C_pred (k,N) are optional (null =
  * coefficients are not materialised: 320 instead of 368 algorithmic bytes / trajectory).
  * variant: 0 = auto, 1 = direct global access kernel, 2..4 = persistent warp-specialised
- * TMA-tiled kernel (2: 4-stage ring, 2 blocks/SM; 3: 3-stage, 3 blocks/SM; 4: 5-stage,
- * 2 blocks/SM); the TMA variants need (T_obs,T_pred,k) = (8,12,6) and n < 2^31. */
+ * TMA-tiled kernel (2: 4-stage ring, 2 blocks/SM, coefficients written by tensor stores when
+ * N % 4 == 0; 3: 3-stage, 3 blocks/SM; 4: as 2 but coefficients stored by the consumer warps);
+ * the TMA variants need (T_obs,T_pred,k) = (8,12,6) and n < 2^31. */
 int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t_obs,
                            int t_pred, const float* U_obs, const float* U_pred, int k,
                            int flags, float* rec_obs, float* rec_pred, float* C_obs,
