@@ -25,6 +25,7 @@ PROTOTYPES = {
     "et_last_error": (C.c_char_p, []),
     "et_device_info": (_i, [_p, _p, _p]),
     "et_launch_count": (_l, []),
+    "et_tune": (_i, [_i, _i]),
     "et_norm_params": (_i, [_p, _l, _i, _i, _p, _p, _p, _p]),
     "et_normalize": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p]),
     "et_denormalize": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p]),

@@ -13,6 +13,7 @@ void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);     // cudaGetLastError -> ET_OK / ET_ERR_CUDA; counts the launch
 int sm_count();                          // SMs of the current device (cached per device)
+int tune_get(int knob);                  // current value of an ET_TUNE_* knob (0 = default)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t as_stream(et_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -387,12 +387,16 @@ constexpr size_t pr_smem_bytes() {
 
 // TMAC: the coefficient rows of a tile are staged in shared memory as two (k, 128) boxes and written by the producer
 // with tensor stores as well (needs N % 4 == 0 for the (k, N) tensor map); otherwise consumers store them directly.
-template <int NS, int MINB, bool TMAC>
+// RECON: write the rank-k reconstructions back (the round trip); false = ETDescriptor.projection only, which instead
+// writes the per-pedestrian normaliser state (ori / rot / sca).
+template <int NS, int MINB, bool TMAC, bool RECON>
 __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(const __grid_constant__ PRMaps maps, int64_t n,
                                                                        int n_tiles, const float* __restrict__ U_obs,
                                                                        const float* __restrict__ U_pred, int flags,
                                                                        float* __restrict__ C_obs,
-                                                                       float* __restrict__ C_pred) {
+                                                                       float* __restrict__ C_pred,
+                                                                       float* __restrict__ ori, float* __restrict__ rot,
+                                                                       float* __restrict__ sca) {
   constexpr int PR_STAGE_BYTES = PRStage<TMAC>::bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stages = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
     // ------------------------------ producer ------------------------------
     if (lane == 0 && my_tiles > 0) {
       prefetch_tensormap(&maps.in_obs);  prefetch_tensormap(&maps.in_pa);  prefetch_tensormap(&maps.in_pb);
-      prefetch_tensormap(&maps.out_obs); prefetch_tensormap(&maps.out_pa); prefetch_tensormap(&maps.out_pb);
+      if (RECON) { prefetch_tensormap(&maps.out_obs); prefetch_tensormap(&maps.out_pa); prefetch_tensormap(&maps.out_pb); }
       if (TMAC && C_obs) prefetch_tensormap(&maps.out_cobs);
       if (TMAC && C_pred) prefetch_tensormap(&maps.out_cpred);
       auto issue_load = [&](int it) {
@@ -442,9 +446,11 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
         const int row0 = ((int)blockIdx.x + it * (int)gridDim.x) * PR_TILE;
         uint8_t* st = stages + (size_t)s * PR_STAGE_BYTES;
         mbar_wait(&done[s], (uint32_t)((it / NS) & 1));
-        tma_store_2d(&maps.out_obs, 0, row0, st);
-        tma_store_2d(&maps.out_pa, 0, row0, st + PR_OBS_BYTES);
-        tma_store_2d(&maps.out_pb, 16, row0, st + PR_OBS_BYTES + PR_PA_BYTES);
+        if (RECON) {
+          tma_store_2d(&maps.out_obs, 0, row0, st);
+          tma_store_2d(&maps.out_pa, 0, row0, st + PR_OBS_BYTES);
+          tma_store_2d(&maps.out_pb, 16, row0, st + PR_OBS_BYTES + PR_PA_BYTES);
+        }
         if (TMAC) {
           if (C_obs) tma_store_2d(&maps.out_cobs, row0, 0, st + PR_LOAD_BYTES);
           if (C_pred) tma_store_2d(&maps.out_cpred, row0, 0, st + PR_LOAD_BYTES + PR_C_BYTES);
@@ -488,12 +494,14 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
       inv_sca = 1.0f / nst.sca;
       normalize_row<16>(xo, nst, flags);
       project_row<16, 6>(xo, Uo, co);
-      unproject_row<16, 6>(co, Uo, xo);
-      denormalize_row<16>(xo, nst, inv_sca, flags);
+      if (RECON) {
+        unproject_row<16, 6>(co, Uo, xo);
+        denormalize_row<16>(xo, nst, inv_sca, flags);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(so + (((uint32_t)c << 4) ^ sw64)) =
-            make_float4(xo[4 * c], xo[4 * c + 1], xo[4 * c + 2], xo[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(so + (((uint32_t)c << 4) ^ sw64)) =
+              make_float4(xo[4 * c], xo[4 * c + 1], xo[4 * c + 2], xo[4 * c + 3]);
+      }
     }
     {
       float xp[24];
@@ -509,17 +517,20 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
       }
       normalize_row<24>(xp, nst, flags);
       project_row<24, 6>(xp, Up, cp);
-      unproject_row<24, 6>(cp, Up, xp);
-      denormalize_row<24>(xp, nst, inv_sca, flags);
+      if (RECON) {
+        unproject_row<24, 6>(cp, Up, xp);
+        denormalize_row<24>(xp, nst, inv_sca, flags);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(sa + (((uint32_t)c << 4) ^ sw64)) =
-            make_float4(xp[4 * c], xp[4 * c + 1], xp[4 * c + 2], xp[4 * c + 3]);
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<float4*>(sa + (((uint32_t)c << 4) ^ sw64)) =
+              make_float4(xp[4 * c], xp[4 * c + 1], xp[4 * c + 2], xp[4 * c + 3]);
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-        *reinterpret_cast<float4*>(sb + (((uint32_t)c << 4) ^ sw32)) =
-            make_float4(xp[16 + 4 * c], xp[17 + 4 * c], xp[18 + 4 * c], xp[19 + 4 * c]);
+        for (int c = 0; c < 2; ++c)
+          *reinterpret_cast<float4*>(sb + (((uint32_t)c << 4) ^ sw32)) =
+              make_float4(xp[16 + 4 * c], xp[17 + 4 * c], xp[18 + 4 * c], xp[19 + 4 * c]);
+      }
     }
+    if (!RECON && i < n) store_norm_state(ori, rot, sca, i, nst, flags);
 
     if (TMAC) {
       float* cb = reinterpret_cast<float*>(st + PR_LOAD_BYTES);
@@ -742,24 +753,26 @@ static int ensure_smem(F kernel, size_t bytes, const char* what) {
   return ET_OK;
 }
 
-template <int NS, int MINB, bool TMAC>
+template <int NS, int MINB, bool TMAC, bool RECON>
 static int launch_pr_tma_c(const float* obs, const float* pred, int64_t n, const float* U_obs, const float* U_pred,
-                           int flags, float* rec_obs, float* rec_pred, float* C_obs, float* C_pred,
-                           cudaStream_t stream) {
+                           int flags, float* rec_obs, float* rec_pred, float* C_obs, float* C_pred, float* ori,
+                           float* rot, float* sca, cudaStream_t stream) {
   PRMaps maps;
   int rc;
   if ((rc = make_tensor_map_2d(&maps.in_obs, obs, (uint64_t)n, 16, 64, 16, PR_TILE, 64))) return rc;
   if ((rc = make_tensor_map_2d(&maps.in_pa, pred, (uint64_t)n, 24, 96, 16, PR_TILE, 64))) return rc;
   if ((rc = make_tensor_map_2d(&maps.in_pb, pred, (uint64_t)n, 24, 96, 8, PR_TILE, 32))) return rc;
-  if ((rc = make_tensor_map_2d(&maps.out_obs, rec_obs, (uint64_t)n, 16, 64, 16, PR_TILE, 64))) return rc;
-  if ((rc = make_tensor_map_2d(&maps.out_pa, rec_pred, (uint64_t)n, 24, 96, 16, PR_TILE, 64))) return rc;
-  if ((rc = make_tensor_map_2d(&maps.out_pb, rec_pred, (uint64_t)n, 24, 96, 8, PR_TILE, 32))) return rc;
+  if (RECON) {
+    if ((rc = make_tensor_map_2d(&maps.out_obs, rec_obs, (uint64_t)n, 16, 64, 16, PR_TILE, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&maps.out_pa, rec_pred, (uint64_t)n, 24, 96, 16, PR_TILE, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&maps.out_pb, rec_pred, (uint64_t)n, 24, 96, 8, PR_TILE, 32))) return rc;
+  }
   if (TMAC) {   // (k, N) row-major coefficient matrices, box = 128 pedestrians x 6 rows
     if (C_obs && (rc = make_tensor_map_2d(&maps.out_cobs, C_obs, 6, (uint32_t)n, (uint64_t)n * 4, PR_TILE, 6, 0))) return rc;
     if (C_pred && (rc = make_tensor_map_2d(&maps.out_cpred, C_pred, 6, (uint32_t)n, (uint64_t)n * 4, PR_TILE, 6, 0))) return rc;
   }
   constexpr size_t smem = pr_smem_bytes<NS, TMAC>();
-  auto kern = project_reconstruct_tma<NS, MINB, TMAC>;
+  auto kern = project_reconstruct_tma<NS, MINB, TMAC, RECON>;
   if ((rc = ensure_smem(kern, smem, "project_reconstruct_tma"))) return rc;
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PR_THREADS, smem);
@@ -767,8 +780,8 @@ static int launch_pr_tma_c(const float* obs, const float* pred, int64_t n, const
   const int n_tiles = (int)((n + PR_TILE - 1) / PR_TILE);
   int grid = sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<grid, PR_THREADS, smem, stream>>>(maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred);
-  return check_launch("project_reconstruct_tma");
+  kern<<<grid, PR_THREADS, smem, stream>>>(maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred, ori, rot, sca);
+  return check_launch(RECON ? "project_reconstruct_tma" : "project_reconstruct_tma(project)");
 }
 
 template <int NS, int MINB>
@@ -777,8 +790,11 @@ static int launch_pr_tma(const float* obs, const float* pred, int64_t n, const f
                          cudaStream_t stream) {
   // tensor stores for the coefficients need a 16-byte row pitch (N % 4 == 0) and aligned bases
   const bool ok = tma_c && (C_obs || C_pred) && n % 4 == 0 && aligned16(C_obs) && aligned16(C_pred);
-  if (ok) return launch_pr_tma_c<NS, MINB, true>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, stream);
-  return launch_pr_tma_c<NS, MINB, false>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, stream);
+  if (ok)
+    return launch_pr_tma_c<NS, MINB, true, true>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, nullptr,
+                                                 nullptr, nullptr, stream);
+  return launch_pr_tma_c<NS, MINB, false, true>(obs, pred, n, U_obs, U_pred, flags, rec_obs, rec_pred, C_obs, C_pred, nullptr,
+                                                nullptr, nullptr, stream);
 }
 
 }  // namespace et
@@ -855,6 +871,9 @@ int et_project(const float* obs, const float* pred, int64_t n, int t_obs, int t_
   ET_REQUIRE(aligned16(obs) && aligned16(pred) && aligned16(rot), ET_ERR_ALIGN, "et_project: pointers must be 16-byte aligned");
   if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
+  if (t_obs == 8 && pred && t_pred == 12 && k == 6 && n >= 4096 && n < ((int64_t)1 << 31) && n % 4 == 0 && aligned16(C_obs) &&
+      aligned16(C_pred) && aligned16(ori))
+    return launch_pr_tma_c<4, 2, true, false>(obs, pred, n, U_obs, U_pred, flags, nullptr, nullptr, C_obs, C_pred, ori, rot, sca, st);
   if (t_obs == 8 && (t_pred == 12 || !pred) && k == 6) {
     project_fast<8, 12, 6><<<blocks_for(n, 128), 128, 0, st>>>(obs, pred, n, U_obs, U_pred, flags, C_obs, C_pred, ori, rot, sca);
     return check_launch("project_fast");

@@ -9,6 +9,9 @@
 namespace et {
 
 static thread_local char g_err[512] = "";
+static std::atomic<int> g_tune[ET_TUNE_COUNT];
+
+int tune_get(int knob) { return (knob >= 0 && knob < ET_TUNE_COUNT) ? g_tune[knob].load(std::memory_order_relaxed) : 0; }
 static std::atomic<int64_t> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -90,6 +93,12 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint32
 extern "C" {
 
 int et_version(void) { return ET_B200_VERSION; }
+
+int et_tune(int knob, int value) {
+  if (knob < 0 || knob >= ET_TUNE_COUNT) return et::fail(ET_ERR_BADARG, "et_tune: unknown knob %d", knob);
+  et::g_tune[knob].store(value, std::memory_order_relaxed);
+  return ET_OK;
+}
 
 const char* et_last_error(void) { return et::g_err; }
 

@@ -60,6 +60,11 @@ int et_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Total number of kernels this library has launched from this process (all threads). */
 int64_t et_launch_count(void);
 
+/* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
+ * Results never depend on them. */
+enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_COUNT = 8 };
+int et_tune(int knob, int value);
+
 /* ---- normaliser: EigenTrajectory/normalizer.py ------------------------------------- */
 /* TrajNorm.calculate_params (normalizer.py:17-28).  obs (N,T_obs,2), T_obs >= 3.
  * ori (N,1,2), rot (N,2,2) = [[c,-s],[s,c]], sca (N,1,1) = (1/||d||)*2; outputs whose
