@@ -27,6 +27,15 @@ UNIT = "trajectories/s"
 N_SETS = 3                                        # rotating buffer sets, each (368 MB) larger than the 126 MB L2
 
 
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -253,7 +262,7 @@ def main():
                        "l2": f"{N_SETS} rotating buffer sets of {n * BYTES_PER_TRAJ / 1e6:.0f} MB each (> 126 MB L2)",
                        "parallelism": f"row-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "project_reconstruct_tma" if args.variant != 1 else "project_reconstruct_direct",
+                         "traffic": measured_traffic() if (args.variant in (0, 2) and n == N_PER_GPU) else None, "kernel": "project_reconstruct_tma" if args.variant != 1 else "project_reconstruct_direct",
                          "algorithmic_bytes_per_launch": n * BYTES_PER_TRAJ, "avg_launch_ms": avg_ms,
                          "min_launch_ms": min(per_launch_ms), "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 208,

@@ -14,11 +14,12 @@ from ._lib import ETLibraryError, load as load_library, launch_count  # noqa: F4
 from .anchor import ETAnchor  # noqa: F401
 from .descriptor import ETDescriptor  # noqa: F401
 from .kmeans import BatchKMeans  # noqa: F401
-from .metrics import compute_batch_ade, compute_batch_ade_fde, compute_batch_fde  # noqa: F401
+from .metrics import (compute_batch_ade, compute_batch_ade_fde, compute_batch_col, compute_batch_fde,  # noqa: F401
+                      compute_batch_metric, compute_batch_tcc)
 from .model import EigenTrajectory  # noqa: F401
 from .normalizer import TrajNorm  # noqa: F401
 from .utils import DotDict  # noqa: F401
 
 __all__ = ["EigenTrajectory", "ETDescriptor", "ETAnchor", "TrajNorm", "BatchKMeans", "compute_batch_ade",
-           "compute_batch_fde", "compute_batch_ade_fde", "DotDict", "ops", "load_library", "launch_count",
+           "compute_batch_fde", "compute_batch_ade_fde", "compute_batch_tcc", "compute_batch_col", "compute_batch_metric", "DotDict", "ops", "load_library", "launch_count",
            "ETLibraryError"]

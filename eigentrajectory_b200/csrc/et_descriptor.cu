@@ -797,6 +797,20 @@ static int launch_pr_tma(const float* obs, const float* pred, int64_t n, const f
                                                 nullptr, nullptr, stream);
 }
 
+// Grid of the reconstruction kernels: persistent (occupancy x SMs) by default; ET_TUNE_REC_BLOCKS_PER_SM > 0 overrides the
+// blocks per SM, < 0 launches one block per tile.
+template <typename F>
+static int64_t rec_grid(F kern, size_t smem, int64_t n_tiles) {
+  const int knob = tune_get(ET_TUNE_REC_BLOCKS_PER_SM);
+  if (knob < 0) return n_tiles;
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_WARPS * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  if (knob > 0 && knob < per_sm) per_sm = knob;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  return grid > n_tiles ? n_tiles : grid;
+}
+
 }  // namespace et
 
 using namespace et;
@@ -938,10 +952,7 @@ int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k,
     auto kern = reconstruct_fast<6, 12, 20>;
     if ((rc = ensure_smem(kern, L::bytes, "reconstruct_fast"))) return rc;
     const int64_t n_tiles = (n + 31) / 32;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_WARPS * 32, L::bytes);
-    int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
-    if (grid > n_tiles) grid = n_tiles;
+    const int64_t grid = rec_grid(kern, L::bytes, n_tiles);
     kern<<<(unsigned)grid, REC_WARPS * 32, L::bytes, st>>>(C, anchor, n, n_tiles, U, flags, ori, rot, sca, out);
     return check_launch("reconstruct_fast");
   }
@@ -966,10 +977,7 @@ int et_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t, co
     auto kern = reconstruct_bwd_fast<6, 12, 20>;
     if ((rc = ensure_smem(kern, L::bytes, "reconstruct_bwd_fast"))) return rc;
     const int64_t n_tiles = (n + 31) / 32;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, REC_WARPS * 32, L::bytes);
-    int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
-    if (grid > n_tiles) grid = n_tiles;
+    const int64_t grid = rec_grid(kern, L::bytes, n_tiles);
     kern<<<(unsigned)grid, REC_WARPS * 32, L::bytes, st>>>(grad_out, n, n_tiles, U, flags, rot, sca, grad_C);
     return check_launch("reconstruct_bwd_fast");
   }

@@ -1,4 +1,4 @@
-"""ADE / FDE -- drop-in for ``utils/metrics.py:73-102`` running on libet_b200.so."""
+"""ADE / FDE / TCC / COL -- drop-in for ``utils/metrics.py:30-155`` running on libet_b200.so."""
 from __future__ import annotations
 
 from . import ops
@@ -26,3 +26,22 @@ def compute_batch_ade(pred, gt):
 def compute_batch_fde(pred, gt):
     r"""Compute FDE(final displacement error) scores for each pedestrian -> np.ndarray (num_ped,)"""
     return ops.ade_fde(pred, gt)[1].cpu().numpy()
+
+
+def compute_batch_tcc(pred, gt):
+    r"""Compute TCC(temporal correlation coefficient) scores for each pedestrian -> np.ndarray (num_ped,)
+    (utils/metrics.py:105-130; same pass over pred as ADE/FDE)"""
+    return ops.ade_fde(pred, gt, want_tcc=True)[2].cpu().numpy()
+
+
+def compute_batch_col(pred, gt=None):
+    r"""Compute COL(collision rate) scores for each pedestrian -> np.ndarray (num_ped,)
+    (utils/metrics.py:133-155; ``gt`` is unused, as in the reference)"""
+    return ops.col(pred).cpu().numpy()
+
+
+def compute_batch_metric(pred, gt):
+    r"""Get ADE, FDE, COL, TCC scores for each pedestrian (utils/metrics.py:30-70; returns tensors in the
+    reference's order ADEs, FDEs, COLs, TCCs).  pred (S,N,T,2), gt (1,N,T,2) or (N,T,2)."""
+    ade, fde, tcc = ops.ade_fde(pred, gt, want_tcc=True)
+    return ade, fde, ops.col(pred), tcc

@@ -450,8 +450,10 @@ def kmeans_seed_step(data, centroids, ncols):
 # ----------------------------------------------------------------------------------------
 # metrics (utils/metrics.py)
 # ----------------------------------------------------------------------------------------
-def ade_fde(pred, gt, want_argmin=False):
-    """min-over-samples ADE and FDE per pedestrian in one pass.  pred (S,N,T,2), gt (N,T,2)|(1,N,T,2)."""
+def ade_fde(pred, gt, want_argmin=False, want_tcc=False):
+    """min-over-samples ADE and FDE per pedestrian in one pass (optionally + arg-min of FDE and the TCC).
+
+    pred (S,N,T,2), gt (N,T,2)|(1,N,T,2) -> (ade, fde[, argmin][, tcc])."""
     p = to_dev(pred)
     g = to_dev(gt).to(p.device)
     if g.dim() == 4:
@@ -462,5 +464,22 @@ def ade_fde(pred, gt, want_argmin=False):
     ade = torch.empty((n,), device=p.device)
     fde = torch.empty((n,), device=p.device)
     arg = torch.empty((n,), dtype=torch.int32, device=p.device) if want_argmin else None
-    check(load().et_ade_fde(ptr(p), ptr(g), s, n, t, ptr(ade), ptr(fde), ptr(arg), stream_of(p.device)), "et_ade_fde")
-    return (ade, fde, arg) if want_argmin else (ade, fde)
+    tcc = torch.empty((n,), device=p.device) if want_tcc else None
+    check(load().et_ade_fde(ptr(p), ptr(g), s, n, t, ptr(ade), ptr(fde), ptr(arg), ptr(tcc), stream_of(p.device)),
+          "et_ade_fde")
+    out = [ade, fde]
+    if want_argmin:
+        out.append(arg)
+    if want_tcc:
+        out.append(tcc)
+    return tuple(out)
+
+
+def col(pred, thres=0.2):
+    """Collision rate per pedestrian of ONE scene: pred (S,N,T,2) -> (N,) percent."""
+    p = to_dev(pred)
+    s, n, t, c = p.shape
+    assert c == 2
+    out = torch.empty((n,), device=p.device)
+    check(load().et_col(ptr(p), s, n, t, float(thres), ptr(out), stream_of(p.device)), "et_col")
+    return out

@@ -192,10 +192,16 @@ int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d,
                         int k_clusters, int ncols, unsigned long long* key_out, et_stream_t stream);
 
 /* ---- metrics: utils/metrics.py ---------------------------------------------------------- */
-/* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass.
- * pred (S,N,T,2), gt (N,T,2); ade (N), fde (N) float; argmin_fde (N) int32 optional. */
+/* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass, optionally with
+ * compute_batch_tcc (metrics.py:105-130) from the same read of pred.
+ * pred (S,N,T,2), gt (N,T,2); ade (N), fde (N) float; argmin_fde (N) int32 optional;
+ * tcc (N) float optional (T >= 2). */
 int et_ade_fde(const float* pred, const float* gt, int s, int64_t n, int t, float* ade,
-               float* fde, int32_t* argmin_fde, et_stream_t stream);
+               float* fde, int32_t* argmin_fde, float* tcc, et_stream_t stream);
+/* compute_batch_col (metrics.py:133-155): all N pedestrians are one scene; col (N) = percent of
+ * samples in which the pedestrian comes within `thres` (reference: 0.2) of another one during
+ * the first 14 quarter-frame interpolated steps. */
+int et_col(const float* pred, int s, int64_t n, int t, float thres, float* col, et_stream_t stream);
 
 #ifdef __cplusplus
 }

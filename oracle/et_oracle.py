@@ -276,6 +276,38 @@ def ade_fde(pred, gt):
     return ade, fde, arg
 
 
+def tcc(pred, gt):
+    """``utils/metrics.py:105-130``: temporal correlation coefficient of the best-FDE sample with the ground truth.
+
+    pred (S,N,T,2), gt (N,T,2) or (1,N,T,2) -> (N,)."""
+    gt = gt.squeeze(dim=0) if gt.dim() == 4 else gt
+    temp = (pred - gt).norm(p=2, dim=-1)
+    pred_best = pred[temp[:, :, -1].argmin(dim=0), range(pred.size(1)), :, :]
+    stack = torch.stack([pred_best, gt], dim=0).permute(3, 1, 0, 2)          # (xy, N, {pred, gt}, T)
+    cov = stack - stack.mean(dim=-1, keepdim=True)
+    factor = 1 / (cov.shape[-1] - 1)
+    cov = factor * cov @ cov.transpose(-1, -2)
+    std = cov.diagonal(offset=0, dim1=-2, dim2=-1).sqrt()
+    corr = (cov / std.unsqueeze(-1) / std.unsqueeze(-2)).clamp(-1, 1)
+    corr[torch.isnan(corr)] = 0
+    return corr[:, :, 0, 1].mean(dim=0)
+
+
+def col(pred, num_interp=4, thres=0.2):
+    """``utils/metrics.py:133-155``: per-pedestrian collision rate (percent of samples in which the pedestrian comes
+    within ``thres`` of another one of the same scene during the first 3.25 interpolated steps).  pred (S,N,T,2) -> (N,)."""
+    pred = pred.permute(0, 2, 1, 3)
+    fp = pred[:, [0], :, :]
+    rel = pred[:, 1:] - pred[:, :-1]
+    rel_dense = rel.div(num_interp).unsqueeze(dim=2).repeat_interleave(repeats=num_interp, dim=2).contiguous()
+    rel_dense = rel_dense.reshape(pred.size(0), num_interp * (pred.size(1) - 1), pred.size(2), pred.size(3))
+    dense = torch.cat([fp, rel_dense], dim=1).cumsum(dim=1)
+    m = dense[:, :3 * num_interp + 2].unsqueeze(dim=2).repeat_interleave(repeats=pred.size(2), dim=2)
+    m = (m - m.transpose(2, 3)).norm(p=2, dim=-1)
+    m = m.add(torch.eye(n=pred.size(2))[None, None, :, :].to(m.dtype)).min(dim=1)[0].lt(thres)
+    return m.sum(dim=1).gt(0).type(pred.dtype).mean(dim=0).mul(100)
+
+
 def forward_losses(C_pred, C_pred_gt, recon, pred_gt):
     """``EigenTrajectory/model.py:119-123``: the three training-loss scalars."""
     e_c = (C_pred - C_pred_gt.unsqueeze(-1)).norm(p=2, dim=0)

@@ -9,11 +9,24 @@ lib = et.load_library()
 n = 200_000
 gt = torch.randn(n, 12, 2, device=dev).cumsum(1)
 pred = gt[None] + torch.randn(20, n, 12, 2, device=dev) * 0.4
-for cfg in (13, 14, 15, 16, 17, 13):
-    lib.et_tune(0, cfg)
-    a, m = time_op(lambda: ops.ade_fde(pred, gt), reps=30)
-    print(f"ADE config {cfg}: avg {1e3*a:.1f} us min {1e3*m:.1f} us -> {n*2024/(a*1e-3)/1e9:.0f} GB/s ({100*n*2024/(a*1e-3)/1e9/6549.1:.1f}%)")
-lib.et_tune(0, 0)
+from eigentrajectory_b200.synthetic import synthetic_trajectories as syn
+o20, p20 = (x.to(dev) for x in syn(n, seed=1))
+hp = et.DotDict(obs_len=8, pred_len=12, k=6, num_samples=20, traj_dim=2, static_dist=0.3)
+dd = et.ETDescriptor(hp).to(dev); dd.parameter_initialization(o20, p20)
+Up = dd.U_pred_trunc.detach()
+_, _, state = ops.project(o20, p20, dd.U_obs_trunc, Up)
+C20 = torch.randn(6, n, 20, device=dev)
+anchor = torch.randn(6, 20, device=dev)
+from eigentrajectory_b200._lib import ptr, stream_of, check
+rec = ops.reconstruct(C20, Up, state, anchor=anchor); gC = torch.empty_like(C20)
+def bwd():
+    check(lib.et_reconstruct_bwd(ptr(rec), n, 20, 6, 12, ptr(Up), 7, ptr(state[1]), ptr(state[2]), ptr(gC), stream_of(dev)), "bwd")
+for knob in (0, -1, 4, 3, 2, 0):
+    lib.et_tune(1, knob)
+    a, m = time_op(lambda: ops.reconstruct(C20, Up, state, anchor=anchor), reps=30)
+    a2, m2 = time_op(bwd, reps=30)
+    print(f"REC knob {knob}: fwd avg {1e3*a:.1f} us ({100*n*2428/(a*1e-3)/1e9/6549.1:.1f}%)   bwd avg {1e3*a2:.1f} us ({100*n*2420/(a2*1e-3)/1e9/6549.1:.1f}%)")
+lib.et_tune(1, 0)
 # projection, new TMA pipeline
 from eigentrajectory_b200.synthetic import synthetic_trajectories
 N = 1_000_000

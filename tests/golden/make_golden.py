@@ -27,7 +27,7 @@ from EigenTrajectory import EigenTrajectory, TrajNorm            # noqa: E402  (
 from EigenTrajectory.descriptor import ETDescriptor              # noqa: E402
 from EigenTrajectory.anchor import ETAnchor                      # noqa: E402
 from EigenTrajectory.kmeans import BatchKMeans                   # noqa: E402
-from utils.metrics import compute_batch_ade, compute_batch_fde   # noqa: E402
+from utils.metrics import compute_batch_ade, compute_batch_fde, compute_batch_tcc, compute_batch_col   # noqa: E402
 from utils.utils import DotDict, augment_trajectory              # noqa: E402
 from utils.dataloader import TrajectoryDataset                   # noqa: E402
 
@@ -187,8 +187,15 @@ def metrics():
     g = torch.Generator().manual_seed(99)
     gt = torch.randn(300, 12, 2, generator=g).cumsum(1)
     pred = gt[None] + torch.randn(20, 300, 12, 2, generator=g) * 0.4
+    # a crowded scene for the collision metric: 48 pedestrians walking through a 6 m x 6 m area
+    p0 = torch.rand(48, 1, 2, generator=g) * 6
+    v = torch.randn(48, 1, 2, generator=g) * 0.4
+    scene_gt = p0 + v * torch.arange(12)[None, :, None]
+    scene_pred = scene_gt[None] + torch.randn(20, 48, 12, 2, generator=g) * 0.15
     save("metrics.npz", pred=npy(pred), gt=npy(gt), ade=compute_batch_ade(pred, gt),
-         fde=compute_batch_fde(pred, gt[None]))
+         fde=compute_batch_fde(pred, gt[None]), tcc=compute_batch_tcc(pred, gt), col=compute_batch_col(pred, gt),
+         scene_pred=npy(scene_pred), scene_gt=npy(scene_gt), scene_col=compute_batch_col(scene_pred, scene_gt),
+         scene_tcc=compute_batch_tcc(scene_pred, scene_gt[None]))
 
 
 def model_forward():

@@ -296,6 +296,29 @@ def test_ade_fde_vs_oracle(et, O, n, s, tlen):
     assert float(z_ade.abs().max()) == 0.0 and float(z_fde.abs().max()) == 0.0
 
 
+def test_tcc_col_golden(et, O):
+    g = load_golden("metrics")
+    for pk, gk, tk, ck in (("pred", "gt", "tcc", "col"), ("scene_pred", "scene_gt", "scene_tcc", "scene_col")):
+        pred, gt = t(g[pk]).cuda(), t(g[gk]).cuda()
+        tcc = et.compute_batch_tcc(pred, gt)
+        col = et.compute_batch_col(pred, gt)
+        assert tcc.dtype == np.float32 and tcc.shape == (pred.size(1),)
+        assert np.abs(tcc - g[tk]).max() <= 2e-5, pk           # correlations live in [-1, 1]: absolute tolerance
+        assert np.array_equal(col, g[ck]), pk                  # counts of collisions are exact
+    ade, fde, cols, tccs = et.compute_batch_metric(t(g["scene_pred"]).cuda(), t(g["scene_gt"]).cuda()[None])
+    assert np.array_equal(cols.cpu().numpy(), g["scene_col"]) and np.abs(tccs.cpu().numpy() - g["scene_tcc"]).max() <= 2e-5
+    # generic-T path and ragged N against the oracle; constant series -> 0 like the reference's NaN rule
+    gen = torch.Generator().manual_seed(5)
+    for n, s, tlen in ((1, 20, 12), (33, 7, 12), (130, 20, 8), (300, 3, 5)):
+        gt = (torch.rand(n, 1, 2, generator=gen) * 4 + torch.randn(n, tlen, 2, generator=gen).cumsum(1) * 0.3)
+        pred = gt[None] + torch.randn(s, n, tlen, 2, generator=gen) * 0.2
+        gt[0] = 0.0                                               # a standing pedestrian: zero variance -> 0/0
+        tcc = et.compute_batch_tcc(pred.cuda(), gt.cuda())
+        assert np.abs(tcc - O.tcc(pred, gt).numpy()).max() <= 2e-5, (n, s, tlen)
+        assert tcc[0] == 0.0
+        assert np.array_equal(et.compute_batch_col(pred.cuda()), O.col(pred).numpy()), (n, s, tlen)
+
+
 def test_ade_fde_nan_propagates(et):
     gt = torch.zeros(40, 12, 2)
     pred = torch.ones(20, 40, 12, 2)

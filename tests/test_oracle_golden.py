@@ -89,6 +89,15 @@ def test_metrics_bit_exact():
     assert np.array_equal(fde.numpy(), g["fde"])
 
 
+def test_tcc_col_bit_exact():
+    g = load_golden("metrics")
+    assert np.array_equal(O.tcc(t(g["pred"]), t(g["gt"])).numpy(), g["tcc"])
+    assert np.array_equal(O.col(t(g["pred"])).numpy(), g["col"])
+    assert np.array_equal(O.col(t(g["scene_pred"])).numpy(), g["scene_col"])
+    assert np.array_equal(O.tcc(t(g["scene_pred"]), t(g["scene_gt"])[None]).numpy(), g["scene_tcc"])
+    assert 0 < g["scene_col"].mean() < 100          # the crowded fixture really has collisions
+
+
 def test_eth_init_spectra_table():
     """frozen singular values of the ETH init matrices; fp32 LAPACK vs fp64 noise floor."""
     g = load_golden("eth_init")
