@@ -91,15 +91,42 @@ __device__ __forceinline__ void best_centroid(const float (&a)[DMAX], int d, flo
   }
 }
 
-template <int DMAX, bool EXACT>
-__device__ __forceinline__ void best_centroid_any(const float (&a)[DMAX], int d, float anorm, const float* cs, int kpitch,
-                                                  const float* bn, int ncols, int kpad, bool nan_possible, float& best,
-                                                  int& label) {
-  // anorm is finite iff every coordinate is (squares are non-negative): one test covers the point
-  if (nan_possible || !(fabsf(anorm) <= 3.0e38f))
-    best_centroid<DMAX, EXACT, true>(a, d, anorm, cs, kpitch, bn, ncols, kpad, best, label);
-  else
-    best_centroid<DMAX, EXACT, false>(a, d, anorm, cs, kpitch, bn, ncols, kpad, best, label);
+// Fast path for PPL points of one lane at once: the centroid rows are read once per group of four columns and feed
+// 4 * PPL independent FMA chains (finite data and centroids only; the caller checks).
+template <int DMAX, bool EXACT, int PPL>
+__device__ __forceinline__ void best_centroid_multi(const float (&a)[PPL][DMAX], int d, const float (&anorm)[PPL],
+                                                    const float* cs, int kpitch, const float* bn, int kpad,
+                                                    float (&best)[PPL], int (&label)[PPL]) {
+#pragma unroll
+  for (int u = 0; u < PPL; ++u) { best[u] = -INFINITY; label[u] = 0; }
+  for (int j0 = 0; j0 < kpad; j0 += 4) {
+    float dot[PPL][4];
+#pragma unroll
+    for (int u = 0; u < PPL; ++u) dot[u][0] = dot[u][1] = dot[u][2] = dot[u][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) {
+      if (EXACT || i < d) {
+        const float4 c4 = *reinterpret_cast<const float4*>(cs + i * kpitch + j0);
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+          dot[u][0] = fmaf(a[u][i], c4.x, dot[u][0]);
+          dot[u][1] = fmaf(a[u][i], c4.y, dot[u][1]);
+          dot[u][2] = fmaf(a[u][i], c4.z, dot[u][2]);
+          dot[u][3] = fmaf(a[u][i], c4.w, dot[u][3]);
+        }
+      }
+    }
+    const float4 b4 = *reinterpret_cast<const float4*>(bn + j0);
+    const float bnv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int u = 0; u < PPL; ++u) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const float y = __fsub_rn(__fsub_rn(__fmul_rn(dot[u][v], 2.0f), anorm[u]), bnv[v]);
+        if (y > best[u]) { best[u] = y; label[u] = j0 + v; }
+      }
+    }
+  }
 }
 
 constexpr int KM_WARPS = 4;                 // warps per block of the seeding kernel and the default assign kernel
@@ -184,47 +211,74 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
     __syncwarp();
   };
 
-  const int64_t stride = (int64_t)gridDim.x * (WARPS * 32);
+  constexpr int PPL = 2;                                   // points per lane and iteration (instruction-level parallelism)
+  const int64_t stride = (int64_t)gridDim.x * (WARPS * 32 * PPL);
   int since_flush = 0;
   // all lanes of a warp iterate together (the loop bound is warp-uniform)
-  float a_next[DMAX];
+  float a_next[PPL][DMAX];
   {
-    const int64_t i0 = (int64_t)blockIdx.x * (WARPS * 32) + warp * 32 + lane;
+    const int64_t b0 = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL);
 #pragma unroll
-    for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
+    for (int u = 0; u < PPL; ++u) {
+      const int64_t i0 = b0 + u * 32 + lane;
+#pragma unroll
+      for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
+    }
   }
-  for (int64_t base = (int64_t)blockIdx.x * (WARPS * 32) + warp * 32; base < n; base += stride) {
-    const int64_t i = base + lane;
-    float a[DMAX];
+  for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL); base < n; base += stride) {
+    float a[PPL][DMAX];
+    int64_t idx[PPL];
 #pragma unroll
-    for (int r = 0; r < DMAX; ++r) a[r] = a_next[r];
-    {   // software prefetch of the next point: its loads are in flight while this one is scored
-      const int64_t in = i + stride;
+    for (int u = 0; u < PPL; ++u) {
+      idx[u] = base + u * 32 + lane;
 #pragma unroll
-      for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
+      for (int r = 0; r < DMAX; ++r) a[u][r] = a_next[u][r];
+      // software prefetch of the next batch: its loads are in flight while this one is scored
+      const int64_t in = idx[u] + stride;
+#pragma unroll
+      for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
     }
-    if (i < n) {
-      float best = 0.f;
-      int label;
-      if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
-        const int64_t li = labels_in[(int64_t)l * n + i];
-        label = (li >= 0 && li < k) ? (int)li : -1;
+    float best[PPL];
+    int label[PPL];
+    if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
+#pragma unroll
+      for (int u = 0; u < PPL; ++u) {
+        best[u] = 0.f;
+        const int64_t li = idx[u] < n ? labels_in[(int64_t)l * n + idx[u]] : -1;
+        label[u] = (li >= 0 && li < k) ? (int)li : -1;
+      }
+    } else {
+      float anorm[PPL];
+      bool finite = !nan_possible;
+#pragma unroll
+      for (int u = 0; u < PPL; ++u) {
+        anorm[u] = sumsq_torch_order<DMAX>(a[u], d, col_is_sequential(idx[u], n));
+        finite = finite && (fabsf(anorm[u]) <= 3.0e38f);   // finite iff every coordinate is
+      }
+      if (finite) {
+        best_centroid_multi<DMAX, EXACT, PPL>(a, d, anorm, cs, KMAX, bn, kpad, best, label);
       } else {
-        const float anorm = sumsq_torch_order<DMAX>(a, d, col_is_sequential(i, n));
-        best_centroid_any<DMAX, EXACT>(a, d, anorm, cs, KMAX, bn, k, kpad, nan_possible, best, label);
-      }
-      if (labels) labels[(int64_t)l * n + i] = label;
-      if (maxsims) maxsims[(int64_t)l * n + i] = best;
-      if (accumulate && label >= 0) {
-        float* slot = lanerec + (label * (d + 1)) * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < DMAX; ++r)
-          if (EXACT || r < d) slot[r * 32] += a[r];
-        slot[d * 32] += 1.0f;
-        sim_acc += (double)best;
+        for (int u = 0; u < PPL; ++u)
+          best_centroid<DMAX, EXACT, true>(a[u], d, anorm[u], cs, KMAX, bn, k, kpad, best[u], label[u]);
       }
     }
-    if (accumulate && ++since_flush == KM_FLUSH_EVERY) {
+#pragma unroll
+    for (int u = 0; u < PPL; ++u) {
+      if (idx[u] < n) {
+        if (labels) labels[(int64_t)l * n + idx[u]] = label[u];
+        if (maxsims) maxsims[(int64_t)l * n + idx[u]] = best[u];
+        if (accumulate && label[u] >= 0) {
+          float* slot = lanerec + (label[u] * (d + 1)) * 32 + lane;
+#pragma unroll
+          for (int r = 0; r < DMAX; ++r)
+            if (EXACT || r < d) slot[r * 32] += a[u][r];
+          slot[d * 32] += 1.0f;
+          sim_acc += (double)best[u];
+        }
+      }
+    }
+    if (accumulate && (since_flush += PPL) >= KM_FLUSH_EVERY) {
       flush();
       since_flush = 0;
     }
@@ -436,7 +490,7 @@ static int km_launch_w(const float* data, const float* centroids, int l, int d, 
   if (per_sm > 8) per_sm = 8;
   int64_t cap = (int64_t)sm_count() * per_sm / l;     // all l * grid.x blocks must be co-resident
   if (cap < 1) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d exceeds the co-resident block budget", l);
-  int64_t gx = (n + KM_THREADS_L - 1) / KM_THREADS_L;
+  int64_t gx = (n + 2 * KM_THREADS_L - 1) / (2 * KM_THREADS_L);     // two points per lane and iteration
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)l);
