@@ -26,6 +26,7 @@ PROTOTYPES = {
     "et_device_info": (_i, [_p, _p, _p]),
     "et_launch_count": (_l, []),
     "et_tune": (_i, [_i, _i]),
+    "et_memcpy_2d_async": (_i, [_p, _sz, _p, _sz, _sz, _sz, _p]),
     "et_norm_params": (_i, [_p, _l, _i, _i, _p, _p, _p, _p]),
     "et_normalize": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p]),
     "et_denormalize": (_i, [_p, _l, _i, _i, _p, _p, _p, _p, _p]),

@@ -104,6 +104,16 @@ const char* et_last_error(void) { return et::g_err; }
 
 int64_t et_launch_count(void) { return et::g_launches.load(std::memory_order_relaxed); }
 
+int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                       et_stream_t stream) {
+  if (rows == 0 || width_bytes == 0) return ET_OK;
+  if (!dst || !src || dst_pitch < width_bytes || src_pitch < width_bytes)
+    return et::fail(ET_ERR_BADARG, "et_memcpy_2d_async: bad pointers or pitches");
+  cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDefault, et::as_stream(stream));
+  if (e != cudaSuccess) return et::fail(ET_ERR_CUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(e));
+  return ET_OK;
+}
+
 int et_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

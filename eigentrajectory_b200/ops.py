@@ -225,7 +225,8 @@ def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, 
     return back_to(rec_obs, obs), back_to(rec_pred, obs), back_to(C_obs, obs), back_to(C_pred, obs)
 
 
-HOST_CHUNK = 131072         # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
+HOST_CHUNK = 131072          # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
+HOST_FIRST_CHUNK = 32768     # a smaller first chunk shortens the pipeline fill
 _side_streams = {}
 
 
@@ -235,6 +236,16 @@ def _streams(device, count=3):
         st = [torch.cuda.Stream(device=device) for _ in range(count)]
         _side_streams[device] = st
     return st
+
+
+def _host_chunks(n):
+    cuts, a = [], 0
+    size = min(HOST_FIRST_CHUNK, HOST_CHUNK)
+    while a < n:
+        b = min(n, a + size)
+        cuts.append((a, b))
+        a, size = b, HOST_CHUNK
+    return cuts
 
 
 def _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coeffs, variant):
@@ -258,11 +269,10 @@ def _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coef
     lib = load()
     for s in streams:
         s.wait_stream(cur)          # U_* were produced on the caller's stream
-    n_chunks = (n + HOST_CHUNK - 1) // HOST_CHUNK
-    for ci in range(n_chunks):
-        a, b = ci * HOST_CHUNK, min(n, (ci + 1) * HOST_CHUNK)
+    for ci, (a, b) in enumerate(_host_chunks(n)):
         m = b - a
         st = streams[ci % len(streams)]
+        sp = C_void_p(st.cuda_stream)
         with torch.cuda.stream(st):
             xo = obs_h[a:b].to(dev, non_blocking=True)
             xp = pred_h[a:b].to(dev, non_blocking=True)
@@ -270,13 +280,14 @@ def _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coef
             co = torch.empty((k, m), device=dev) if want_coeffs else None
             cp = torch.empty((k, m), device=dev) if want_coeffs else None
             check(lib.et_project_reconstruct(ptr(xo), ptr(xp), m, t_obs, t_pred, ptr(Uo), ptr(Up), k, flags, ptr(ro), ptr(rp),
-                                             ptr(co), ptr(cp), variant, C_void_p(st.cuda_stream)), "et_project_reconstruct")
+                                             ptr(co), ptr(cp), variant, sp), "et_project_reconstruct")
             rec_obs[a:b].copy_(ro, non_blocking=True)
             rec_pred[a:b].copy_(rp, non_blocking=True)
-            if want_coeffs:
-                for j in range(k):
-                    C_obs[j, a:b].copy_(co[j], non_blocking=True)
-                    C_pred[j, a:b].copy_(cp[j], non_blocking=True)
+            if want_coeffs:      # (k, m) device block -> columns [a, b) of the (k, N) host matrix: one pitched copy each
+                for host, devbuf in ((C_obs, co), (C_pred, cp)):
+                    check(lib.et_memcpy_2d_async(C_void_p(host.data_ptr() + 4 * a), 4 * n, ptr(devbuf), 4 * m, 4 * m, k, sp),
+                          "et_memcpy_2d_async")
+                    devbuf.record_stream(st)
     for s in streams:
         s.synchronize()             # results live in host memory: they must be complete on return
     return rec_obs, rec_pred, C_obs, C_pred

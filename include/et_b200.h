@@ -60,6 +60,11 @@ int et_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Total number of kernels this library has launched from this process (all threads). */
 int64_t et_launch_count(void);
 
+/* Plumbing for host-buffer callers: asynchronous pitched copy (either direction, pinned host memory
+ * for true asynchrony) of `rows` rows of width_bytes, e.g. a (k, chunk) slice of a (k, N) matrix. */
+int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                       size_t width_bytes, size_t rows, et_stream_t stream);
+
 /* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
  * Results never depend on them. */
 enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_COUNT = 8 };

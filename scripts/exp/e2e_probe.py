@@ -35,7 +35,7 @@ bw(both, n * 192, "H2D + D2H concurrently (192MB)")
 hp = et.DotDict(obs_len=8, pred_len=12, k=6, num_samples=20, traj_dim=2, static_dist=0.3)
 desc = et.ETDescriptor(hp).to(dev)
 desc.parameter_initialization(obs.to(dev), pred.to(dev))
-for chunk in (32768, 65536, 131072, 262144):
+for chunk in (65536, 131072, 262144):
     ops.HOST_CHUNK = chunk
     for wc in (True, False):
         ts = []

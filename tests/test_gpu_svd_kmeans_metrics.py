@@ -369,3 +369,56 @@ def test_model_forward_matches_reference(et):
         assert (U.T @ U - torch.eye(6, dtype=torch.float64)).abs().max() < 1e-6
         assert float((projector(U) - projector(g[key])).norm()) < 5e-5
     assert torch.isfinite(model2.ET_m_anchor.C_anchor).all() and model2.ET_m_anchor.C_anchor.shape == (6, 20)
+
+
+def test_model_forward_empty_groups_and_host_tensors(et):
+    """All-static and all-moving scenes (an empty group on either side) and CPU inputs through the wrapper."""
+    import types
+    g = load_golden("model_forward")
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.W = torch.nn.Parameter(t(g["W"]).clone())
+
+        def forward(self, x):
+            return (self.W.to(x.device) @ x).reshape(6, 20, -1).permute(0, 2, 1)
+
+    hook = types.SimpleNamespace(
+        model_forward_pre_hook=lambda C, o, info=None: torch.cat([C, o], dim=0),
+        model_forward=lambda x, m: m(x),
+        model_forward_post_hook=lambda y, info=None: y)
+    sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd_")}
+    obs, pred = t(g["obs"]), t(g["pred"])
+    ref = None
+    for static_dist in (1e9, 0.0, HP["static_dist"]):       # everybody static / everybody moving / mixed
+        model = et.EigenTrajectory(Stub(), hook, et.DotDict(dict(HP, static_dist=static_dist))).cuda()
+        model.load_state_dict(sd, strict=False)
+        out = model(obs.cuda(), pred.cuda())
+        assert out["recon_traj"].shape == (20, 57, 12, 2)
+        if static_dist == 1e9:
+            assert torch.isfinite(out["recon_traj"]).all() and torch.isfinite(out["loss_euclidean_ade"])
+        out["loss_euclidean_ade"].backward() if torch.isfinite(out["loss_euclidean_ade"]) else None
+        if static_dist == HP["static_dist"]:
+            ref = out["recon_traj"].detach().cpu()
+    # the same mixed scene with host tensors: results come back on the host and agree
+    model_cpu = et.EigenTrajectory(Stub(), hook, et.DotDict(dict(HP)))
+    model_cpu.load_state_dict(sd, strict=False)
+    out = model_cpu(obs, pred)
+    assert not out["recon_traj"].is_cuda
+    assert rel_max(out["recon_traj"].detach(), ref) < 1e-6
+
+
+def test_anchor_generation_quality_vs_sklearn(et):
+    """anchor.py:65-71 uses sklearn KMeans (n_init = 10): parity is statistical -- our inertia must be comparable."""
+    sk = pytest.importorskip("sklearn.cluster")
+    obs, pred, mask = eth_init_groups()
+    d = et.ETDescriptor(et.DotDict(HP), norm_sca=True).cuda()
+    pred_norm, U_pred = d.parameter_initialization(obs[mask].cuda(), pred[mask].cuda())
+    a = et.ETAnchor(et.DotDict(HP)).cuda()
+    a.anchor_generation(pred_norm, U_pred)
+    assert a.C_anchor.shape == (6, 20) and torch.isfinite(a.C_anchor).all()
+    C = d.to_ET_space(pred_norm, U_pred).T.cpu().numpy()                       # (N, 6)
+    ours = ((C[:, None, :] - a.C_anchor.detach().cpu().numpy().T[None]) ** 2).sum(-1).min(1).sum()
+    ref = sk.KMeans(n_clusters=20, random_state=0, init="k-means++", n_init=10).fit(C).inertia_
+    assert ours <= 1.10 * ref, (ours, ref)
