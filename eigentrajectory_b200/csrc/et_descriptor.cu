@@ -819,24 +819,24 @@ extern "C" {
 
 int et_norm_params(const float* obs, int64_t n, int t_obs, int flags, float* ori, float* rot, float* sca,
                    et_stream_t stream) {
+  if (n == 0) return ET_OK;
   ET_REQUIRE(obs || n == 0, ET_ERR_BADARG, "et_norm_params: obs is null");
   ET_REQUIRE(t_obs >= 3 && t_obs <= ET_MAX_T, ET_ERR_UNSUPPORTED, "et_norm_params: T_obs = %d outside [3, %d]", t_obs, ET_MAX_T);
   ET_REQUIRE(n >= 0, ET_ERR_BADARG, "et_norm_params: n < 0");
   ET_REQUIRE(aligned16(obs) && aligned16(rot), ET_ERR_ALIGN, "et_norm_params: pointers must be 16-byte aligned");
-  if (n == 0) return ET_OK;
   norm_params_kernel<<<blocks_for(n, 256), 256, 0, as_stream(stream)>>>(obs, n, t_obs, flags, ori, rot, sca);
   return check_launch("norm_params_kernel");
 }
 
 static int normalize_common(bool fwd, const float* traj, int64_t n, int t, int flags, const float* ori,
                             const float* rot, const float* sca, float* out, et_stream_t stream) {
+  if (n == 0) return ET_OK;
   ET_REQUIRE((traj && out) || n == 0, ET_ERR_BADARG, "et_(de)normalize: null trajectory pointer");
   ET_REQUIRE(t >= 1 && n >= 0, ET_ERR_BADARG, "et_(de)normalize: bad shape");
   ET_REQUIRE(!(flags & ET_NORM_ORI) || ori, ET_ERR_BADARG, "et_(de)normalize: ori flag set but ori is null");
   ET_REQUIRE(!(flags & ET_NORM_ROT) || rot, ET_ERR_BADARG, "et_(de)normalize: rot flag set but rot is null");
   ET_REQUIRE(!(flags & ET_NORM_SCA) || sca, ET_ERR_BADARG, "et_(de)normalize: sca flag set but sca is null");
   ET_REQUIRE(aligned16(traj) && aligned16(out) && aligned16(rot), ET_ERR_ALIGN, "et_(de)normalize: alignment");
-  if (n == 0) return ET_OK;
   if (fwd)
     normalize_points_kernel<true><<<blocks_for(n * t, 256), 256, 0, as_stream(stream)>>>(traj, n, t, flags, ori, rot, sca, out);
   else
@@ -857,8 +857,8 @@ int et_denormalize(const float* traj, int64_t n, int t, int flags, const float* 
 int et_to_et_space(const float* traj, int64_t n, int t, const float* U, int k, float* C, et_stream_t stream) {
   int rc = check_shape(n, t, k);
   if (rc) return rc;
-  ET_REQUIRE((traj && U && C) || n == 0, ET_ERR_BADARG, "et_to_et_space: null pointer");
   if (n == 0) return ET_OK;
+  ET_REQUIRE((traj && U && C) || n == 0, ET_ERR_BADARG, "et_to_et_space: null pointer");
   to_et_space_generic<<<blocks_for(n, 128), 128, 2 * t * k * sizeof(float), as_stream(stream)>>>(traj, n, 2 * t, U, k, C);
   return check_launch("to_et_space_generic");
 }
@@ -867,8 +867,8 @@ int et_to_euclidean_space(const float* C, int64_t ldc_k, int64_t ldc_n, int64_t 
                           float* traj, et_stream_t stream) {
   int rc = check_shape(n, t, k);
   if (rc) return rc;
-  ET_REQUIRE((traj && U && C) || n == 0, ET_ERR_BADARG, "et_to_euclidean_space: null pointer");
   if (n == 0) return ET_OK;
+  ET_REQUIRE((traj && U && C) || n == 0, ET_ERR_BADARG, "et_to_euclidean_space: null pointer");
   to_euclidean_generic<<<blocks_for(n, 128), 128, 2 * t * k * sizeof(float), as_stream(stream)>>>(C, ldc_k, ldc_n, n, 2 * t, U, k, traj);
   return check_launch("to_euclidean_generic");
 }
@@ -880,10 +880,10 @@ int et_project(const float* obs, const float* pred, int64_t n, int t_obs, int t_
   if (rc) return rc;
   if (pred && (rc = check_shape(n, t_pred, k))) return rc;
   ET_REQUIRE(t_obs >= 3, ET_ERR_UNSUPPORTED, "et_project: T_obs = %d < 3", t_obs);
+  if (n == 0) return ET_OK;
   ET_REQUIRE((obs && U_obs && C_obs) || n == 0, ET_ERR_BADARG, "et_project: obs / U_obs / C_obs null");
   ET_REQUIRE(!pred || (U_pred && C_pred), ET_ERR_BADARG, "et_project: pred given but U_pred / C_pred null");
   ET_REQUIRE(aligned16(obs) && aligned16(pred) && aligned16(rot), ET_ERR_ALIGN, "et_project: pointers must be 16-byte aligned");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (t_obs == 8 && pred && t_pred == 12 && k == 6 && n >= 4096 && n < ((int64_t)1 << 31) && n % 4 == 0 && aligned16(C_obs) &&
       aligned16(C_pred) && aligned16(ori))
@@ -905,12 +905,12 @@ int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t
   if (rc) return rc;
   if ((rc = check_shape(n, t_pred, k))) return rc;
   ET_REQUIRE(t_obs >= 3, ET_ERR_UNSUPPORTED, "et_project_reconstruct: T_obs = %d < 3", t_obs);
+  if (n == 0) return ET_OK;
   ET_REQUIRE((obs && pred && U_obs && U_pred && rec_obs && rec_pred) || n == 0, ET_ERR_BADARG,
              "et_project_reconstruct: null pointer");
   ET_REQUIRE(aligned16(obs) && aligned16(pred) && aligned16(rec_obs) && aligned16(rec_pred), ET_ERR_ALIGN,
              "et_project_reconstruct: trajectory pointers must be 16-byte aligned");
   ET_REQUIRE(variant >= 0 && variant <= 4, ET_ERR_BADARG, "et_project_reconstruct: variant %d", variant);
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   const bool fast = (t_obs == 8 && t_pred == 12 && k == 6);
   if (!fast) {
@@ -940,12 +940,12 @@ int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k,
   int rc = check_shape(n, t, k);
   if (rc) return rc;
   ET_REQUIRE(s >= 1, ET_ERR_BADARG, "et_reconstruct: S = %d", s);
+  if (n == 0) return ET_OK;
   ET_REQUIRE((C && U && out) || n == 0, ET_ERR_BADARG, "et_reconstruct: null pointer");
   ET_REQUIRE(!(flags & ET_NORM_ORI) || ori, ET_ERR_BADARG, "et_reconstruct: ori flag set but ori is null");
   ET_REQUIRE(!(flags & ET_NORM_ROT) || rot, ET_ERR_BADARG, "et_reconstruct: rot flag set but rot is null");
   ET_REQUIRE(!(flags & ET_NORM_SCA) || sca, ET_ERR_BADARG, "et_reconstruct: sca flag set but sca is null");
   ET_REQUIRE(aligned16(C) && aligned16(out) && aligned16(rot), ET_ERR_ALIGN, "et_reconstruct: pointers must be 16-byte aligned");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (k == 6 && t == 12 && s == 20 && n >= 32) {
     using L = RecSmem<6, 12, 20>;
@@ -966,11 +966,11 @@ int et_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t, co
   int rc = check_shape(n, t, k);
   if (rc) return rc;
   ET_REQUIRE(s >= 1, ET_ERR_BADARG, "et_reconstruct_bwd: S = %d", s);
+  if (n == 0) return ET_OK;
   ET_REQUIRE((grad_out && U && grad_C) || n == 0, ET_ERR_BADARG, "et_reconstruct_bwd: null pointer");
   ET_REQUIRE(!(flags & ET_NORM_ROT) || rot, ET_ERR_BADARG, "et_reconstruct_bwd: rot flag set but rot is null");
   ET_REQUIRE(!(flags & ET_NORM_SCA) || sca, ET_ERR_BADARG, "et_reconstruct_bwd: sca flag set but sca is null");
   ET_REQUIRE(aligned16(grad_out) && aligned16(grad_C) && aligned16(rot), ET_ERR_ALIGN, "et_reconstruct_bwd: alignment");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (k == 6 && t == 12 && s == 20 && n >= 32) {
     using L = RecSmem<6, 12, 20>;

@@ -575,9 +575,9 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
                      const int32_t* status, et_stream_t stream) {
   int rc = km_check(l, d, n, k_clusters);
   if (rc) return rc;
+  if (n == 0) return ET_OK;
   ET_REQUIRE((data && centroids) || n == 0, ET_ERR_BADARG, "et_kmeans_assign: data / centroids null");
   ET_REQUIRE(!sums || (counts && workspace), ET_ERR_BADARG, "et_kmeans_assign: sums given without counts / workspace");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   return km_dispatch(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status, nullptr, st);
 }
@@ -586,9 +586,9 @@ int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d,
                          double* sums, double* counts, void* workspace, et_stream_t stream) {
   int rc = km_check(l, d, n, k_clusters);
   if (rc) return rc;
+  if (n == 0) return ET_OK;
   ET_REQUIRE((data && labels) || n == 0, ET_ERR_BADARG, "et_kmeans_accumulate: data / labels null");
   ET_REQUIRE(sums && counts && workspace, ET_ERR_BADARG, "et_kmeans_accumulate: sums / counts / workspace null");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   return km_dispatch(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr, labels, st);
 }
@@ -627,10 +627,10 @@ int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d,
                         unsigned long long* key_out, et_stream_t stream) {
   int rc = km_check(l, d, n, k_clusters);
   if (rc) return rc;
-  ET_REQUIRE(data && centroids && key_out, ET_ERR_BADARG, "et_kmeans_seed_step: null pointer");
+  ET_REQUIRE(key_out && (n == 0 || (data && centroids)), ET_ERR_BADARG, "et_kmeans_seed_step: null pointer");
   ET_REQUIRE(ncols >= 1 && ncols < k_clusters, ET_ERR_BADARG, "et_kmeans_seed_step: ncols = %d outside [1, K)", ncols);
   cudaStream_t st = as_stream(stream);
-  fill_u64_kernel<<<(l + 255) / 256, 256, 0, st>>>(key_out, l, ~0ull);
+  fill_u64_kernel<<<(l + 255) / 256, 256, 0, st>>>(key_out, l, ~0ull);   // an empty shard proposes "no candidate"
   if ((rc = check_launch("fill_u64_kernel"))) return rc;
   if (n == 0) return ET_OK;
   dim3 grid(km_grid(n), l);

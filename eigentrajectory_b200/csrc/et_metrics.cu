@@ -293,8 +293,8 @@ using namespace et;
 
 extern "C" int et_col(const float* pred, int s, int64_t n, int t, float thres, float* col, et_stream_t stream) {
   ET_REQUIRE(n >= 0 && s >= 1 && t >= 1, ET_ERR_BADARG, "et_col: bad shape (S=%d, N=%lld, T=%d)", s, (long long)n, t);
-  ET_REQUIRE((pred && col) || n == 0, ET_ERR_BADARG, "et_col: null pointer");
   if (n == 0) return ET_OK;
+  ET_REQUIRE((pred && col) || n == 0, ET_ERR_BADARG, "et_col: null pointer");
   const int avail = 4 * (t - 1) + 1;                 // dense steps that exist
   const int steps = avail < COL_STEPS ? avail : COL_STEPS;
   col_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, as_stream(stream)>>>(pred, s, n, t, steps, thres, col);
@@ -304,9 +304,9 @@ extern "C" int et_col(const float* pred, int s, int64_t n, int t, float thres, f
 extern "C" int et_ade_fde(const float* pred, const float* gt, int s, int64_t n, int t, float* ade, float* fde,
                           int32_t* argmin_fde, float* tcc, et_stream_t stream) {
   ET_REQUIRE(n >= 0 && s >= 1 && t >= 1, ET_ERR_BADARG, "et_ade_fde: bad shape (S=%d, N=%lld, T=%d)", s, (long long)n, t);
+  if (n == 0) return ET_OK;
   ET_REQUIRE((pred && gt && ade && fde) || n == 0, ET_ERR_BADARG, "et_ade_fde: null pointer");
   ET_REQUIRE(aligned16(pred) && aligned16(gt), ET_ERR_ALIGN, "et_ade_fde: pred / gt must be 16-byte aligned");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (t == 12 && n >= 32) {
     const int64_t n_tiles = (n + 31) / 32;

@@ -486,10 +486,10 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
   ET_REQUIRE(t_obs >= 1 && t_obs <= ET_MAX_T && (!pred || (t_pred >= 1 && t_pred <= ET_MAX_T)), ET_ERR_UNSUPPORTED,
              "et_gram: T outside [1, %d]", ET_MAX_T);
   ET_REQUIRE(!flags || t_obs >= 3, ET_ERR_UNSUPPORTED, "et_gram: normalisation needs T_obs >= 3");
+  if (n == 0) return ET_OK;
   ET_REQUIRE((obs && G_obs) || n == 0, ET_ERR_BADARG, "et_gram: obs / G_obs null");
   ET_REQUIRE(!pred || G_pred, ET_ERR_BADARG, "et_gram: pred given but G_pred null");
   ET_REQUIRE(aligned16(obs) && aligned16(pred), ET_ERR_ALIGN, "et_gram: trajectory pointers must be 16-byte aligned");
-  if (n == 0) return ET_OK;
   cudaStream_t st = as_stream(stream);
   if (t_obs == 8 && (!pred || t_pred == 12)) {
     ET_REQUIRE(workspace, ET_ERR_BADARG, "et_gram: workspace of et_gram_workspace_bytes() zero-initialised bytes required");
