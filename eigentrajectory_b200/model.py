@@ -3,8 +3,10 @@
 The caller of the hot path: it keeps the reference's constructor, ``calculate_parameters`` and
 ``forward`` (including the three predictor hook calls at model.py:93-95) so any ``baseline/``
 predictor plugs in unchanged, and routes projection / anchor + reconstruction through the CUDA
-kernels.  The static/moving split is still boolean-mask indexing (device plumbing); fusing it
-away is the next row of the scope table.
+kernels.  ``forward`` has two implementations with identical results: the default ``fused`` one
+decides moving/static per pedestrian inside the kernels (two launches, no boolean-mask gathers and
+no host synchronisation -- SURVEY.md section 8f-1); ``fused = False`` follows the reference's
+gather / scatter structure group by group.
 """
 from __future__ import annotations
 
@@ -41,6 +43,11 @@ class EigenTrajectory(nn.Module):
         self.ET_s_descriptor = ETDescriptor(hyper_params=hyper_params, norm_sca=False)
         self.ET_m_anchor = ETAnchor(hyper_params=hyper_params)
         self.ET_s_anchor = ETAnchor(hyper_params=hyper_params)
+        self.fused = True
+
+    def _can_fuse(self):
+        tm, ts = self.ET_m_descriptor.traj_normalizer, self.ET_s_descriptor.traj_normalizer
+        return (self.fused and (tm.ori, tm.rot, tm.sca) == (True, True, True) and (ts.ori, ts.rot, ts.sca) == (True, True, False))
 
     def _moving_mask(self, obs_traj):
         return (obs_traj[:, -1] - obs_traj[:, -3]).div(2).norm(p=2, dim=-1) > self.static_dist
@@ -70,6 +77,8 @@ class EigenTrajectory(nn.Module):
         Returns:
             output (dict): recon_traj (S,N,T,2) and, when pred_traj is given, the three loss scalars
         """
+        if self._can_fuse():
+            return self._forward_fused(obs_traj, pred_traj, addl_info)
         n_ped = obs_traj.size(0)
         dev = obs_traj.device
 
@@ -116,6 +125,47 @@ class EigenTrajectory(nn.Module):
             C_pred_gt = C_pred_gt.detach()
 
             # Loss calculation
+            error_coefficient = (C_pred - C_pred_gt.unsqueeze(dim=-1)).norm(p=2, dim=0)
+            error_displacement = (pred_traj_recon - pred_traj.unsqueeze(dim=0)).norm(p=2, dim=-1)
+            output["loss_eigentraj"] = error_coefficient.min(dim=-1)[0].mean()
+            output["loss_euclidean_ade"] = error_displacement.mean(dim=-1).min(dim=0)[0].mean()
+            output["loss_euclidean_fde"] = error_displacement[:, :, -1].min(dim=0)[0].mean()
+
+        return output
+
+    def _forward_fused(self, obs_traj, pred_traj=None, addl_info=None):
+        r"""Same results as ``forward`` with ``fused = False``; the moving/static decision, both projections, the
+        anchor add and both reconstructions happen inside two kernels."""
+        from . import ops
+        dm, ds = self.ET_m_descriptor, self.ET_s_descriptor
+        C_obs, C_pred_gt, state, moving = ops.forward_project(
+            obs_traj, pred_traj, dm.U_obs_trunc, ds.U_obs_trunc, dm.U_pred_trunc, ds.U_pred_trunc, self.static_dist)
+        C_obs, C_pred_gt = ops.back_to(C_obs, obs_traj), ops.back_to(C_pred_gt, obs_traj)
+
+        # Absolute coordinate
+        obs_ori = ops.back_to(state[0], obs_traj).squeeze(dim=1).T.clone()
+        obs_ori -= obs_ori.mean(dim=1, keepdim=True)  # move scene to origin
+
+        # Trajectory prediction (plugin seam, unchanged)
+        input_data = self.hook_func.model_forward_pre_hook(C_obs, obs_ori, addl_info)
+        output_data = self.hook_func.model_forward(input_data, self.baseline_model)
+        C_pred_refine = self.hook_func.model_forward_post_hook(output_data, addl_info)
+        if C_pred_refine.size(2) != self.s:
+            C_pred_refine = C_pred_refine[:, :, :self.s]
+
+        # Anchor refinement + reconstruction
+        am, an = self.ET_m_anchor.C_anchor.detach(), self.ET_s_anchor.C_anchor.detach()
+        pred_traj_recon = ops.forward_reconstruct(C_pred_refine, am, an, dm.U_pred_trunc, ds.U_pred_trunc, moving, state)
+        output = {"recon_traj": pred_traj_recon}
+
+        if pred_traj is not None:
+            mv = ops.back_to(moving, C_pred_refine)
+            anchors = torch.where(mv[None, :, None], am.to(C_pred_refine.device)[:, None, :],
+                                  an.to(C_pred_refine.device)[:, None, :])
+            C_pred = anchors + C_pred_refine
+            C_pred_gt = C_pred_gt.detach().to(C_pred.device)
+
+            # Loss calculation (model.py:119-123)
             error_coefficient = (C_pred - C_pred_gt.unsqueeze(dim=-1)).norm(p=2, dim=0)
             error_displacement = (pred_traj_recon - pred_traj.unsqueeze(dim=0)).norm(p=2, dim=-1)
             output["loss_eigentraj"] = error_coefficient.min(dim=-1)[0].mean()

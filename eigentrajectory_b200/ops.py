@@ -225,6 +225,79 @@ def project_reconstruct(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True, 
     return back_to(rec_obs, obs), back_to(rec_pred, obs), back_to(C_obs, obs), back_to(C_pred, obs)
 
 
+# ----------------------------------------------------------------------------------------
+# EigenTrajectory.forward glue without boolean-mask gathers (EigenTrajectory/model.py:73-105)
+# ----------------------------------------------------------------------------------------
+def forward_project(obs, pred, U_obs_m, U_obs_s, U_pred_m, U_pred_s, static_dist):
+    """Moving/static split + both projections in one launch.
+
+    Returns (C_obs (k,N), C_pred (k,N)|None, (ori, rot, sca) of every row, moving (N,) bool), all on the
+    compute device.  Static rows carry sca = 1."""
+    x = to_dev(obs)
+    n, t_obs = _ntc(x)
+    dev = x.device
+    p = to_dev(pred).to(dev) if pred is not None else None
+    t_pred = p.size(1) if p is not None else 0
+    Uom, Uos = to_dev(U_obs_m).to(dev), to_dev(U_obs_s).to(dev)
+    Upm = to_dev(U_pred_m).to(dev) if p is not None else None
+    Ups = to_dev(U_pred_s).to(dev) if p is not None else None
+    k = Uom.size(1)
+    C_obs = torch.empty((k, n), device=dev)
+    C_pred = torch.empty((k, n), device=dev) if p is not None else None
+    ori, rot, sca = torch.empty((n, 1, 2), device=dev), torch.empty((n, 2, 2), device=dev), torch.empty((n, 1, 1), device=dev)
+    moving = torch.empty((n,), dtype=torch.uint8, device=dev)
+    check(load().et_forward_project(ptr(x), ptr(p), n, t_obs, t_pred, ptr(Uom), ptr(Uos), ptr(Upm), ptr(Ups), k,
+                                    float(static_dist), ptr(C_obs), ptr(C_pred), ptr(ori), ptr(rot), ptr(sca), ptr(moving),
+                                    stream_of(dev)), "et_forward_project")
+    return C_obs, C_pred, (ori, rot, sca), moving.view(torch.bool)
+
+
+class _ForwardReconstruct(torch.autograd.Function):
+    """out (S,N,T,2) = denormalise(U_g (C + anchor_g)), g = moving[n]; differentiable wrt C only."""
+
+    @staticmethod
+    def forward(ctx, C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca):
+        k, n, s = C.shape
+        t = U_m.size(0) // 2
+        out = torch.empty((s, n, t, 2), device=C.device)
+        check(load().et_forward_reconstruct(ptr(C), ptr(anchor_m), ptr(anchor_s), n, s, k, t, ptr(U_m), ptr(U_s), ptr(moving),
+                                            ptr(ori), ptr(rot), ptr(sca), ptr(out), stream_of(C.device)),
+              "et_forward_reconstruct")
+        ctx.save_for_backward(U_m, U_s, moving, rot, sca)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        U_m, U_s, moving, rot, sca = ctx.saved_tensors
+        g = grad_out.contiguous()
+        s, n, t, _ = g.shape
+        k = U_m.size(1)
+        grad_C = torch.empty((k, n, s), device=g.device)
+        check(load().et_forward_reconstruct_bwd(ptr(g), n, s, k, t, ptr(U_m), ptr(U_s), ptr(moving), ptr(rot), ptr(sca),
+                                                ptr(grad_C), stream_of(g.device)), "et_forward_reconstruct_bwd")
+        return (grad_C,) + (None,) * 8
+
+
+def forward_reconstruct(C_pred, anchor_m, anchor_s, U_m, U_s, moving, state):
+    """Anchor refinement + reconstruction of the moving and static rows in one launch (autograd wrt C_pred)."""
+    dev = state[0].device
+    like = C_pred
+    Cd = C_pred if C_pred.is_cuda else C_pred.to(dev)
+    Cd = Cd.float().contiguous()
+    args = (to_dev(anchor_m).to(dev), to_dev(anchor_s).to(dev), to_dev(U_m).to(dev), to_dev(U_s).to(dev),
+            moving.view(torch.uint8), *state)
+    if Cd.requires_grad and torch.is_grad_enabled():
+        out = _ForwardReconstruct.apply(Cd, *args)
+    else:
+        out = _ForwardReconstruct.forward(_NoCtx(), Cd.detach(), *args)
+    return back_to(out, like)
+
+
+class _NoCtx:
+    def save_for_backward(self, *a):
+        pass
+
+
 HOST_CHUNK = 131072          # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
 HOST_FIRST_CHUNK = 32768     # a smaller first chunk shortens the pipeline fill
 _side_streams = {}

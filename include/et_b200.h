@@ -124,6 +124,27 @@ int et_project_reconstruct(const float* obs, const float* pred, int64_t n, int t
                            int flags, float* rec_obs, float* rec_pred, float* C_obs,
                            float* C_pred, int variant, et_stream_t stream);
 
+/* ---- EigenTrajectory.forward glue without boolean-mask gathers (model.py:73-105) -------------- */
+/* Per pedestrian: moving iff ||(last - third_last)/2|| > static_dist (model.py:46,73); moving rows are
+ * normalised with ori|rot|sca and projected on U_*_m, static rows with ori|rot on U_*_s -- what
+ * ET_m_descriptor / ET_s_descriptor.projection do on the two gathered groups (model.py:80-83).
+ * Outputs: C_obs (k,N), C_pred (k,N) when pred != null, the normaliser state of every row
+ * (ori (N,1,2), rot (N,2,2), sca (N,1,1) with sca = 1 on static rows) and moving (N) uint8. */
+int et_forward_project(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred,
+                       const float* U_obs_m, const float* U_obs_s, const float* U_pred_m,
+                       const float* U_pred_s, int k, float static_dist, float* C_obs, float* C_pred,
+                       float* ori, float* rot, float* sca, unsigned char* moving, et_stream_t stream);
+/* Anchor refinement + reconstruction of both groups in one launch (model.py:98-105):
+ * out (S,N,T,2) = denormalise(U_g (C[:,n,:] + anchor_g)), g = moving[n].  Anchors (k,S): both or none. */
+int et_forward_reconstruct(const float* C, const float* anchor_m, const float* anchor_s, int64_t n,
+                           int s, int k, int t, const float* U_m, const float* U_s,
+                           const unsigned char* moving, const float* ori, const float* rot,
+                           const float* sca, float* out, et_stream_t stream);
+/* Gradient of et_forward_reconstruct wrt C: grad_C (k,N,S) = U_g^T ((grad_out R) / sca). */
+int et_forward_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, int t,
+                               const float* U_m, const float* U_s, const unsigned char* moving,
+                               const float* rot, const float* sca, float* grad_C, et_stream_t stream);
+
 /* ---- eigen-basis: ETDescriptor.truncated_SVD (descriptor.py:91-114) ------------------ */
 /* One pass over the data: G_obs (2T_obs x 2T_obs) += M_obs M_obs^T and, when pred != null,
  * G_pred += M_pred M_pred^T, in float64 (FP64 tensor-core DMMA on the (8,12) fast path), where

@@ -347,20 +347,25 @@ def test_model_forward_matches_reference(et):
         model_forward=lambda x, m: m(x),
         model_forward_post_hook=lambda y, info=None: y)
     hp = et.DotDict(dict(HP))
-    model = et.EigenTrajectory(Stub(), hook, hp).cuda()
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd_")}
-    missing = model.load_state_dict(sd, strict=False)
-    assert not missing.unexpected_keys
-    assert sorted(k for k in model.state_dict() if k.startswith("ET_")) == sorted(sd)
     obs, pred = t(g["obs"]).cuda(), t(g["pred"]).cuda()
-    out = model(obs, pred)
-    assert rel_max(out["recon_traj"].detach().cpu(), g["recon"]) < TOL
-    for key, ref in (("loss_eigentraj", "loss_eigentraj"), ("loss_euclidean_ade", "loss_ade"), ("loss_euclidean_fde", "loss_fde")):
-        assert abs(float(out[key]) - float(g[ref])) <= TOL * abs(float(g[ref])), key
-    (out["loss_eigentraj"] + out["loss_euclidean_ade"] + out["loss_euclidean_fde"]).backward()
-    assert rel_max(model.baseline_model.W.grad.cpu(), g["grad_W"]) < 2e-5
-    test_out = model(obs)
-    assert rel_max(test_out["recon_traj"].detach().cpu(), g["recon_test"]) < TOL and "loss_eigentraj" not in test_out
+    for fused in (True, False):          # two kernels without mask gathers / the reference's gather-scatter structure
+        model = et.EigenTrajectory(Stub(), hook, hp).cuda()
+        model.fused = fused
+        missing = model.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys
+        assert sorted(k for k in model.state_dict() if k.startswith("ET_")) == sorted(sd)
+        launches = et.launch_count()
+        out = model(obs, pred)
+        launches = et.launch_count() - launches
+        assert launches == (2 if fused else 4), launches
+        assert rel_max(out["recon_traj"].detach().cpu(), g["recon"]) < TOL
+        for key, ref in (("loss_eigentraj", "loss_eigentraj"), ("loss_euclidean_ade", "loss_ade"), ("loss_euclidean_fde", "loss_fde")):
+            assert abs(float(out[key].detach()) - float(g[ref])) <= TOL * abs(float(g[ref])), (key, fused)
+        (out["loss_eigentraj"] + out["loss_euclidean_ade"] + out["loss_euclidean_fde"]).backward()
+        assert rel_max(model.baseline_model.W.grad.cpu(), g["grad_W"]) < 2e-5
+        test_out = model(obs)
+        assert rel_max(test_out["recon_traj"].detach().cpu(), g["recon_test"]) < TOL and "loss_eigentraj" not in test_out
     # calculate_parameters runs end to end on the device and yields orthonormal bases + finite anchors
     model2 = et.EigenTrajectory(Stub(), hook, hp).cuda()
     model2.calculate_parameters(t(g["init_obs"]).cuda(), t(g["init_pred"]).cuda())
@@ -392,15 +397,22 @@ def test_model_forward_empty_groups_and_host_tensors(et):
     obs, pred = t(g["obs"]), t(g["pred"])
     ref = None
     for static_dist in (1e9, 0.0, HP["static_dist"]):       # everybody static / everybody moving / mixed
-        model = et.EigenTrajectory(Stub(), hook, et.DotDict(dict(HP, static_dist=static_dist))).cuda()
-        model.load_state_dict(sd, strict=False)
-        out = model(obs.cuda(), pred.cuda())
-        assert out["recon_traj"].shape == (20, 57, 12, 2)
-        if static_dist == 1e9:
-            assert torch.isfinite(out["recon_traj"]).all() and torch.isfinite(out["loss_euclidean_ade"])
-        out["loss_euclidean_ade"].backward() if torch.isfinite(out["loss_euclidean_ade"]) else None
+        recs = {}
+        for fused in (True, False):
+            model = et.EigenTrajectory(Stub(), hook, et.DotDict(dict(HP, static_dist=static_dist))).cuda()
+            model.fused = fused
+            model.load_state_dict(sd, strict=False)
+            out = model(obs.cuda(), pred.cuda())
+            assert out["recon_traj"].shape == (20, 57, 12, 2)
+            if static_dist == 1e9:
+                assert torch.isfinite(out["recon_traj"]).all() and torch.isfinite(out["loss_euclidean_ade"])
+            if torch.isfinite(out["loss_euclidean_ade"]):
+                out["loss_euclidean_ade"].backward()
+                recs[fused] = (out["recon_traj"].detach().cpu(), model.baseline_model.W.grad.cpu())
+        if len(recs) == 2:                                    # fused and gather/scatter structure agree
+            assert rel_max(recs[True][0], recs[False][0]) < 1e-6 and rel_max(recs[True][1], recs[False][1]) < 1e-5
         if static_dist == HP["static_dist"]:
-            ref = out["recon_traj"].detach().cpu()
+            ref = recs[True][0]
     # the same mixed scene with host tensors: results come back on the host and agree
     model_cpu = et.EigenTrajectory(Stub(), hook, et.DotDict(dict(HP)))
     model_cpu.load_state_dict(sd, strict=False)
