@@ -252,19 +252,22 @@ def forward_project(obs, pred, U_obs_m, U_obs_s, U_pred_m, U_pred_s, static_dist
     return C_obs, C_pred, (ori, rot, sca), moving.view(torch.bool)
 
 
+def _forward_reconstruct_raw(C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca):
+    k, n, s = C.shape
+    t = U_m.size(0) // 2
+    out = torch.empty((s, n, t, 2), device=C.device)
+    check(load().et_forward_reconstruct(ptr(C), ptr(anchor_m), ptr(anchor_s), n, s, k, t, ptr(U_m), ptr(U_s), ptr(moving),
+                                        ptr(ori), ptr(rot), ptr(sca), ptr(out), stream_of(C.device)), "et_forward_reconstruct")
+    return out
+
+
 class _ForwardReconstruct(torch.autograd.Function):
     """out (S,N,T,2) = denormalise(U_g (C + anchor_g)), g = moving[n]; differentiable wrt C only."""
 
     @staticmethod
     def forward(ctx, C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca):
-        k, n, s = C.shape
-        t = U_m.size(0) // 2
-        out = torch.empty((s, n, t, 2), device=C.device)
-        check(load().et_forward_reconstruct(ptr(C), ptr(anchor_m), ptr(anchor_s), n, s, k, t, ptr(U_m), ptr(U_s), ptr(moving),
-                                            ptr(ori), ptr(rot), ptr(sca), ptr(out), stream_of(C.device)),
-              "et_forward_reconstruct")
         ctx.save_for_backward(U_m, U_s, moving, rot, sca)
-        return out
+        return _forward_reconstruct_raw(C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -289,13 +292,8 @@ def forward_reconstruct(C_pred, anchor_m, anchor_s, U_m, U_s, moving, state):
     if Cd.requires_grad and torch.is_grad_enabled():
         out = _ForwardReconstruct.apply(Cd, *args)
     else:
-        out = _ForwardReconstruct.forward(_NoCtx(), Cd.detach(), *args)
+        out = _forward_reconstruct_raw(Cd.detach(), *args)
     return back_to(out, like)
-
-
-class _NoCtx:
-    def save_for_backward(self, *a):
-        pass
 
 
 HOST_CHUNK = 131072          # pedestrians per pipelined chunk of the host-buffer path (multiple of the 128-row tile)
