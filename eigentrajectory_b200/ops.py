@@ -371,10 +371,12 @@ _gram_ws = {}
 
 
 def _gram_workspace(device):
-    ws = _gram_ws.get(device)
+    """Zero-initialised scratch of et_gram, one per (device, stream): concurrent streams never share barrier counters."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _gram_ws.get(key)
     if ws is None:
         ws = torch.zeros(int(load().et_gram_workspace_bytes()), dtype=torch.uint8, device=device)
-        _gram_ws[device] = ws
+        _gram_ws[key] = ws
     return ws
 
 

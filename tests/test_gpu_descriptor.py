@@ -80,6 +80,30 @@ def test_projection_matches_reference(et, tag, sca):
     assert rel_max(rec.cpu(), g[f"rec_pred_{tag}"]) < TOL
 
 
+@pytest.mark.parametrize("n", [4096, 4097, 8192, 100_000, 100_002])
+@pytest.mark.parametrize("sca", [True, False])
+def test_projection_large_batches_vs_oracle(et, O, n, sca):
+    """n >= 4096 with n % 4 == 0 takes the TMA pipeline (coefficients by tensor stores, state by coalesced stores);
+    other sizes the thread-per-row kernel.  Both against the oracle, including the stored normaliser state."""
+    g = load_golden("descriptor_syn")
+    tag = "sca1" if sca else "sca0"
+    d = make_desc(et, g, tag, sca)
+    obs, pred = O.synthetic_trajectories(n, seed=n)
+    C_obs, C_pred = d.projection(obs.cuda(), pred.cuda())
+    o_co, o_cp, (o_ori, o_rot, o_sca) = O.descriptor_projection(obs, pred, t(g[f"U_obs_{tag}"]), t(g[f"U_pred_{tag}"]), True, True, sca)
+    assert rel_max(C_obs.cpu(), o_co) < TOL and rel_max(C_pred.cpu(), o_cp) < TOL
+    tn = d.traj_normalizer
+    assert torch.equal(tn.traj_ori.cpu(), o_ori) and (tn.traj_rot.cpu() - o_rot).abs().max() < 5e-7
+    if sca:
+        assert rel_max(tn.traj_sca.cpu(), o_sca) < 1e-6
+    # the state written by the fused kernel drives reconstruction of the same batch
+    C20 = torch.randn(6, n, 20, generator=torch.Generator().manual_seed(1)) * 0.3
+    if n <= 8192:
+        rec = d.reconstruction(C20.cuda())
+        o_rec = O.descriptor_reconstruction(C20, t(g[f"U_pred_{tag}"]), (o_ori, o_rot, o_sca))
+        assert rel_max(rec.cpu(), o_rec) < TOL
+
+
 @pytest.mark.parametrize("tag,sca", [("sca1", True), ("sca0", False)])
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_project_reconstruct_matches_reference(et, tag, sca, variant):
