@@ -13,3 +13,4 @@ for line in open("gpurun_out/kernels.log"):
     if "avg_ms" in r: print(f"{r['op'][:70]:70s} {1e3*r['avg_ms']:9.1f} us  {r['achieved_gbs']:8.1f} GB/s  {100*r['frac_of_measured_hbm_peak']:5.1f}%")
 PY
 timeout -k 5 300 python bench.py --no-cpu-baseline > gpurun_out/bench_default.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench_default.log | cut -c1-1800
+timeout -k 5 300 python scripts/bench_forward.py > gpurun_out/forward_latency.log 2>&1; echo "forward latency exit $?"; cat gpurun_out/forward_latency.log | cut -c1-200
