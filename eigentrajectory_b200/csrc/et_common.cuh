@@ -133,8 +133,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned nblocks) {
 // Sum element e over n_part partial records (stride rec doubles) with one warp: lanes stride over the
 // partials, fixed shuffle tree => the result depends only on (n_part, data), never on timing.
 __device__ __forceinline__ double warp_fold(const double* partials, int rec, int n_part, int e, int lane) {
-  double s = 0.0;
-  for (int p = lane; p < n_part; p += 32) s += __ldcg(partials + (size_t)p * rec + e);
+  // four independent load/accumulate streams per lane: the L2 round trips overlap instead of forming one chain
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int p = lane;
+  for (; p + 96 < n_part; p += 128) {
+    const double v0 = __ldcg(partials + (size_t)p * rec + e);
+    const double v1 = __ldcg(partials + (size_t)(p + 32) * rec + e);
+    const double v2 = __ldcg(partials + (size_t)(p + 64) * rec + e);
+    const double v3 = __ldcg(partials + (size_t)(p + 96) * rec + e);
+    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+  }
+  for (; p < n_part; p += 32) s0 += __ldcg(partials + (size_t)p * rec + e);
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;

@@ -31,6 +31,7 @@ constexpr int GR_GO = 16 * 16, GR_GP = 24 * 24;
 //
 // Each warp walks its tiles of 32 pedestrians with a one-tile register prefetch: the global loads of tile i+1 are in
 // flight while the DMMA phase of tile i runs, so the fp64 tensor pipe is not left idle behind HBM latency.
+template <int UNROLL>
 __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restrict__ obs, const float* __restrict__ pred,
                                                            int64_t n, int flags, double* __restrict__ G_obs,
                                                            double* __restrict__ G_pred, unsigned* __restrict__ ticket,
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
     fetch(tile + wstride);   // next tile's loads fly during the DMMA phase below
     __syncwarp();
     // 8 k-steps of 4 pedestrians; fragment f holds x[ped 4*ks + t4][8 f + g] (serves as A and as B)
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int ks = 0; ks < 8; ++ks) {
       const float* xr = xw + (4 * ks + t4) * GR_PITCH + g;
       double f[5];
@@ -497,9 +498,15 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     int grid = gram_grid();
     const int64_t need = ((n + 31) / 32 + GR_WARPS - 1) / GR_WARPS;
     if (grid > need) grid = (int)need;
-    cudaError_t ce = launch_cooperative(gram_fast, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred,
-                                        reinterpret_cast<unsigned*>(workspace),
-                                        reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128));
+    unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
+    double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128);
+    cudaError_t ce;
+    switch (tune_get(ET_TUNE_GRAM_UNROLL)) {
+      case 1: ce = launch_cooperative(gram_fast<1>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 4: ce = launch_cooperative(gram_fast<4>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 8: ce = launch_cooperative(gram_fast<8>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      default: ce = launch_cooperative(gram_fast<2>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+    }
     if (ce != cudaSuccess) return fail(ET_ERR_CUDA, "gram_fast: cooperative launch: %s", cudaGetErrorString(ce));
     return check_launch("gram_fast");
   }
