@@ -75,6 +75,45 @@ __device__ __forceinline__ void norm_bwd(float& a, float& b, const NormState& p,
   if (flags & ET_NORM_ORI) { a += p.ox; b += p.oy; }
 }
 
+// Denormalisation as one affine map per pedestrian: out = (a, b) M + o with M = R^T / sca and o = ori folded once, so the
+// per-point cost is four FMAs and no flag tests (differs from scale-then-rotate-then-shift by <= 1 ulp per operation).
+struct AffineBwd {
+  float m00, m01, m10, m11, ox, oy;
+};
+__device__ __forceinline__ AffineBwd make_affine_bwd(const NormState& p, int flags) {
+  const float inv = (flags & ET_NORM_SCA) ? 1.0f / p.sca : 1.0f;
+  AffineBwd t;
+  if (flags & ET_NORM_ROT) { t.m00 = p.r00 * inv; t.m01 = p.r01 * inv; t.m10 = p.r10 * inv; t.m11 = p.r11 * inv; }
+  else { t.m00 = inv; t.m01 = 0.f; t.m10 = 0.f; t.m11 = inv; }
+  t.ox = (flags & ET_NORM_ORI) ? p.ox : 0.f;
+  t.oy = (flags & ET_NORM_ORI) ? p.oy : 0.f;
+  return t;
+}
+__device__ __forceinline__ void affine_bwd(float& a, float& b, const AffineBwd& t) {
+  const float na = fmaf(a, t.m00, fmaf(b, t.m01, t.ox));
+  const float nb = fmaf(a, t.m10, fmaf(b, t.m11, t.oy));
+  a = na; b = nb;
+}
+
+// Normalisation likewise: out = ((a, b) - o) F with F = R * sca (two subtractions + four multiply-adds per point).
+struct AffineFwd {
+  float f00, f01, f10, f11, ox, oy;
+};
+__device__ __forceinline__ AffineFwd make_affine_fwd(const NormState& p, int flags) {
+  const float sc = (flags & ET_NORM_SCA) ? p.sca : 1.0f;
+  AffineFwd t;
+  if (flags & ET_NORM_ROT) { t.f00 = p.r00 * sc; t.f01 = p.r01 * sc; t.f10 = p.r10 * sc; t.f11 = p.r11 * sc; }
+  else { t.f00 = sc; t.f01 = 0.f; t.f10 = 0.f; t.f11 = sc; }
+  t.ox = (flags & ET_NORM_ORI) ? p.ox : 0.f;
+  t.oy = (flags & ET_NORM_ORI) ? p.oy : 0.f;
+  return t;
+}
+__device__ __forceinline__ void affine_fwd(float& a, float& b, const AffineFwd& t) {
+  const float da = a - t.ox, db = b - t.oy;
+  a = fmaf(da, t.f00, db * t.f10);
+  b = fmaf(da, t.f01, db * t.f11);
+}
+
 // Read a stored state (ori (N,1,2), rot (N,2,2), sca (N,1,1)); absent parts are identity.
 __device__ __forceinline__ NormState load_norm_state(const float* ori, const float* rot, const float* sca,
                                                      int64_t i, int flags) {

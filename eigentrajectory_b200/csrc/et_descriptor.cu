@@ -62,9 +62,14 @@ __device__ __forceinline__ void normalize_row(float (&x)[T2], const NormState& s
   for (int t = 0; t < T2 / 2; ++t) norm_fwd(x[2 * t], x[2 * t + 1], st, flags);
 }
 template <int T2>
-__device__ __forceinline__ void denormalize_row(float (&x)[T2], const NormState& st, float inv_sca, int flags) {
+__device__ __forceinline__ void normalize_row(float (&x)[T2], const AffineFwd& af) {
 #pragma unroll
-  for (int t = 0; t < T2 / 2; ++t) norm_bwd(x[2 * t], x[2 * t + 1], st, inv_sca, flags);
+  for (int t = 0; t < T2 / 2; ++t) affine_fwd(x[2 * t], x[2 * t + 1], af);
+}
+template <int T2>
+__device__ __forceinline__ void denormalize_row(float (&x)[T2], const AffineBwd& af) {
+#pragma unroll
+  for (int t = 0; t < T2 / 2; ++t) affine_bwd(x[2 * t], x[2 * t + 1], af);
 }
 
 template <int T2>
@@ -294,14 +299,15 @@ __global__ void __launch_bounds__(128) project_fast(const float* __restrict__ ob
   const NormState st = make_norm_state(xo[2 * TO - 2], xo[2 * TO - 1], xo[2 * TO - 6], xo[2 * TO - 5]);
   store_norm_state(ori, rot, sca, i, st, flags);
   float c[K];
-  normalize_row<2 * TO>(xo, st, flags);
+  const AffineFwd af = make_affine_fwd(st, flags);
+  normalize_row<2 * TO>(xo, af);
   project_row<2 * TO, K>(xo, Uo, c);
 #pragma unroll
   for (int j = 0; j < K; ++j) C_obs[(int64_t)j * n + i] = c[j];
   if (pred) {
     float xp[2 * TP];
     load_row_global<2 * TP>(xp, pred, i);
-    normalize_row<2 * TP>(xp, st, flags);
+    normalize_row<2 * TP>(xp, af);
     project_row<2 * TP, K>(xp, Up, c);
 #pragma unroll
     for (int j = 0; j < K; ++j) C_pred[(int64_t)j * n + i] = c[j];
@@ -327,28 +333,29 @@ __global__ void __launch_bounds__(128, 4) project_reconstruct_direct(
   load_row_global<2 * TO>(xo, obs, i);
   load_row_global<2 * TP>(xp, pred, i);
   const NormState st = make_norm_state(xo[2 * TO - 2], xo[2 * TO - 1], xo[2 * TO - 6], xo[2 * TO - 5]);
-  const float inv_sca = 1.0f / st.sca;
+  const AffineFwd af = make_affine_fwd(st, flags);
+  const AffineBwd ab = make_affine_bwd(st, flags);
   float c[K];
   {
-    normalize_row<2 * TO>(xo, st, flags);
+    normalize_row<2 * TO>(xo, af);
     project_row<2 * TO, K>(xo, Uo, c);
     if (C_obs) {
 #pragma unroll
       for (int j = 0; j < K; ++j) C_obs[(int64_t)j * n + i] = c[j];
     }
     unproject_row<2 * TO, K>(c, Uo, xo);
-    denormalize_row<2 * TO>(xo, st, inv_sca, flags);
+    denormalize_row<2 * TO>(xo, ab);
     store_row_global<2 * TO>(xo, rec_obs, i);
   }
   {
-    normalize_row<2 * TP>(xp, st, flags);
+    normalize_row<2 * TP>(xp, af);
     project_row<2 * TP, K>(xp, Up, c);
     if (C_pred) {
 #pragma unroll
       for (int j = 0; j < K; ++j) C_pred[(int64_t)j * n + i] = c[j];
     }
     unproject_row<2 * TP, K>(c, Up, xp);
-    denormalize_row<2 * TP>(xp, st, inv_sca, flags);
+    denormalize_row<2 * TP>(xp, ab);
     store_row_global<2 * TP>(xp, rec_pred, i);
   }
 }
@@ -482,7 +489,8 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
 
     float co[6], cp[6];
     NormState nst;
-    float inv_sca;
+    AffineFwd af;
+    AffineBwd ab;
     {
       float xo[16];
 #pragma unroll
@@ -491,12 +499,13 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
         xo[4 * c] = v.x; xo[4 * c + 1] = v.y; xo[4 * c + 2] = v.z; xo[4 * c + 3] = v.w;
       }
       nst = make_norm_state(xo[14], xo[15], xo[10], xo[11]);
-      inv_sca = 1.0f / nst.sca;
-      normalize_row<16>(xo, nst, flags);
+      af = make_affine_fwd(nst, flags);
+      ab = make_affine_bwd(nst, flags);
+      normalize_row<16>(xo, af);
       project_row<16, 6>(xo, Uo, co);
       if (RECON) {
         unproject_row<16, 6>(co, Uo, xo);
-        denormalize_row<16>(xo, nst, inv_sca, flags);
+        denormalize_row<16>(xo, ab);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<float4*>(so + (((uint32_t)c << 4) ^ sw64)) =
@@ -515,11 +524,11 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
         const float4 v = *reinterpret_cast<const float4*>(sb + (((uint32_t)c << 4) ^ sw32));
         xp[16 + 4 * c] = v.x; xp[17 + 4 * c] = v.y; xp[18 + 4 * c] = v.z; xp[19 + 4 * c] = v.w;
       }
-      normalize_row<24>(xp, nst, flags);
+      normalize_row<24>(xp, af);
       project_row<24, 6>(xp, Up, cp);
       if (RECON) {
         unproject_row<24, 6>(cp, Up, xp);
-        denormalize_row<24>(xp, nst, inv_sca, flags);
+        denormalize_row<24>(xp, ab);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           *reinterpret_cast<float4*>(sa + (((uint32_t)c << 4) ^ sw64)) =
@@ -564,18 +573,19 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
 //    coefficient block into shared memory once; warp w reconstructs samples w, w+4, ... -- each lane one
 //    pedestrian -- into a warp-private 32 x 96 B slab which one bulk store writes to out[s, n0:n0+32]
 //    (contiguous 3 KB).  Two slabs per warp keep a store in flight while the next sample is computed.
-//    ~41 KB of shared memory per block => five blocks (20 warps) per SM.
+//    The next tile's coefficient block and normaliser state are prefetched while the current tile is computed.
+//    ~57 KB of shared memory per block => four blocks (16 warps) per SM.
 // =======================================================================================
 constexpr int REC_WARPS = 4;
 
-template <int K, int T, int S>
+template <int K, int T, int S, int CBUF = 1>
 struct RecSmem {
   static constexpr int C_FLOATS = K * 32 * S;
   static constexpr int SLAB_FLOATS = 32 * 2 * T;
   static constexpr int U_FLOATS = 2 * T * UPITCH;
   static constexpr int A_FLOATS = K * S;
   static constexpr size_t bytes =
-      128 + (size_t)(C_FLOATS + REC_WARPS * 2 * SLAB_FLOATS + U_FLOATS + A_FLOATS) * 4 + (2 * REC_WARPS + 2) * 8;
+      128 + (size_t)(CBUF * C_FLOATS + REC_WARPS * 2 * SLAB_FLOATS + U_FLOATS + A_FLOATS) * 4 + (2 * REC_WARPS + 2) * 8;
 };
 
 template <int K, int T, int S>
@@ -586,48 +596,63 @@ __global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_fast(const float* 
                                                                    const float* __restrict__ rot,
                                                                    const float* __restrict__ sca,
                                                                    float* __restrict__ out) {
-  using L = RecSmem<K, T, S>;
+  using L = RecSmem<K, T, S, 2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float* Cs = reinterpret_cast<float*>(base);
-  float* slabs = Cs + L::C_FLOATS;
+  float* Cbuf = reinterpret_cast<float*>(base);                 // two tiles: the next one loads while this one computes
+  float* slabs = Cbuf + 2 * L::C_FLOATS;
   float* Us = slabs + REC_WARPS * 2 * L::SLAB_FLOATS;
   float* As = Us + L::U_FLOATS;
-  uint64_t* full = reinterpret_cast<uint64_t*>(As + L::A_FLOATS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(As + L::A_FLOATS);   // full[0], full[1]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_basis<2 * T, K>(Us, U, threadIdx.x, REC_WARPS * 32);
   for (int e = threadIdx.x; e < K * S; e += REC_WARPS * 32) As[e] = anchor ? __ldg(anchor + e) : 0.f;
   if (threadIdx.x == 0) {
-    mbar_init(full, 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
 
-  float* slab = slabs + warp * 2 * L::SLAB_FLOATS;
-  uint32_t parity = 0;
-  int slab_sel = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  auto load_tile = [&](int64_t tile, int buf) {     // thread 0 only
     const int64_t n0 = tile * 32;
     const int rows = (int)((n - n0) < 32 ? (n - n0) : 32);
-    if (threadIdx.x == 0) {
-      mbar_arrive_expect_tx(full, (uint32_t)(K * rows * S * 4));
+    mbar_arrive_expect_tx(&full[buf], (uint32_t)(K * rows * S * 4));
 #pragma unroll
-      for (int j = 0; j < K; ++j)
-        bulk_load(Cs + j * 32 * S, C + ((int64_t)j * n + n0) * S, (uint32_t)(rows * S * 4), full);
-    }
-    const int64_t i = n0 + lane;
-    const NormState st = load_norm_state(ori, rot, sca, i < n ? i : n - 1, flags);
-    const float inv_sca = 1.0f / st.sca;
-    mbar_wait(full, parity);
-    parity ^= 1u;
+    for (int j = 0; j < K; ++j)
+      bulk_load(Cbuf + buf * L::C_FLOATS + j * 32 * S, C + ((int64_t)j * n + n0) * S, (uint32_t)(rows * S * 4), &full[buf]);
+  };
+  auto load_state = [&](int64_t tile) {
+    const int64_t i = tile * 32 + lane;
+    return load_norm_state(ori, rot, sca, i < n ? i : n - 1, flags);
+  };
+
+  float* slab = slabs + warp * 2 * L::SLAB_FLOATS;
+  int slab_sel = 0;
+  int64_t tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  if (threadIdx.x == 0) load_tile(tile, 0);
+  NormState st_next = load_state(tile);
+  for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t n0 = tile * 32;
+    const int rows = (int)((n - n0) < 32 ? (n - n0) : 32);
+    const int64_t next = tile + gridDim.x;
+    // prefetch the next tile: its coefficient block into the other buffer (every warp left it at the end of the previous
+    // iteration) and its normaliser state into registers
+    if (threadIdx.x == 0 && next < n_tiles) load_tile(next, buf ^ 1);
+    const AffineBwd af = make_affine_bwd(st_next, flags);
+    if (next < n_tiles) st_next = load_state(next);
+    const float* Cs = Cbuf + buf * L::C_FLOATS;
+    mbar_wait(&full[buf], (uint32_t)((it >> 1) & 1));
     for (int s = warp; s < S; s += REC_WARPS) {
       float c[K];
 #pragma unroll
       for (int j = 0; j < K; ++j) c[j] = As[j * S + s] + Cs[j * 32 * S + lane * S + s];
       float y[2 * T];
       unproject_row<2 * T, K>(c, Us, y);
-      denormalize_row<2 * T>(y, st, inv_sca, flags);
+      denormalize_row<2 * T>(y, af);
       // the slab about to be overwritten was handed to a bulk store two samples ago
       if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
@@ -643,7 +668,7 @@ __global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_fast(const float* 
       }
       slab_sel ^= 1;
     }
-    __syncthreads();   // every warp has finished reading Cs before the next tile's bulk load overwrites it
+    __syncthreads();   // every warp has finished reading this buffer before the tile after next is loaded into it
   }
   if (lane == 0) bulk_wait_all<0>();
 }
@@ -683,7 +708,11 @@ __global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_bwd_fast(const flo
     const uint32_t slab_bytes = (uint32_t)(rows * 2 * T * 4);
     const int64_t i = n0 + lane;
     const NormState st = load_norm_state(nullptr, rot, sca, i < n ? i : n - 1, flags & ~ET_NORM_ORI);
-    const float inv_sca = 1.0f / st.sca;
+    // d m = (g R) / sca as one 2x2 map per pedestrian
+    const float inv_sca = (flags & ET_NORM_SCA) ? 1.0f / st.sca : 1.0f;
+    const bool rotate = (flags & ET_NORM_ROT) != 0;
+    const float q00 = (rotate ? st.r00 : 1.f) * inv_sca, q10 = (rotate ? st.r10 : 0.f) * inv_sca;
+    const float q01 = (rotate ? st.r01 : 0.f) * inv_sca, q11 = (rotate ? st.r11 : 1.f) * inv_sca;
     if (lane == 0) {
       const uint32_t b = cnt & 1u;
       mbar_arrive_expect_tx(&bar[b], slab_bytes);
@@ -710,13 +739,9 @@ __global__ void __launch_bounds__(REC_WARPS * 32) reconstruct_bwd_fast(const flo
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        float a = g[2 * t], bb = g[2 * t + 1];
-        if (flags & ET_NORM_ROT) {
-          const float na = a * st.r00 + bb * st.r10, nb = a * st.r01 + bb * st.r11;
-          a = na; bb = nb;
-        }
-        if (flags & ET_NORM_SCA) { a *= inv_sca; bb *= inv_sca; }
-        g[2 * t] = a; g[2 * t + 1] = bb;
+        const float a = g[2 * t], bb = g[2 * t + 1];
+        g[2 * t] = fmaf(a, q00, bb * q10);
+        g[2 * t + 1] = fmaf(a, q01, bb * q11);
       }
       float c[K];
       project_row<2 * T, K>(g, Us, c);
@@ -948,7 +973,7 @@ int et_reconstruct(const float* C, const float* anchor, int64_t n, int s, int k,
   ET_REQUIRE(aligned16(C) && aligned16(out) && aligned16(rot), ET_ERR_ALIGN, "et_reconstruct: pointers must be 16-byte aligned");
   cudaStream_t st = as_stream(stream);
   if (k == 6 && t == 12 && s == 20 && n >= 32) {
-    using L = RecSmem<6, 12, 20>;
+    using L = RecSmem<6, 12, 20, 2>;
     auto kern = reconstruct_fast<6, 12, 20>;
     if ((rc = ensure_smem(kern, L::bytes, "reconstruct_fast"))) return rc;
     const int64_t n_tiles = (n + 31) / 32;

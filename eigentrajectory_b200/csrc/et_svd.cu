@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
         x[4 * c] = raw[c].x; x[4 * c + 1] = raw[c].y; x[4 * c + 2] = raw[c].z; x[4 * c + 3] = raw[c].w;
       }
       if (flags && tile * 32 + lane < n) {
-        const NormState st = make_norm_state(x[14], x[15], x[10], x[11]);
+        const AffineFwd af = make_affine_fwd(make_norm_state(x[14], x[15], x[10], x[11]), flags);
 #pragma unroll
-        for (int t = 0; t < 20; ++t) norm_fwd(x[2 * t], x[2 * t + 1], st, flags);
+        for (int t = 0; t < 20; ++t) affine_fwd(x[2 * t], x[2 * t + 1], af);
       }
       float4* row = reinterpret_cast<float4*>(xw + lane * GR_PITCH);
 #pragma unroll

@@ -410,7 +410,7 @@ def test_model_forward_empty_groups_and_host_tensors(et):
                 out["loss_euclidean_ade"].backward()
                 recs[fused] = (out["recon_traj"].detach().cpu(), model.baseline_model.W.grad.cpu())
         if len(recs) == 2:                                    # fused and gather/scatter structure agree
-            assert rel_max(recs[True][0], recs[False][0]) < 1e-6 and rel_max(recs[True][1], recs[False][1]) < 1e-5
+            assert rel_max(recs[True][0], recs[False][0]) < 1e-6 and rel_max(recs[True][1], recs[False][1]) < 3e-5
         if static_dist == HP["static_dist"]:
             ref = recs[True][0]
     # the same mixed scene with host tensors: results come back on the host and agree
