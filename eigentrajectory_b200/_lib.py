@@ -39,6 +39,8 @@ PROTOTYPES = {
     "et_forward_project": (_i, [_p, _p, _l, _i, _i, _p, _p, _p, _p, _i, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
     "et_forward_reconstruct": (_i, [_p, _p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "et_forward_reconstruct_bwd": (_i, [_p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "et_forward_losses": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "et_forward_losses_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "et_gram_workspace_bytes": (_sz, []),
     "et_gram": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p]),
     "et_eig_jacobi": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),

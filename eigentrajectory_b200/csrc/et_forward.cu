@@ -139,6 +139,150 @@ __global__ void forward_reconstruct_bwd_kernel(const float* __restrict__ grad_ou
   }
 }
 
+// ---- the three training losses of model.py:119-123 in one launch -----------------------------------------------
+//   loss_eigentraj     = mean_n min_s || C_pred[:,n,s] - C_gt[:,n] ||_2          (C_pred = anchor_g + C_refine)
+//   loss_euclidean_ade = mean_n min_s mean_t || recon[s,n,t] - gt[n,t] ||_2
+//   loss_euclidean_fde = mean_n min_s        || recon[s,n,T-1] - gt[n,T-1] ||_2
+// One thread per pedestrian scans the S samples (torch.min semantics: first minimum, NaN wins), records the three
+// arg-mins for the backward pass and its three minima; the last block to finish sums the per-pedestrian minima in
+// index order (deterministic) and writes the means.  workspace: one uint32 ticket (zero on entry / exit).
+__device__ __forceinline__ bool takes_min(float v, float best, bool first) {
+  return first || v < best || (v != v && best == best);
+}
+
+__global__ void forward_losses_kernel(const float* __restrict__ C, const float* __restrict__ anchor_m,
+                                      const float* __restrict__ anchor_s, const unsigned char* __restrict__ moving,
+                                      const float* __restrict__ C_gt, const float* __restrict__ recon,
+                                      const float* __restrict__ gt, int64_t n, int s, int k, int t,
+                                      float* __restrict__ per_ped /* 3 x N minima */, int32_t* __restrict__ argmins /* 3 x N */,
+                                      float* __restrict__ losses /* 3 */, unsigned* __restrict__ ticket) {
+  __shared__ unsigned is_last;
+  __shared__ double red[3][128];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float* an = moving[i] ? anchor_m : anchor_s;
+    float cg[ET_MAX_K];
+    for (int j = 0; j < k; ++j) cg[j] = __ldg(C_gt + (int64_t)j * n + i);
+    float b_ec = 0.f, b_ade = 0.f, b_fde = 0.f;
+    int a_ec = 0, a_ade = 0, a_fde = 0;
+    for (int si = 0; si < s; ++si) {
+      float ss = 0.f;
+      for (int j = 0; j < k; ++j) {
+        float v = __ldg(C + ((int64_t)j * n + i) * s + si);
+        if (an) v = __ldg(an + j * s + si) + v;
+        const float df = v - cg[j];
+        ss = fmaf(df, df, ss);
+      }
+      const float ec = sqrtf(ss);
+      const float2* rp = reinterpret_cast<const float2*>(recon) + ((int64_t)si * n + i) * t;
+      const float2* gp = reinterpret_cast<const float2*>(gt) + i * t;
+      float sum = 0.f, last = 0.f;
+      for (int q = 0; q < t; ++q) {
+        const float2 a = __ldg(rp + q), b = __ldg(gp + q);
+        const float dx = a.x - b.x, dy = a.y - b.y;
+        last = sqrtf(fmaf(dy, dy, dx * dx));
+        sum += last;
+      }
+      const float ade = sum / (float)t;
+      if (takes_min(ec, b_ec, si == 0)) { b_ec = ec; a_ec = si; }
+      if (takes_min(ade, b_ade, si == 0)) { b_ade = ade; a_ade = si; }
+      if (takes_min(last, b_fde, si == 0)) { b_fde = last; a_fde = si; }
+    }
+    per_ped[i] = b_ec; per_ped[n + i] = b_ade; per_ped[2 * n + i] = b_fde;
+    argmins[i] = a_ec; argmins[n + i] = a_ade; argmins[2 * n + i] = a_fde;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int m = 0; m < 3; ++m) {
+    double acc = 0.0;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) acc += (double)__ldcg(per_ped + m * n + e);
+    red[m][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double tot = 0.0;
+    for (int q = 0; q < (int)blockDim.x; ++q) tot += red[threadIdx.x][q];
+    losses[threadIdx.x] = (float)(tot / (double)n);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// Gradient of w_ec * loss_eigentraj + w_ade * loss_ade + w_fde * loss_fde wrt C_refine (k,N,S): only the arg-min samples of
+// each pedestrian receive a gradient.  The displacement part goes through d recon / d C = U_g^T ((. R) / sca).
+// accumulate = 0: the thread first zero-fills its pedestrian's (k x S) block; 1: grad_C already holds a dense part.
+__global__ void forward_losses_bwd_kernel(const float* __restrict__ C, const float* __restrict__ anchor_m,
+                                          const float* __restrict__ anchor_s, const unsigned char* __restrict__ moving,
+                                          const float* __restrict__ C_gt, const float* __restrict__ recon,
+                                          const float* __restrict__ gt, int64_t n, int s, int k, int t2,
+                                          const float* __restrict__ U_m, const float* __restrict__ U_s,
+                                          const float* __restrict__ rot, const float* __restrict__ sca,
+                                          const int32_t* __restrict__ argmins, const float* __restrict__ w /* 3 */,
+                                          int accumulate, float* __restrict__ grad_C) {
+  extern __shared__ float Us[];
+  float* Um = Us;
+  float* Usx = Um + t2 * k;
+  stage(Um, U_m, t2 * k);
+  stage(Usx, U_s, t2 * k);
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = t2 / 2;
+  const bool mv = moving[i] != 0;
+  const float* an = mv ? anchor_m : anchor_s;
+  const float* Ub = mv ? Um : Usx;
+  if (!accumulate)
+    for (int j = 0; j < k; ++j)
+      for (int si = 0; si < s; ++si) grad_C[((int64_t)j * n + i) * s + si] = 0.f;
+  const float inv_n = 1.0f / (float)n;
+  const float w_ec = __ldg(w) * inv_n, w_ade = __ldg(w + 1) * inv_n / (float)t, w_fde = __ldg(w + 2) * inv_n;
+  // coefficient loss: d ||v|| / d v = v / ||v|| (0 at v = 0)
+  {
+    const int si = argmins[i];
+    float v[ET_MAX_K], ss = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float c = __ldg(C + ((int64_t)j * n + i) * s + si);
+      if (an) c = __ldg(an + j * s + si) + c;
+      v[j] = c - __ldg(C_gt + (int64_t)j * n + i);
+      ss = fmaf(v[j], v[j], ss);
+    }
+    const float nrm = sqrtf(ss);
+    const float sc = nrm > 0.f ? w_ec / nrm : 0.f;
+    for (int j = 0; j < k; ++j) grad_C[((int64_t)j * n + i) * s + si] += sc * v[j];
+  }
+  // displacement losses: ADE touches every frame of its arg-min sample, FDE the last frame of its own
+  const NormState st = load_norm_state(nullptr, rot, sca, i, ET_NORM_ROT | ET_NORM_SCA);
+  const float inv_sca = 1.0f / st.sca;
+  const float2* gp = reinterpret_cast<const float2*>(gt) + i * t;
+  for (int part = 0; part < 2; ++part) {
+    const int si = argmins[(part + 1) * n + i];
+    const float wt = part ? w_fde : w_ade;
+    const float2* rp = reinterpret_cast<const float2*>(recon) + ((int64_t)si * n + i) * t;
+    float g[FMAX2T];
+    for (int q = 0; q < t; ++q) {
+      float gx = 0.f, gy = 0.f;
+      if (part == 0 || q == t - 1) {
+        const float2 a = __ldg(rp + q), b = __ldg(gp + q);
+        const float dx = a.x - b.x, dy = a.y - b.y;
+        const float d = sqrtf(fmaf(dy, dy, dx * dx));
+        const float sc = d > 0.f ? wt / d : 0.f;
+        gx = sc * dx;
+        gy = sc * dy;
+      }
+      g[2 * q] = (gx * st.r00 + gy * st.r10) * inv_sca;
+      g[2 * q + 1] = (gx * st.r01 + gy * st.r11) * inv_sca;
+    }
+    for (int j = 0; j < k; ++j) {
+      float acc = 0.f;
+      for (int r = 0; r < t2; ++r) acc = fmaf(Ub[r * k + j], g[r], acc);
+      grad_C[((int64_t)j * n + i) * s + si] += acc;
+    }
+  }
+}
+
 static int fwd_check(const char* who, int64_t n, int t, int k) {
   if (n < 0) return fail(ET_ERR_BADARG, "%s: n < 0", who);
   if (t < 1 || t > ET_MAX_T) return fail(ET_ERR_UNSUPPORTED, "%s: T = %d outside [1, %d]", who, t, ET_MAX_T);
@@ -198,6 +342,36 @@ int et_forward_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, i
   forward_reconstruct_bwd_kernel<<<(unsigned)((n * s + 127) / 128), 128, (size_t)2 * 2 * t * k * sizeof(float),
                                    as_stream(stream)>>>(grad_out, n, s, k, 2 * t, U_m, U_s, moving, rot, sca, grad_C);
   return check_launch("forward_reconstruct_bwd_kernel");
+}
+
+int et_forward_losses(const float* C, const float* anchor_m, const float* anchor_s, const unsigned char* moving,
+                      const float* C_gt, const float* recon, const float* gt, int64_t n, int s, int k, int t,
+                      float* per_ped, int32_t* argmins, float* losses, void* workspace, et_stream_t stream) {
+  int rc = fwd_check("et_forward_losses", n, t, k);
+  if (rc) return rc;
+  ET_REQUIRE(s >= 1 && n >= 1, ET_ERR_BADARG, "et_forward_losses: needs S >= 1 and N >= 1 (the mean over N of an empty batch is undefined)");
+  ET_REQUIRE(C && moving && C_gt && recon && gt && per_ped && argmins && losses && workspace, ET_ERR_BADARG,
+             "et_forward_losses: null pointer");
+  ET_REQUIRE((anchor_m == nullptr) == (anchor_s == nullptr), ET_ERR_BADARG, "et_forward_losses: give both anchor sets or none");
+  forward_losses_kernel<<<(unsigned)((n + 127) / 128), 128, 0, as_stream(stream)>>>(
+      C, anchor_m, anchor_s, moving, C_gt, recon, gt, n, s, k, t, per_ped, argmins, losses, reinterpret_cast<unsigned*>(workspace));
+  return check_launch("forward_losses_kernel");
+}
+
+int et_forward_losses_bwd(const float* C, const float* anchor_m, const float* anchor_s, const unsigned char* moving,
+                          const float* C_gt, const float* recon, const float* gt, int64_t n, int s, int k, int t,
+                          const float* U_m, const float* U_s, const float* rot, const float* sca, const int32_t* argmins,
+                          const float* loss_weights, int accumulate, float* grad_C, et_stream_t stream) {
+  int rc = fwd_check("et_forward_losses_bwd", n, t, k);
+  if (rc) return rc;
+  ET_REQUIRE(s >= 1, ET_ERR_BADARG, "et_forward_losses_bwd: S = %d", s);
+  if (n == 0) return ET_OK;
+  ET_REQUIRE(C && moving && C_gt && recon && gt && U_m && U_s && rot && sca && argmins && loss_weights && grad_C, ET_ERR_BADARG,
+             "et_forward_losses_bwd: null pointer");
+  ET_REQUIRE(aligned16(rot), ET_ERR_ALIGN, "et_forward_losses_bwd: rot must be 16-byte aligned");
+  forward_losses_bwd_kernel<<<(unsigned)((n + 127) / 128), 128, (size_t)2 * 2 * t * k * sizeof(float), as_stream(stream)>>>(
+      C, anchor_m, anchor_s, moving, C_gt, recon, gt, n, s, k, 2 * t, U_m, U_s, rot, sca, argmins, loss_weights, accumulate, grad_C);
+  return check_launch("forward_losses_bwd_kernel");
 }
 
 }  // extern "C"

@@ -4,9 +4,10 @@ The caller of the hot path: it keeps the reference's constructor, ``calculate_pa
 ``forward`` (including the three predictor hook calls at model.py:93-95) so any ``baseline/``
 predictor plugs in unchanged, and routes projection / anchor + reconstruction through the CUDA
 kernels.  ``forward`` has two implementations with identical results: the default ``fused`` one
-decides moving/static per pedestrian inside the kernels (two launches, no boolean-mask gathers and
-no host synchronisation -- SURVEY.md section 8f-1); ``fused = False`` follows the reference's
-gather / scatter structure group by group.
+decides moving/static per pedestrian inside the kernels and computes the three training losses in one
+more launch (three launches forward, one or two backward, no boolean-mask gathers and no host
+synchronisation -- SURVEY.md section 8f-1); ``fused = False`` follows the reference's gather / scatter
+structure group by group with the loss reductions as tensor algebra.
 """
 from __future__ import annotations
 
@@ -153,23 +154,17 @@ class EigenTrajectory(nn.Module):
         if C_pred_refine.size(2) != self.s:
             C_pred_refine = C_pred_refine[:, :, :self.s]
 
-        # Anchor refinement + reconstruction
+        # Anchor refinement + reconstruction (+ the three losses of model.py:119-123 when training)
         am, an = self.ET_m_anchor.C_anchor.detach(), self.ET_s_anchor.C_anchor.detach()
-        pred_traj_recon = ops.forward_reconstruct(C_pred_refine, am, an, dm.U_pred_trunc, ds.U_pred_trunc, moving, state)
-        output = {"recon_traj": pred_traj_recon}
-
-        if pred_traj is not None:
-            mv = ops.back_to(moving, C_pred_refine)
-            anchors = torch.where(mv[None, :, None], am.to(C_pred_refine.device)[:, None, :],
-                                  an.to(C_pred_refine.device)[:, None, :])
-            C_pred = anchors + C_pred_refine
-            C_pred_gt = C_pred_gt.detach().to(C_pred.device)
-
-            # Loss calculation (model.py:119-123)
-            error_coefficient = (C_pred - C_pred_gt.unsqueeze(dim=-1)).norm(p=2, dim=0)
-            error_displacement = (pred_traj_recon - pred_traj.unsqueeze(dim=0)).norm(p=2, dim=-1)
-            output["loss_eigentraj"] = error_coefficient.min(dim=-1)[0].mean()
-            output["loss_euclidean_ade"] = error_displacement.mean(dim=-1).min(dim=0)[0].mean()
-            output["loss_euclidean_fde"] = error_displacement[:, :, -1].min(dim=0)[0].mean()
+        if pred_traj is None or obs_traj.size(0) == 0:
+            recon = ops.forward_reconstruct(C_pred_refine, am, an, dm.U_pred_trunc, ds.U_pred_trunc, moving, state)
+            output = {"recon_traj": recon}
+            if pred_traj is not None:     # empty scene: the reference's means over zero pedestrians are NaN
+                nan = recon.new_full((), float("nan"))
+                output.update(loss_eigentraj=nan, loss_euclidean_ade=nan, loss_euclidean_fde=nan)
+            return output
+        recon, l_ec, l_ade, l_fde = ops.forward_reconstruct_losses(
+            C_pred_refine, am, an, dm.U_pred_trunc, ds.U_pred_trunc, moving, state, C_pred_gt, pred_traj)
+        output = {"recon_traj": recon, "loss_eigentraj": l_ec, "loss_euclidean_ade": l_ade, "loss_euclidean_fde": l_fde}
 
         return output

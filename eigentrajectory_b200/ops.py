@@ -281,6 +281,76 @@ class _ForwardReconstruct(torch.autograd.Function):
         return (grad_C,) + (None,) * 8
 
 
+_loss_ws = {}
+
+
+def _loss_workspace(device):
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _loss_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(16, dtype=torch.uint8, device=device)
+        _loss_ws[key] = ws
+    return ws
+
+
+class _ForwardReconLosses(torch.autograd.Function):
+    """(recon, loss_eigentraj, loss_euclidean_ade, loss_euclidean_fde) of model.py:98-123 in two launches; the backward
+    pass is one sparse kernel (only arg-min samples carry gradient) plus the dense reconstruction backward if `recon`
+    itself is used downstream."""
+
+    @staticmethod
+    def forward(ctx, C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca, C_gt, gt):
+        ctx.set_materialize_grads(False)
+        recon = _forward_reconstruct_raw(C, anchor_m, anchor_s, U_m, U_s, moving, ori, rot, sca)
+        k, n, s = C.shape
+        t = recon.size(2)
+        per_ped = torch.empty((3, n), device=C.device)
+        argmins = torch.empty((3, n), dtype=torch.int32, device=C.device)
+        losses = torch.empty((3,), device=C.device)
+        check(load().et_forward_losses(ptr(C), ptr(anchor_m), ptr(anchor_s), ptr(moving), ptr(C_gt), ptr(recon), ptr(gt), n, s, k,
+                                       t, ptr(per_ped), ptr(argmins), ptr(losses), ptr(_loss_workspace(C.device)),
+                                       stream_of(C.device)), "et_forward_losses")
+        ctx.save_for_backward(C, anchor_m, anchor_s, U_m, U_s, moving, rot, sca, C_gt, gt, recon, argmins)
+        return recon, losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, g_recon, g_ec, g_ade, g_fde):
+        C, anchor_m, anchor_s, U_m, U_s, moving, rot, sca, C_gt, gt, recon, argmins = ctx.saved_tensors
+        k, n, s = C.shape
+        t = recon.size(2)
+        lib = load()
+        grad_C = torch.empty((k, n, s), device=C.device)
+        accumulate = 0
+        if g_recon is not None:
+            g = g_recon.contiguous()
+            check(lib.et_forward_reconstruct_bwd(ptr(g), n, s, k, t, ptr(U_m), ptr(U_s), ptr(moving), ptr(rot), ptr(sca),
+                                                 ptr(grad_C), stream_of(C.device)), "et_forward_reconstruct_bwd")
+            accumulate = 1
+        if g_ec is not None or g_ade is not None or g_fde is not None:
+            zero = torch.zeros((), device=C.device)
+            w = torch.stack([zero if v is None else v.float() for v in (g_ec, g_ade, g_fde)])
+            check(lib.et_forward_losses_bwd(ptr(C), ptr(anchor_m), ptr(anchor_s), ptr(moving), ptr(C_gt), ptr(recon), ptr(gt), n,
+                                            s, k, t, ptr(U_m), ptr(U_s), ptr(rot), ptr(sca), ptr(argmins), ptr(w), accumulate,
+                                            ptr(grad_C), stream_of(C.device)), "et_forward_losses_bwd")
+        elif not accumulate:
+            grad_C.zero_()
+        return (grad_C,) + (None,) * 10
+
+
+def forward_reconstruct_losses(C_pred, anchor_m, anchor_s, U_m, U_s, moving, state, C_pred_gt, pred_gt):
+    """Anchor refinement + reconstruction + the three training losses (model.py:98-123).
+
+    Returns (recon (S,N,T,2), loss_eigentraj, loss_euclidean_ade, loss_euclidean_fde); autograd wrt C_pred."""
+    dev = state[0].device
+    like = C_pred
+    Cd = C_pred if C_pred.is_cuda else C_pred.to(dev)
+    Cd = Cd.float().contiguous()
+    args = (to_dev(anchor_m).to(dev), to_dev(anchor_s).to(dev), to_dev(U_m).to(dev), to_dev(U_s).to(dev),
+            moving.view(torch.uint8), *state, to_dev(C_pred_gt).to(dev), to_dev(pred_gt).to(dev))
+    recon, l_ec, l_ade, l_fde = _ForwardReconLosses.apply(Cd, *args)
+    return back_to(recon, like), back_to(l_ec, like), back_to(l_ade, like), back_to(l_fde, like)
+
+
 def forward_reconstruct(C_pred, anchor_m, anchor_s, U_m, U_s, moving, state):
     """Anchor refinement + reconstruction of the moving and static rows in one launch (autograd wrt C_pred)."""
     dev = state[0].device

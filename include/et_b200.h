@@ -145,6 +145,25 @@ int et_forward_reconstruct_bwd(const float* grad_out, int64_t n, int s, int k, i
                                const float* U_m, const float* U_s, const unsigned char* moving,
                                const float* rot, const float* sca, float* grad_C, et_stream_t stream);
 
+/* The three training losses of model.py:119-123 in one launch: losses[3] = {loss_eigentraj,
+ * loss_euclidean_ade, loss_euclidean_fde} (means over N of per-pedestrian minima over S, torch.min
+ * semantics); per_ped (3,N) minima and argmins (3,N) int32 are kept for the backward pass.
+ * C (k,N,S) are the refined coefficients BEFORE the anchor add; C_gt (k,N); recon (S,N,T,2); gt (N,T,2).
+ * workspace: 4 bytes, zero-filled once. */
+int et_forward_losses(const float* C, const float* anchor_m, const float* anchor_s,
+                      const unsigned char* moving, const float* C_gt, const float* recon,
+                      const float* gt, int64_t n, int s, int k, int t, float* per_ped,
+                      int32_t* argmins, float* losses, void* workspace, et_stream_t stream);
+/* grad_C (k,N,S) of sum_m loss_weights[m] * losses[m] (loss_weights: DEVICE float[3], the upstream
+ * gradients of the three scalars): only arg-min samples receive gradient; the displacement terms are
+ * chained through d recon / d C.  accumulate = 0 overwrites grad_C, 1 adds to it. */
+int et_forward_losses_bwd(const float* C, const float* anchor_m, const float* anchor_s,
+                          const unsigned char* moving, const float* C_gt, const float* recon,
+                          const float* gt, int64_t n, int s, int k, int t, const float* U_m,
+                          const float* U_s, const float* rot, const float* sca,
+                          const int32_t* argmins, const float* loss_weights, int accumulate,
+                          float* grad_C, et_stream_t stream);
+
 /* ---- eigen-basis: ETDescriptor.truncated_SVD (descriptor.py:91-114) ------------------ */
 /* One pass over the data: G_obs (2T_obs x 2T_obs) += M_obs M_obs^T and, when pred != null,
  * G_pred += M_pred M_pred^T, in float64 (FP64 tensor-core DMMA on the (8,12) fast path), where

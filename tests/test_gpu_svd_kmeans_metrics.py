@@ -358,7 +358,7 @@ def test_model_forward_matches_reference(et):
         launches = et.launch_count()
         out = model(obs, pred)
         launches = et.launch_count() - launches
-        assert launches == (2 if fused else 4), launches
+        assert launches == (3 if fused else 4), launches          # project + reconstruct + losses | 2 x (project + reconstruct)
         assert rel_max(out["recon_traj"].detach().cpu(), g["recon"]) < TOL
         for key, ref in (("loss_eigentraj", "loss_eigentraj"), ("loss_euclidean_ade", "loss_ade"), ("loss_euclidean_fde", "loss_fde")):
             assert abs(float(out[key].detach()) - float(g[ref])) <= TOL * abs(float(g[ref])), (key, fused)
