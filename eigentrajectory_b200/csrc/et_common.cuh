@@ -150,6 +150,32 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two independent IEEE fp32 operations per instruction) -------
+typedef unsigned long long f32x2_t;   // lo = bits 0..31 (lower address when loaded from memory), hi = bits 32..63
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // ---- grid-wide reduction of per-block partial records (cooperative launches only) --------------
 // One-shot, self-resetting barrier over all blocks of the grid.  ctr[0] = arrivals, ctr[1] = departures; both are
 // zero on entry and zero again on exit.  Needs every block co-resident: launch with launch_cooperative().

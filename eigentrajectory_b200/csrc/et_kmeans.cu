@@ -91,39 +91,73 @@ __device__ __forceinline__ void best_centroid(const float (&a)[DMAX], int d, flo
   }
 }
 
-// Fast path for PPL points of one lane at once: the centroid rows are read once per group of four columns and feed
-// 4 * PPL independent FMA chains (finite data and centroids only; the caller checks).
-template <int DMAX, bool EXACT, int PPL>
-__device__ __forceinline__ void best_centroid_multi(const float (&a)[PPL][DMAX], int d, const float (&anorm)[PPL],
-                                                    const float* cs, int kpitch, const float* bn, int kpad,
-                                                    float (&best)[PPL], int (&label)[PPL]) {
+// Scalar scan against NEGATED centroid norms (nbn), best similarity only: the seeding kernel's path for a point whose own
+// norm is outside the packed fast path's range.
+template <int DMAX, bool EXACT>
+__device__ __forceinline__ void best_centroid_neg(const float (&a)[DMAX], int d, float anorm, const float* cs, int kpitch,
+                                                  const float* nbn, int kpad, float& best) {
+  best = -INFINITY;
+  for (int j = 0; j < kpad; ++j) {
+    float dot = 0.f;
 #pragma unroll
-  for (int u = 0; u < PPL; ++u) { best[u] = -INFINITY; label[u] = 0; }
+    for (int i = 0; i < DMAX; ++i)
+      if (EXACT || i < d) dot = fmaf(a[i], cs[i * kpitch + j], dot);
+    const float y = __fadd_rn(__fsub_rn(__fmul_rn(dot, 2.0f), anorm), nbn[j]);
+    if (y > best) best = y;
+  }
+}
+
+// Fast path for PPL points of one lane at once (finite data and centroids only; the caller checks).  Two centroids
+// per instruction: the data value is duplicated into an fp32 pair and multiplied with the pair (c_j, c_j+1) by one
+// FFMA2, so the 6 x K multiply-adds of a point cost 3 K instructions; 2 dot, - |a|^2, - |b|^2 are FMUL2 / FADD2.  Each
+// half of a packed operation is an ordinary IEEE fp32 operation, hence every similarity keeps the reference's exact
+// rounding sequence (x - y == x + (-y) bit for bit; the centroid norms are staged negated in nbn).
+// KPAD > 0: the padded cluster count is known at compile time and the scan is fully unrolled (shared-memory operands
+// become immediate offsets); KPAD == 0: run-time kpad.  LABELS = false keeps only the best similarity (seeding).
+template <int DMAX, bool EXACT, int PPL, int KPAD, bool LABELS>
+__device__ __forceinline__ void best_centroid_packed(const float (&a)[PPL][DMAX], int d, const float (&anorm)[PPL],
+                                                     const float* cs, int kpitch, const float* nbn, int kpad_rt,
+                                                     float (&best)[PPL], int (&label)[PPL]) {
+  f32x2_t ad[PPL][DMAX], nan2[PPL];
+#pragma unroll
+  for (int u = 0; u < PPL; ++u) {
+#pragma unroll
+    for (int i = 0; i < DMAX; ++i) ad[u][i] = pack2(a[u][i], a[u][i]);
+    nan2[u] = pack2(-anorm[u], -anorm[u]);
+    best[u] = -INFINITY;
+    label[u] = 0;
+  }
+  const f32x2_t two = pack2(2.0f, 2.0f), zero = pack2(0.f, 0.f);
+  const int kpad = KPAD > 0 ? KPAD : kpad_rt;
+#pragma unroll
   for (int j0 = 0; j0 < kpad; j0 += 4) {
-    float dot[PPL][4];
+    f32x2_t dot[PPL][2];
 #pragma unroll
-    for (int u = 0; u < PPL; ++u) dot[u][0] = dot[u][1] = dot[u][2] = dot[u][3] = 0.f;
+    for (int u = 0; u < PPL; ++u) dot[u][0] = dot[u][1] = zero;
 #pragma unroll
     for (int i = 0; i < DMAX; ++i) {
       if (EXACT || i < d) {
-        const float4 c4 = *reinterpret_cast<const float4*>(cs + i * kpitch + j0);
+        const ulonglong2 c4 = *reinterpret_cast<const ulonglong2*>(cs + i * kpitch + j0);
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
-          dot[u][0] = fmaf(a[u][i], c4.x, dot[u][0]);
-          dot[u][1] = fmaf(a[u][i], c4.y, dot[u][1]);
-          dot[u][2] = fmaf(a[u][i], c4.z, dot[u][2]);
-          dot[u][3] = fmaf(a[u][i], c4.w, dot[u][3]);
+          dot[u][0] = fma2(ad[u][i], c4.x, dot[u][0]);
+          dot[u][1] = fma2(ad[u][i], c4.y, dot[u][1]);
         }
       }
     }
-    const float4 b4 = *reinterpret_cast<const float4*>(bn + j0);
-    const float bnv[4] = {b4.x, b4.y, b4.z, b4.w};
+    const ulonglong2 nb4 = *reinterpret_cast<const ulonglong2*>(nbn + j0);
 #pragma unroll
     for (int u = 0; u < PPL; ++u) {
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const float y = __fsub_rn(__fsub_rn(__fmul_rn(dot[u][v], 2.0f), anorm[u]), bnv[v]);
-        if (y > best[u]) { best[u] = y; label[u] = j0 + v; }
+      for (int h = 0; h < 2; ++h) {
+        float y0, y1;
+        unpack2(add2(add2(mul2(dot[u][h], two), nan2[u]), h ? nb4.y : nb4.x), y0, y1);
+        if (LABELS) {
+          if (y0 > best[u]) { best[u] = y0; label[u] = j0 + 2 * h; }
+          if (y1 > best[u]) { best[u] = y1; label[u] = j0 + 2 * h + 1; }
+        } else {
+          best[u] = fmaxf(best[u], fmaxf(y0, y1));
+        }
       }
     }
   }
@@ -131,16 +165,19 @@ __device__ __forceinline__ void best_centroid_multi(const float (&a)[PPL][DMAX],
 
 constexpr int KM_WARPS = 4;                 // warps per block of the seeding kernel and the default assign kernel
 constexpr int KM_THREADS = KM_WARPS * 32;
+constexpr float KM_FAST_NORM_MAX = 1.0e37f;   // squared norms up to here take the packed fast path
 constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates in fp32 before folding into fp64
 
 // workspace: two uint32 barrier counters (zero on entry / exit) padded to 128 B, then gridDim.x * gridDim.y partial
 // records of (d*K + K + 1) doubles.  Cooperative launch.
 //
 // Centroid accumulation without atomics: every lane owns a private fp32 record [cluster][d sums, count] in shared
-// memory, laid out [entry][lane] so that a warp's read-modify-write hits 32 different banks.  A lane adds at most
-// KM_FLUSH_EVERY points into its record before the warp folds the 32 lane records into float64 registers
-// (rotated, conflict-free column sums in a fixed order), so totals carry fp64 accuracy and are reproducible.
-template <int DMAX, int KMAX, int WARPS, bool EXACT>
+// memory.  Coordinates are kept as fp32 pairs laid out [cluster][pair][lane] (a warp's 64-bit read-modify-write covers
+// 256 contiguous bytes: conflict-free, and one FADD2 updates two coordinates), the odd coordinate (if any) and the
+// count as singles [cluster][single][lane].  A lane adds at most KM_FLUSH_EVERY points into its record before the warp
+// folds the 32 lane records into float64 registers in a fixed order, so totals carry fp64 accuracy and are
+// reproducible.  KPAD: compile-time padded cluster count of the packed scan (0 = run time).
+template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
 __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
     int64_t* __restrict__ labels, float* __restrict__ maxsims, double* __restrict__ sums, double* __restrict__ counts,
@@ -151,14 +188,23 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
   constexpr int NQ = (RECMAX + 31) / 32;
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* cs = reinterpret_cast<float*>(km_smem);            // [DMAX][KMAX]
-  float* bn = cs + DMAX * KMAX;                             // [KMAX]
-  double* blk = reinterpret_cast<double*>(bn + KMAX);       // [rec + 1]
+  float* bn = cs + DMAX * KMAX;                             // [KMAX]   |b_j|^2
+  float* nbn = bn + KMAX;                                   // [KMAX]  -|b_j|^2 (packed scan)
+  double* blk = reinterpret_cast<double*>(nbn + KMAX);      // [rec + 1]
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (EXACT) d = DMAX;                                      // lets the record layout below fold to constants
   const int rec = k * (d + 1);
-  float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // [rec][32]
+  float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // rec * 32 floats
   const bool accumulate = sums != nullptr;
+  const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
+  float* lanesingle = lanerec + (size_t)k * npair * 64;
+  // float offset of column `col` (= lane) of record entry (c, r), r in [0, d]
+  auto rec_offset = [&](int c, int r, int col) -> int {
+    return r < 2 * npair ? ((c * npair + (r >> 1)) * 32 + col) * 2 + (r & 1)
+                         : k * npair * 64 + (c * nsingle + (r - 2 * npair)) * 32 + col;
+  };
 
-  for (int e = tid; e < DMAX * KMAX + KMAX; e += (WARPS * 32)) cs[e] = 0.f;   // cs and bn (contiguous), padding included
+  for (int e = tid; e < DMAX * KMAX + 2 * KMAX; e += (WARPS * 32)) cs[e] = 0.f;   // cs, bn, nbn (contiguous), padding included
   __syncthreads();
   if (centroids)
     for (int e = tid; e < d * k; e += (WARPS * 32)) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
@@ -176,9 +222,13 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
 #pragma unroll
       for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
       bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, k));
-      if (!(bnorm <= 3.0e38f)) nan_centroid = 1;      // NaN or inf centroid: take the torch.max-exact path
+      // NaN / inf / huge centroid: take the torch.max-exact scalar path.  Below KM_FAST_NORM_MAX for both norms
+      // |2 dot| <= 2 sqrt(|a|^2 |b|^2) cannot overflow, so ptxas contracting fl(2 dot) - |a|^2 into one FFMA2 in the
+      // packed scan (2 dot is exact) yields the same bits as the reference's separate mul_ and sub_.
+      if (!(bnorm <= KM_FAST_NORM_MAX)) nan_centroid = 1;
     }
     bn[tid] = bnorm;
+    nbn[tid] = -bnorm;
   }
   __syncthreads();
   const bool nan_possible = nan_centroid != 0;
@@ -189,19 +239,21 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
   for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
   double sim_acc = 0.0;
 
-  // fold the 32 lane records into the fp64 registers: lane i owns entries i, i+32, ...; it walks the 32 lane
-  // columns of each of its entries starting at its own column (bank = column => conflict-free)
+  // fold the 32 lane records into the fp64 registers: lane i owns entries i, i+32, ... (entry e = cluster * (d+1) + r);
+  // it walks the 32 lane columns of each of its entries starting at its own column, always in the same order
   auto flush = [&]() {
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
       if (e < rec) {
-        float* row = lanerec + e * 32;
+        const int c = e / (d + 1), r = e - c * (d + 1);
+        float* row = lanerec + rec_offset(c, r, 0);
+        const int step = r < 2 * npair ? 2 : 1;
         double s = 0.0;
 #pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-          const int col = (c + lane) & 31;
+        for (int cc = 0; cc < 32; ++cc) {
+          const int col = ((cc + lane) & 31) * step;
           s += (double)row[col];
           row[col] = 0.f;
         }
@@ -253,10 +305,10 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
         anorm[u] = sumsq_torch_order<DMAX>(a[u], d, col_is_sequential(idx[u], n));
-        finite = finite && (fabsf(anorm[u]) <= 3.0e38f);   // finite iff every coordinate is
+        finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
       }
       if (finite) {
-        best_centroid_multi<DMAX, EXACT, PPL>(a, d, anorm, cs, KMAX, bn, kpad, best, label);
+        best_centroid_packed<DMAX, EXACT, PPL, KPAD, true>(a, d, anorm, cs, KMAX, nbn, kpad, best, label);
       } else {
 #pragma unroll
         for (int u = 0; u < PPL; ++u)
@@ -269,11 +321,21 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
         if (labels) labels[(int64_t)l * n + idx[u]] = label[u];
         if (maxsims) maxsims[(int64_t)l * n + idx[u]] = best[u];
         if (accumulate && label[u] >= 0) {
-          float* slot = lanerec + (label[u] * (d + 1)) * 32 + lane;
+          f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * 32 + lane;
 #pragma unroll
-          for (int r = 0; r < DMAX; ++r)
-            if (EXACT || r < d) slot[r * 32] += a[u][r];
-          slot[d * 32] += 1.0f;
+          for (int p2 = 0; p2 < DMAX / 2; ++p2)
+            if (EXACT || p2 < npair) pslot[p2 * 32] = add2(pslot[p2 * 32], pack2(a[u][2 * p2], a[u][2 * p2 + 1]));
+          float* sslot = lanesingle + (label[u] * nsingle) * 32 + lane;
+          if (d & 1) {
+            float last = 0.f;
+#pragma unroll
+            for (int r = 0; r < DMAX; ++r)
+              if (r == d - 1) last = a[u][r];
+            sslot[0] += last;
+            sslot[32] += 1.0f;
+          } else {
+            sslot[0] += 1.0f;
+          }
           sim_acc += (double)best[u];
         }
       }
@@ -325,7 +387,7 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
 
 template <int DMAX, int KMAX>
 static size_t km_smem_bytes(int d, int k, int warps, bool accumulate) {
-  return (size_t)(DMAX * KMAX + KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
+  return (size_t)(DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
          (accumulate ? (size_t)warps * k * (d + 1) * 32 * sizeof(float) : 0);
 }
 
@@ -395,8 +457,10 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
   __shared__ __align__(16) float cs[DMAX * KMAX];
   __shared__ __align__(16) float bn[KMAX];
   __shared__ unsigned long long wmin[KM_WARPS];
+  __shared__ int huge_centroid;
   for (int e = threadIdx.x; e < DMAX * KMAX; e += KM_THREADS) cs[e] = 0.f;
   if (threadIdx.x < KMAX) bn[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) huge_centroid = 0;
   __syncthreads();
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* dl = data + (int64_t)l * d * n;
@@ -418,10 +482,17 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
 #pragma unroll
       for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
       bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, ncols));
+      if (!(bnorm <= KM_FAST_NORM_MAX)) huge_centroid = 1;
     }
-    bn[tid] = bnorm;
+    bn[tid] = -bnorm;     // negated for the packed scan; padding columns: similarity -inf
   }
   __syncthreads();
+  const bool scalar_only = huge_centroid != 0;
+  if (scalar_only) {      // the scalar scan subtracts |b|^2
+    __syncthreads();
+    if (tid < kpad) bn[tid] = -bn[tid];
+    __syncthreads();
+  }
   unsigned long long key = ~0ull;
   const int64_t sstride = (int64_t)gridDim.x * KM_THREADS;
   float a_next[DMAX];
@@ -431,19 +502,24 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
     for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
   }
   for (int64_t i = (int64_t)blockIdx.x * KM_THREADS + tid; i < n; i += sstride) {
-    float a[DMAX];
+    float a[1][DMAX];
 #pragma unroll
-    for (int r = 0; r < DMAX; ++r) a[r] = a_next[r];
+    for (int r = 0; r < DMAX; ++r) a[0][r] = a_next[r];
     {
       const int64_t in = i + sstride;
 #pragma unroll
       for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
     }
-    const float anorm = sumsq_torch_order<DMAX>(a, d, col_is_sequential(i, n));
-    float best;
-    int label;
-    best_centroid<DMAX, EXACT, false>(a, d, anorm, cs, KMAX, bn, ncols, kpad, best, label);
-    const unsigned long long kk = pack_min_key(best, i);
+    const float an[1] = {sumsq_torch_order<DMAX>(a[0], d, col_is_sequential(i, n))};
+    float best[1];
+    int label[1];
+    if (!scalar_only && fabsf(an[0]) <= KM_FAST_NORM_MAX)
+      best_centroid_packed<DMAX, EXACT, 1, 0, false>(a, d, an, cs, KMAX, bn, kpad, best, label);
+    else if (scalar_only)
+      best_centroid<DMAX, EXACT, false>(a[0], d, an[0], cs, KMAX, bn, ncols, kpad, best[0], label[0]);
+    else
+      best_centroid_neg<DMAX, EXACT>(a[0], d, an[0], cs, KMAX, bn, kpad, best[0]);
+    const unsigned long long kk = pack_min_key(best[0], i);
     key = kk < key ? kk : key;
   }
 #pragma unroll
@@ -474,11 +550,11 @@ __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l,
 }
 
 // Launch the assign kernel (cooperatively when it accumulates: the fold needs a grid barrier).
-template <int DMAX, int KMAX, int WARPS, bool EXACT>
-static int km_launch_w(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
+template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
+static int km_launch_k(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
                      const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
-  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT>;
+  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT, KPAD>;
   constexpr int KM_THREADS_L = WARPS * 32;
   const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, sums != nullptr);
   if (smem > 200 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
@@ -505,6 +581,18 @@ static int km_launch_w(const float* data, const float* centroids, int l, int d, 
                                          labels_in);
   }
   return check_launch("kmeans_assign_kernel");
+}
+
+// 20 anchors (padded count 20) is the reference configuration: its scan is unrolled at compile time
+template <int DMAX, int KMAX, int WARPS, bool EXACT>
+static int km_launch_w(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
+                       float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
+                       const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+  if (EXACT && ((k + 3) & ~3) == 20)
+    return km_launch_k<DMAX, KMAX, WARPS, EXACT, EXACT ? 20 : 0>(data, centroids, l, d, n, k, labels, maxsims, sums, counts,
+                                                                 simsum, workspace, status, labels_in, st);
+  return km_launch_k<DMAX, KMAX, WARPS, EXACT, 0>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
+                                                  workspace, status, labels_in, st);
 }
 
 template <int DMAX, int KMAX, bool EXACT>
