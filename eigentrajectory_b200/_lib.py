@@ -47,12 +47,15 @@ PROTOTYPES = {
     "et_svd_small": (_i, [_p, _p, _i, _l, _i, _i, _p, _p, _p]),
     "et_kmeans_workspace_bytes": (_sz, [_i, _i, _i]),
     "et_kmeans_assign": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "et_kmeans_lloyd": (_i, [_p, _p, _i, _i, _l, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p]),
     "et_kmeans_accumulate": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p]),
     "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _p]),
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),
     "et_kmeans_seed_step": (_i, [_p, _p, _i, _i, _l, _i, _i, _p, _p]),
     "et_ade_fde": (_i, [_p, _p, _i, _l, _i, _p, _p, _p, _p, _p]),
     "et_col": (_i, [_p, _i, _l, _i, C.c_float, _p, _p]),
+    "et_dataset_parse_host": (_i, [C.c_char_p, _sz, C.c_char, _p, _l, _p]),
+    "et_dataset_windows_host": (_i, [_p, _l, _i, _i, _i, _d, _i, _p, _p, _p, _l, _l, _p, _p]),
 }
 
 _lib = None

@@ -215,6 +215,29 @@ __device__ __forceinline__ double warp_fold(const double* partials, int rec, int
   return s;
 }
 
+// Same for partials stored entry-major (v[0 .. n_part) contiguous for one entry): a warp's loads are coalesced and all
+// in flight together, so the fold costs about one L2 round trip instead of one per 128 partial records.
+__device__ __forceinline__ double warp_fold_contig(const double* v, int n_part, int lane) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int p = lane;
+  for (; p + 96 < n_part; p += 128) {
+    const double v0 = __ldcg(v + p);
+    const double v1 = __ldcg(v + p + 32);
+    const double v2 = __ldcg(v + p + 64);
+    const double v3 = __ldcg(v + p + 96);
+    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+  }
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+  if (p < n_part) t0 = __ldcg(v + p);
+  if (p + 32 < n_part) t1 = __ldcg(v + p + 32);
+  if (p + 64 < n_part) t2 = __ldcg(v + p + 64);
+  s0 += t0; s1 += t1; s2 += t2;
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
 // Cooperative launch wrapper (guarantees co-residency or fails loudly).
 template <typename... Args>
 inline cudaError_t launch_cooperative(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -168,8 +168,44 @@ constexpr int KM_THREADS = KM_WARPS * 32;
 constexpr float KM_FAST_NORM_MAX = 1.0e37f;   // squared norms up to here take the packed fast path
 constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates in fp32 before folding into fp64
 
-// workspace: two uint32 barrier counters (zero on entry / exit) padded to 128 B, then gridDim.x * gridDim.y partial
-// records of (d*K + K + 1) doubles.  Cooperative launch.
+// Whole-fit mode of the assign kernel: with cent_out != null the kernel runs the complete Lloyd loop of
+// BatchKMeans.fit (kmeans.py:226-239) -- assign + accumulate, grid fold, centroid division, error test -- for up to
+// max_iter iterations without returning to the host, then one more scan that writes the labels of the last assignment.
+struct KmLloyd {
+  int max_iter;
+  double tol;
+  float* cent_out;          // (l,d,K) centroids after the last update
+  double* totals;           // scratch: l * (K (d+1) + 1) folded sums, then l per-entry errors
+  double* err;              // [1] sum (old - new)^2 of the last iteration (over all l, as calculate_error)
+  int32_t* status;          // [2] {converged, iterations done}
+  double* simsum_last;      // (l) sum of best similarities of the last assignment
+  int64_t* labels_final;    // (l,N) optional
+};
+
+// Reusable grid barrier for the whole-fit mode: ctr[0] counts arrivals monotonically (barrier number `phase`, 1-based,
+// completes at phase * nblocks).  km_barrier_exit() restores the zero state once every block has left its last spin.
+__device__ __forceinline__ void km_barrier(unsigned* ctr, unsigned nblocks, unsigned phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&ctr[0], 1u);
+    const unsigned target = phase * nblocks;
+    while (*reinterpret_cast<volatile unsigned*>(&ctr[0]) < target) __nanosleep(20);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void km_barrier_exit(unsigned* ctr, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&ctr[1], 1u) == nblocks - 1) {
+    ctr[0] = 0u;
+    ctr[1] = 0u;
+    __threadfence();
+  }
+}
+
+// workspace: four uint32 barrier counters (zero on entry / exit) padded to 128 B, then gridDim.x * gridDim.y partial
+// records of (d*K + K + 1) doubles (then the whole-fit scratch).  Cooperative launch.
 //
 // Centroid accumulation without atomics: every lane owns a private fp32 record [cluster][d sums, count] in shared
 // memory.  Coordinates are kept as fp32 pairs laid out [cluster][pair][lane] (a warp's 64-bit read-modify-write covers
@@ -178,24 +214,27 @@ constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates 
 // folds the 32 lane records into float64 registers in a fixed order, so totals carry fp64 accuracy and are
 // reproducible.  KPAD: compile-time padded cluster count of the packed scan (0 = run time).
 template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
-__global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
     int64_t* __restrict__ labels, float* __restrict__ maxsims, double* __restrict__ sums, double* __restrict__ counts,
     double* __restrict__ simsum, unsigned* __restrict__ barrier_ctr, double* __restrict__ partials,
-    const int32_t* __restrict__ status, const int64_t* __restrict__ labels_in) {
+    const int32_t* __restrict__ status, const int64_t* __restrict__ labels_in, const KmLloyd fit) {
   if (status && status[0] != 0) return;   // converged on an earlier iteration: nothing to do (uniform over the grid)
   constexpr int RECMAX = KMAX * (DMAX + 1);
   constexpr int NQ = (RECMAX + 31) / 32;
+  constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* cs = reinterpret_cast<float*>(km_smem);            // [DMAX][KMAX]
   float* bn = cs + DMAX * KMAX;                             // [KMAX]   |b_j|^2
   float* nbn = bn + KMAX;                                   // [KMAX]  -|b_j|^2 (packed scan)
-  double* blk = reinterpret_cast<double*>(nbn + KMAX);      // [rec + 1]
+  float* csn = nbn + KMAX;                                  // [DMAX][KMAX] updated centroids (whole-fit mode)
+  double* blk = reinterpret_cast<double*>(csn + DMAX * KMAX);   // [rec + 1]
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (EXACT) d = DMAX;                                      // lets the record layout below fold to constants
   const int rec = k * (d + 1);
   float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // rec * 32 floats
-  const bool accumulate = sums != nullptr;
+  const bool whole_fit = fit.cent_out != nullptr;
+  const bool accumulate = sums != nullptr || whole_fit;
   const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
   float* lanesingle = lanerec + (size_t)k * npair * 64;
   // float offset of column `col` (= lane) of record entry (c, r), r in [0, d]
@@ -203,191 +242,260 @@ __global__ void __launch_bounds__(WARPS * 32) kmeans_assign_kernel(
     return r < 2 * npair ? ((c * npair + (r >> 1)) * 32 + col) * 2 + (r & 1)
                          : k * npair * 64 + (c * nsingle + (r - 2 * npair)) * 32 + col;
   };
+  __shared__ int nan_centroid;
+  __shared__ double red_s[WARPS];
 
-  for (int e = tid; e < DMAX * KMAX + 2 * KMAX; e += (WARPS * 32)) cs[e] = 0.f;   // cs, bn, nbn (contiguous), padding included
+  for (int e = tid; e < 2 * DMAX * KMAX + 2 * KMAX; e += THREADS) cs[e] = 0.f;   // cs, bn, nbn, csn (contiguous), padding included
   __syncthreads();
   if (centroids)
-    for (int e = tid; e < d * k; e += (WARPS * 32)) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
+    for (int e = tid; e < d * k; e += THREADS) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
   if (accumulate)
     for (int e = lane; e < rec * 32; e += 32) lanerec[e] = 0.f;
-  __syncthreads();
-  __shared__ int nan_centroid;
-  if (tid == 0) nan_centroid = 0;
-  __syncthreads();
   const int kpad = (k + 3) & ~3;
-  if (tid < kpad) {
-    float bnorm = INFINITY;           // padding columns: similarity -inf
-    if (tid < k) {
-      float v[DMAX];
-#pragma unroll
-      for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
-      bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, k));
-      // NaN / inf / huge centroid: take the torch.max-exact scalar path.  Below KM_FAST_NORM_MAX for both norms
-      // |2 dot| <= 2 sqrt(|a|^2 |b|^2) cannot overflow, so ptxas contracting fl(2 dot) - |a|^2 into one FFMA2 in the
-      // packed scan (2 dot is exact) yields the same bits as the reference's separate mul_ and sub_.
-      if (!(bnorm <= KM_FAST_NORM_MAX)) nan_centroid = 1;
-    }
-    bn[tid] = bnorm;
-    nbn[tid] = -bnorm;
-  }
-  __syncthreads();
-  const bool nan_possible = nan_centroid != 0;
-
   const float* dl = data + (int64_t)l * d * n;
+  const int out_rec = rec + 1;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  unsigned phase = 0;
   double acc[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
   double sim_acc = 0.0;
 
   // fold the 32 lane records into the fp64 registers: lane i owns entries i, i+32, ... (entry e = cluster * (d+1) + r);
   // it walks the 32 lane columns of each of its entries starting at its own column, always in the same order
+  // (the NQ chains of a lane advance together: NQ independent fp64 additions per step instead of one long chain)
   auto flush = [&]() {
     __syncwarp();
+    float* row[NQ];
+    int step[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       const int e = lane + 32 * q;
-      if (e < rec) {
-        const int c = e / (d + 1), r = e - c * (d + 1);
-        float* row = lanerec + rec_offset(c, r, 0);
-        const int step = r < 2 * npair ? 2 : 1;
-        double s = 0.0;
-#pragma unroll 8
-        for (int cc = 0; cc < 32; ++cc) {
-          const int col = ((cc + lane) & 31) * step;
-          s += (double)row[col];
-          row[col] = 0.f;
+      const int c = e / (d + 1), r = e - c * (d + 1);
+      row[q] = e < rec ? lanerec + rec_offset(c, r, 0) : nullptr;
+      step[q] = r < 2 * npair ? 2 : 1;
+    }
+    double s[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) s[q] = 0.0;
+#pragma unroll 4
+    for (int cc = 0; cc < 32; ++cc) {
+      const int col = (cc + lane) & 31;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (row[q]) {
+          s[q] += (double)row[q][col * step[q]];
+          row[q][col * step[q]] = 0.f;
         }
-        acc[q] += s;
       }
     }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] += s[q];
     __syncwarp();
   };
 
-  constexpr int PPL = 2;                                   // points per lane and iteration (instruction-level parallelism)
-  const int64_t stride = (int64_t)gridDim.x * (WARPS * 32 * PPL);
-  int since_flush = 0;
-  // all lanes of a warp iterate together (the loop bound is warp-uniform)
-  float a_next[PPL][DMAX];
-  {
-    const int64_t b0 = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL);
+  bool final_pass = false;      // whole-fit mode: the label-writing scan after the last update
+  for (int it = 0;; ++it) {
+    // ---- centroid norms in torch's summation order (cs holds this pass's centroids) ----
+    __syncthreads();
+    if (tid == 0) nan_centroid = 0;
+    __syncthreads();
+    if (tid < kpad) {
+      float bnorm = INFINITY;           // padding columns: similarity -inf
+      if (tid < k) {
+        float v[DMAX];
 #pragma unroll
-    for (int u = 0; u < PPL; ++u) {
-      const int64_t i0 = b0 + u * 32 + lane;
-#pragma unroll
-      for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
+        for (int i = 0; i < DMAX; ++i) v[i] = (i < d) ? cs[i * KMAX + tid] : 0.f;
+        bnorm = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, k));
+        // NaN / inf / huge centroid: take the torch.max-exact scalar path.  Below KM_FAST_NORM_MAX for both norms
+        // |2 dot| <= 2 sqrt(|a|^2 |b|^2) cannot overflow, so ptxas contracting fl(2 dot) - |a|^2 into one FFMA2 in the
+        // packed scan (2 dot is exact) yields the same bits as the reference's separate mul_ and sub_.
+        if (!(bnorm <= KM_FAST_NORM_MAX)) nan_centroid = 1;
+      }
+      bn[tid] = bnorm;
+      nbn[tid] = -bnorm;
     }
-  }
-  for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL); base < n; base += stride) {
-    float a[PPL][DMAX];
-    int64_t idx[PPL];
+    __syncthreads();
+    const bool nan_possible = nan_centroid != 0;
+    const bool acc_pass = accumulate && !final_pass;
+    int64_t* labels_out = whole_fit ? (final_pass ? fit.labels_final : nullptr) : labels;
+    float* maxsims_out = whole_fit ? nullptr : maxsims;
 #pragma unroll
-    for (int u = 0; u < PPL; ++u) {
-      idx[u] = base + u * 32 + lane;
-#pragma unroll
-      for (int r = 0; r < DMAX; ++r) a[u][r] = a_next[u][r];
-      // software prefetch of the next batch: its loads are in flight while this one is scored
-      const int64_t in = idx[u] + stride;
-#pragma unroll
-      for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
-    }
-    float best[PPL];
-    int label[PPL];
-    if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    sim_acc = 0.0;
+
+    constexpr int PPL = 2;                                   // points per lane and iteration (instruction-level parallelism)
+    const int64_t stride = (int64_t)gridDim.x * (WARPS * 32 * PPL);
+    int since_flush = 0;
+    // all lanes of a warp iterate together (the loop bound is warp-uniform)
+    float a_next[PPL][DMAX];
+    {
+      const int64_t b0 = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL);
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
-        best[u] = 0.f;
-        const int64_t li = idx[u] < n ? labels_in[(int64_t)l * n + idx[u]] : -1;
-        label[u] = (li >= 0 && li < k) ? (int)li : -1;
+        const int64_t i0 = b0 + u * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
       }
-    } else {
-      float anorm[PPL];
-      bool finite = !nan_possible;
+    }
+    for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL); base < n; base += stride) {
+      float a[PPL][DMAX];
+      int64_t idx[PPL];
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
-        anorm[u] = sumsq_torch_order<DMAX>(a[u], d, col_is_sequential(idx[u], n));
-        finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
+        idx[u] = base + u * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < DMAX; ++r) a[u][r] = a_next[u][r];
+        // software prefetch of the next batch: its loads are in flight while this one is scored
+        const int64_t in = idx[u] + stride;
+#pragma unroll
+        for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
       }
-      if (finite) {
-        best_centroid_packed<DMAX, EXACT, PPL, KPAD, true>(a, d, anorm, cs, KMAX, nbn, kpad, best, label);
+      float best[PPL];
+      int label[PPL];
+      if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+          best[u] = 0.f;
+          const int64_t li = idx[u] < n ? labels_in[(int64_t)l * n + idx[u]] : -1;
+          label[u] = (li >= 0 && li < k) ? (int)li : -1;
+        }
       } else {
+        float anorm[PPL];
+        bool finite = !nan_possible;
 #pragma unroll
-        for (int u = 0; u < PPL; ++u)
-          best_centroid<DMAX, EXACT, true>(a[u], d, anorm[u], cs, KMAX, bn, k, kpad, best[u], label[u]);
+        for (int u = 0; u < PPL; ++u) {
+          anorm[u] = sumsq_torch_order<DMAX>(a[u], d, col_is_sequential(idx[u], n));
+          finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
+        }
+        if (finite) {
+          best_centroid_packed<DMAX, EXACT, PPL, KPAD, true>(a, d, anorm, cs, KMAX, nbn, kpad, best, label);
+        } else {
+#pragma unroll
+          for (int u = 0; u < PPL; ++u)
+            best_centroid<DMAX, EXACT, true>(a[u], d, anorm[u], cs, KMAX, bn, k, kpad, best[u], label[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < PPL; ++u) {
+        if (idx[u] < n) {
+          if (labels_out) labels_out[(int64_t)l * n + idx[u]] = label[u];
+          if (maxsims_out) maxsims_out[(int64_t)l * n + idx[u]] = best[u];
+          if (acc_pass && label[u] >= 0) {
+            f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * 32 + lane;
+#pragma unroll
+            for (int p2 = 0; p2 < DMAX / 2; ++p2)
+              if (EXACT || p2 < npair) pslot[p2 * 32] = add2(pslot[p2 * 32], pack2(a[u][2 * p2], a[u][2 * p2 + 1]));
+            float* sslot = lanesingle + (label[u] * nsingle) * 32 + lane;
+            if (d & 1) {
+              float last = 0.f;
+#pragma unroll
+              for (int r = 0; r < DMAX; ++r)
+                if (r == d - 1) last = a[u][r];
+              sslot[0] += last;
+              sslot[32] += 1.0f;
+            } else {
+              sslot[0] += 1.0f;
+            }
+            sim_acc += (double)best[u];
+          }
+        }
+      }
+      if (acc_pass && (since_flush += PPL) >= KM_FLUSH_EVERY) {
+        flush();
+        since_flush = 0;
       }
     }
+    if (!acc_pass) break;
+    flush();
+
+    // ---- block reduction in fixed warp order ----
+    for (int e = tid; e <= rec; e += THREADS) blk[e] = 0.0;
 #pragma unroll
-    for (int u = 0; u < PPL; ++u) {
-      if (idx[u] < n) {
-        if (labels) labels[(int64_t)l * n + idx[u]] = label[u];
-        if (maxsims) maxsims[(int64_t)l * n + idx[u]] = best[u];
-        if (accumulate && label[u] >= 0) {
-          f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * 32 + lane;
+    for (int o = 16; o > 0; o >>= 1) sim_acc += __shfl_xor_sync(0xffffffffu, sim_acc, o);
+    __syncthreads();
+    for (int w = 0; w < WARPS; ++w) {
+      if (warp == w) {
 #pragma unroll
-          for (int p2 = 0; p2 < DMAX / 2; ++p2)
-            if (EXACT || p2 < npair) pslot[p2 * 32] = add2(pslot[p2 * 32], pack2(a[u][2 * p2], a[u][2 * p2 + 1]));
-          float* sslot = lanesingle + (label[u] * nsingle) * 32 + lane;
-          if (d & 1) {
-            float last = 0.f;
-#pragma unroll
-            for (int r = 0; r < DMAX; ++r)
-              if (r == d - 1) last = a[u][r];
-            sslot[0] += last;
-            sslot[32] += 1.0f;
-          } else {
-            sslot[0] += 1.0f;
-          }
-          sim_acc += (double)best[u];
+        for (int q = 0; q < NQ; ++q) {
+          const int e = lane + 32 * q;
+          if (e < rec) blk[e] += acc[q];
+        }
+        if (lane == 0) blk[rec] += sim_acc;
+      }
+      __syncthreads();
+    }
+    // partial records are stored entry-major ([l][entry][block]) so that the fold below reads contiguous doubles
+    double* lpart = partials + (size_t)l * gridDim.x * out_rec;
+    for (int e = tid; e < out_rec; e += THREADS) lpart[(size_t)e * gridDim.x + blockIdx.x] = blk[e];
+    // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
+    if (!whole_fit) grid_barrier(barrier_ctr, nblocks);
+    else km_barrier(barrier_ctr + 2, nblocks, ++phase);
+    for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
+      const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
+      if (lane == 0) {
+        if (whole_fit) {
+          fit.totals[(size_t)l * out_rec + e] = tot;
+        } else if (e < rec) {
+          const int c = e / (d + 1), r = e % (d + 1);
+          if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
+          else counts[(int64_t)l * k + c] += tot;
+        } else if (simsum) {
+          simsum[l] += tot;
         }
       }
     }
-    if (accumulate && (since_flush += PPL) >= KM_FLUSH_EVERY) {
-      flush();
-      since_flush = 0;
-    }
-  }
-  if (!accumulate) return;
-  flush();
+    if (!whole_fit) break;
 
-  // ---- block reduction in fixed warp order ----
-  for (int e = tid; e <= rec; e += (WARPS * 32)) blk[e] = 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sim_acc += __shfl_xor_sync(0xffffffffu, sim_acc, o);
-  __syncthreads();
-  for (int w = 0; w < WARPS; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const int e = lane + 32 * q;
-        if (e < rec) blk[e] += acc[q];
-      }
-      if (lane == 0) blk[rec] += sim_acc;
+    // ---- whole-fit mode: division, error and convergence test, identically in every block (compute_centroids'
+    // division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` kmeans.py:239) ----
+    km_barrier(barrier_ctr + 2, nblocks, ++phase);
+    const double* tl = fit.totals + (size_t)l * out_rec;
+    double e2 = 0.0;
+    for (int e = tid; e < d * k; e += THREADS) {
+      const int r = e / k, c = e - r * k;
+      const float v = (float)(__ldcg(tl + c * (d + 1) + r) / __ldcg(tl + c * (d + 1) + d));   // 0/0 -> NaN as the reference
+      csn[r * KMAX + c] = v;
+      const double df = (double)cs[r * KMAX + c] - (double)v;
+      e2 += df * df;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    if (lane == 0) red_s[warp] = e2;
     __syncthreads();
-  }
-  const int out_rec = rec + 1;
-  const unsigned nblocks = gridDim.x * gridDim.y;
-  double* part = partials + ((size_t)l * gridDim.x + blockIdx.x) * out_rec;
-  for (int e = tid; e < out_rec; e += (WARPS * 32)) part[e] = blk[e];
-  // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
-  grid_barrier(barrier_ctr, nblocks);
-  const double* lpart = partials + (size_t)l * gridDim.x * out_rec;
-  for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
-    const double tot = warp_fold(lpart, out_rec, (int)gridDim.x, e, lane);
-    if (lane == 0) {
-      if (e < rec) {
-        const int c = e / (d + 1), r = e % (d + 1);
-        if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
-        else counts[(int64_t)l * k + c] += tot;
-      } else if (simsum) {
-        simsum[l] += tot;
+    double err = 0.0;
+    for (int w = 0; w < WARPS; ++w) err += red_s[w];
+    if (gridDim.y > 1) {       // the reference's error runs over every batch entry: exchange the per-entry errors
+      double* errs = fit.totals + (size_t)gridDim.y * out_rec;
+      if (blockIdx.x == 0 && tid == 0) errs[l] = err;
+      km_barrier(barrier_ctr + 2, nblocks, ++phase);
+      err = 0.0;
+      for (int y = 0; y < (int)gridDim.y; ++y) err += __ldcg(errs + y);
+    }
+    const bool converged = err <= fit.tol;
+    final_pass = converged || it + 1 >= fit.max_iter;
+    const bool stop = final_pass && !fit.labels_final;     // nobody wants the labels: skip the last scan
+    if (blockIdx.x == 0) {
+      if (final_pass) {
+        for (int e = tid; e < d * k; e += THREADS) fit.cent_out[(int64_t)l * d * k + e] = csn[(e / k) * KMAX + (e % k)];
+        if (tid == 0 && fit.simsum_last) fit.simsum_last[l] = __ldcg(tl + rec);
+      }
+      if (l == 0 && tid == 0 && final_pass) {
+        if (fit.err) fit.err[0] = err;
+        if (fit.status) { fit.status[0] = converged ? 1 : 0; fit.status[1] = it + 1; }
       }
     }
+    if (!final_pass) {         // next assignment runs against the updated centroids
+      __syncthreads();
+      for (int e = tid; e < DMAX * KMAX; e += THREADS) cs[e] = csn[e];
+    }
+    // on the final pass cs keeps the centroids of the last assignment: its labels are the ones fit() returns
+    if (stop) break;
   }
+  if (whole_fit) km_barrier_exit(barrier_ctr + 2, nblocks);
 }
 
 template <int DMAX, int KMAX>
 static size_t km_smem_bytes(int d, int k, int warps, bool accumulate) {
-  return (size_t)(DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
+  return (size_t)(2 * DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
          (accumulate ? (size_t)warps * k * (d + 1) * 32 * sizeof(float) : 0);
 }
 
@@ -553,11 +661,12 @@ __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l,
 template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
 static int km_launch_k(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
-                     const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+                     const int32_t* status, const int64_t* labels_in, KmLloyd fit, cudaStream_t st) {
   auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT, KPAD>;
   constexpr int KM_THREADS_L = WARPS * 32;
-  const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, sums != nullptr);
-  if (smem > 200 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
+  const bool coop = sums != nullptr || fit.cent_out != nullptr;    // accumulating launches fold over the grid
+  const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, coop);
+  if (smem > 226 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   int per_sm = 0;
@@ -572,13 +681,14 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
   dim3 grid((unsigned)gx, (unsigned)l);
   unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
   double* parts = workspace ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128) : nullptr;
-  if (sums) {
+  if (fit.cent_out) fit.totals = parts + (size_t)sm_count() * 8 * ((size_t)k * (d + 1) + 1);   // behind the partial records
+  if (coop) {
     e = launch_cooperative(kern, grid, dim3(KM_THREADS_L), smem, st, data, centroids, d, n, k, labels, maxsims, sums, counts,
-                           simsum, ctr, parts, status, labels_in);
+                           simsum, ctr, parts, status, labels_in, fit);
     if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cooperative launch: %s", cudaGetErrorString(e));
   } else {
     kern<<<grid, KM_THREADS_L, smem, st>>>(data, centroids, d, n, k, labels, maxsims, sums, counts, simsum, ctr, parts, status,
-                                         labels_in);
+                                         labels_in, fit);
   }
   return check_launch("kmeans_assign_kernel");
 }
@@ -587,38 +697,45 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
 template <int DMAX, int KMAX, int WARPS, bool EXACT>
 static int km_launch_w(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                        float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
-                       const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+                       const int32_t* status, const int64_t* labels_in, const KmLloyd& fit, cudaStream_t st) {
   if (EXACT && ((k + 3) & ~3) == 20)
     return km_launch_k<DMAX, KMAX, WARPS, EXACT, EXACT ? 20 : 0>(data, centroids, l, d, n, k, labels, maxsims, sums, counts,
-                                                                 simsum, workspace, status, labels_in, st);
+                                                                 simsum, workspace, status, labels_in, fit, st);
   return km_launch_k<DMAX, KMAX, WARPS, EXACT, 0>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
-                                                  workspace, status, labels_in, st);
+                                                  workspace, status, labels_in, fit, st);
 }
 
 template <int DMAX, int KMAX, bool EXACT>
 static int km_launch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
-                     const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+                     const int32_t* status, const int64_t* labels_in, const KmLloyd& fit, cudaStream_t st) {
+  // accumulating launches of the reference shape: ONE 12-warp block per SM while its lane-private records fit shared
+  // memory -- a third of the partial records and grid-barrier arrivals of the 3 x 4-warp configuration
+  if constexpr (EXACT) {
+    if ((sums != nullptr || fit.cent_out != nullptr) && km_smem_bytes<DMAX, KMAX>(d, k, 12, true) <= 224 * 1024)
+      return km_launch_w<DMAX, KMAX, 12, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
+                                                status, labels_in, fit, st);
+  }
   // four warps per block while their lane-private records fit ~100 KB, otherwise one warp per block
-  if (km_smem_bytes<DMAX, KMAX>(d, k, KM_WARPS, sums != nullptr) <= 100 * 1024)
+  if (km_smem_bytes<DMAX, KMAX>(d, k, KM_WARPS, sums != nullptr || fit.cent_out != nullptr) <= 100 * 1024)
     return km_launch_w<DMAX, KMAX, KM_WARPS, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
-                                                    workspace, status, labels_in, st);
+                                                    workspace, status, labels_in, fit, st);
   return km_launch_w<DMAX, KMAX, 1, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
-                                           status, labels_in, st);
+                                           status, labels_in, fit, st);
 }
 
 // (6, <=32) is the reference configuration (k = 6 coefficients, 20 anchors): compile-time d.
 static int km_dispatch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                        float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
-                       const int32_t* status, const int64_t* labels_in, cudaStream_t st) {
+                       const int32_t* status, const int64_t* labels_in, const KmLloyd& fit, cudaStream_t st) {
   if (d == 6 && k <= 32)
     return km_launch<6, 32, true>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
-                                  labels_in, st);
+                                  labels_in, fit, st);
   if (d <= 8 && k <= 32)
     return km_launch<8, 32, false>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
-                                   labels_in, st);
+                                   labels_in, fit, st);
   return km_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
-                                                          workspace, status, labels_in, st);
+                                                          workspace, status, labels_in, fit, st);
 }
 
 static int km_grid(int64_t n) {
@@ -654,8 +771,10 @@ extern "C" {
 
 size_t et_kmeans_workspace_bytes(int l, int d, int k_clusters) {
   if (l < 1 || d < 1 || k_clusters < 1) return 0;
-  // 128 B of barrier counters + one partial record per co-resident block (at most 8 per SM in total)
-  return 128 + (size_t)sm_count() * 8 * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
+  // 128 B of barrier counters + one partial record per co-resident block (at most 8 per SM in total) + the whole-fit
+  // scratch of et_kmeans_lloyd (l folded records and l per-entry errors)
+  const size_t rec = (size_t)k_clusters * (d + 1) + 1;
+  return 128 + ((size_t)sm_count() * 8 * rec + (size_t)l * (rec + 1)) * sizeof(double);
 }
 
 int et_kmeans_assign(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
@@ -667,7 +786,28 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
   ET_REQUIRE((data && centroids) || n == 0, ET_ERR_BADARG, "et_kmeans_assign: data / centroids null");
   ET_REQUIRE(!sums || (counts && workspace), ET_ERR_BADARG, "et_kmeans_assign: sums given without counts / workspace");
   cudaStream_t st = as_stream(stream);
-  return km_dispatch(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status, nullptr, st);
+  return km_dispatch(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status, nullptr,
+                     KmLloyd{}, st);
+}
+
+int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int max_iter,
+                    double tol, float* centroids_out, int64_t* labels, double* err, int32_t* status, double* simsum_last,
+                    void* workspace, et_stream_t stream) {
+  int rc = km_check(l, d, n, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(data && centroids && centroids_out && workspace, ET_ERR_BADARG, "et_kmeans_lloyd: null pointer");
+  ET_REQUIRE(n >= 1, ET_ERR_BADARG, "et_kmeans_lloyd: no points");
+  ET_REQUIRE(max_iter >= 1, ET_ERR_BADARG, "et_kmeans_lloyd: max_iter = %d < 1", max_iter);
+  KmLloyd fit{};
+  fit.max_iter = max_iter;
+  fit.tol = tol;
+  fit.cent_out = centroids_out;
+  fit.err = err;
+  fit.status = status;
+  fit.simsum_last = simsum_last;
+  fit.labels_final = labels;
+  return km_dispatch(data, centroids, l, d, n, k_clusters, nullptr, nullptr, nullptr, nullptr, nullptr, workspace, nullptr, nullptr,
+                     fit, as_stream(stream));
 }
 
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n, int k_clusters,
@@ -678,7 +818,8 @@ int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d,
   ET_REQUIRE((data && labels) || n == 0, ET_ERR_BADARG, "et_kmeans_accumulate: data / labels null");
   ET_REQUIRE(sums && counts && workspace, ET_ERR_BADARG, "et_kmeans_accumulate: sums / counts / workspace null");
   cudaStream_t st = as_stream(stream);
-  return km_dispatch(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr, labels, st);
+  return km_dispatch(data, nullptr, l, d, n, k_clusters, nullptr, nullptr, sums, counts, nullptr, workspace, nullptr, labels,
+                     KmLloyd{}, st);
 }
 
 int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_clusters, const float* old_centroids,

@@ -30,9 +30,12 @@ class BatchKMeans(nn.Module):
             'random': randomly chose initial centroids from input data.
             'kmeans++': use the (deterministic farthest-point) k-means++ of the reference. (default: 'kmeans++')
 
-    ``sync_every``: Lloyd iterations enqueued between host checks of the device-side convergence
-    flag (the reference synchronises every iteration at kmeans.py:239; the stopping iteration is the
-    same, later launches are no-ops).
+    ``fused`` (default): the whole Lloyd loop of ``fit`` runs in ONE persistent cooperative kernel
+    (``et_kmeans_lloyd``: grid barriers instead of relaunches, convergence test on the device).
+    ``fused = False`` / ``verbose``: one assign + finalize launch pair per iteration, ``sync_every``
+    iterations enqueued between host checks of the device-side convergence flag (the reference
+    synchronises every iteration at kmeans.py:239; the stopping iteration is the same, later
+    launches are no-ops).  Both produce identical centroids, labels and iteration counts.
     """
 
     def __init__(self, n_clusters, n_redo=1, max_iter=100, tol=1e-4, init_mode="kmeans++", verbose=False):
@@ -44,6 +47,7 @@ class BatchKMeans(nn.Module):
         self.init_mode = init_mode
         self.verbose = verbose
         self.sync_every = 8
+        self.fused = True        # whole Lloyd loop in one persistent kernel; False: one launch pair per iteration
         self.n_iter_ = None
         self.inertia_ = None
 
@@ -141,6 +145,13 @@ class BatchKMeans(nn.Module):
     def _lloyd(self, x, centroids, acc):
         """Run Lloyd iterations from ``centroids`` on the device.  Returns (labels, centroids, n_iter, error, inertia)."""
         l, d, n = x.shape
+        if self.fused and not self.verbose and self.max_iter >= 1:
+            # one persistent cooperative launch for the whole loop (no host round trip per iteration); the single
+            # host read below is the result the caller needs anyway
+            labels, final = ops.kmeans_lloyd(x, centroids.contiguous(), acc, self.max_iter, self.tol)
+            _, n_iter = (int(v) for v in acc.status.tolist())
+            inertia = -(acc.simsum_last / n).mean()
+            return labels, final, n_iter, acc.err.clone(), inertia
         bufs = [centroids.contiguous().clone(), torch.empty_like(centroids)]
         acc.reset()
         done = 0

@@ -561,6 +561,21 @@ def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None
     return maxsims, labels
 
 
+def kmeans_lloyd(data, centroids, acc, max_iter, tol, want_labels=True):
+    """The whole Lloyd loop of ``BatchKMeans.fit`` in one persistent launch (no host sync inside).
+
+    Returns (labels (l,N) int64 of the last assignment | None, centroids (l,d,K) after the last update);
+    ``acc.status`` = {converged, iterations}, ``acc.err``, ``acc.simsum_last`` are filled on the device."""
+    l, d, n = data.shape
+    k = centroids.size(-1)
+    out = torch.empty((l, d, k), device=data.device)
+    labels = torch.empty((l, n), dtype=torch.int64, device=data.device) if want_labels else None
+    check(load().et_kmeans_lloyd(ptr(data), ptr(centroids), l, d, n, k, int(max_iter), float(tol), ptr(out), ptr(labels),
+                                 ptr(acc.err), ptr(acc.status), ptr(acc.simsum_last), ptr(acc.ws), stream_of(data.device)),
+          "et_kmeans_lloyd")
+    return labels, out
+
+
 def kmeans_accumulate(data, labels, acc):
     """Masked sums / counts of compute_centroids for given labels (added into ``acc``)."""
     l, d, n = data.shape

@@ -205,6 +205,17 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
                      int k_clusters, int64_t* labels, float* maxsims, double* sums,
                      double* counts, double* simsum, void* workspace, const int32_t* status,
                      et_stream_t stream);
+/* The whole Lloyd loop of BatchKMeans.fit (kmeans.py:226-239) in ONE persistent cooperative launch: up to max_iter
+ * iterations of {get_labels, compute_centroids, calculate_error, `if error <= tol: break`} with the grid-wide sums
+ * folded behind in-kernel grid barriers, no host round trip and no relaunch (the data stay L2 resident), then one
+ * more scan that writes the labels of the last assignment -- the ones fit() returns -- when labels != null.
+ * centroids (l,d,K) in; centroids_out (l,d,K) = centroids after the last update; optional err[1] (float64, error of
+ * the last iteration over all l), status (device int32[2]) = {converged, iterations done}, simsum_last (l) = sum of
+ * the best similarities of the last assignment (inertia = -simsum_last / N).  Arithmetic identical to the
+ * et_kmeans_assign + et_kmeans_finalize sequence.  workspace: et_kmeans_workspace_bytes(), zero-filled once. */
+int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
+                    int max_iter, double tol, float* centroids_out, int64_t* labels, double* err,
+                    int32_t* status, double* simsum_last, void* workspace, et_stream_t stream);
 /* Accumulation half of compute_centroids (kmeans.py:160-184) for caller-supplied labels
  * (l,N) int64; labels outside [0,K) are ignored.  sums / counts / workspace as above. */
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n,
@@ -247,6 +258,27 @@ int et_ade_fde(const float* pred, const float* gt, int s, int64_t n, int t, floa
  * samples in which the pedestrian comes within `thres` (reference: 0.2) of another one during
  * the first 14 quarter-frame interpolated steps. */
 int et_col(const float* pred, int s, int64_t n, int t, float thres, float* col, et_stream_t stream);
+
+/* ---- dataset preprocessing (HOST side): utils/dataloader.py ------------------------------ */
+/* read_file (dataloader.py:121-132): parse a text buffer of `<frame><delim><ped><delim><x><delim><y>` lines
+ * (each line stripped, split on delim, every field through float()) into rows_host (capacity, 4) float64.
+ * rows_host = null only counts.  *n_rows_host receives the number of rows.  A blank line, a field that is not a
+ * number or a line without exactly four fields is ET_ERR_BADARG (the reference raises ValueError / fails later). */
+int et_dataset_parse_host(const char* text_host, size_t len, char delim, double* rows_host,
+                          int64_t capacity, int64_t* n_rows_host);
+/* The per-file body of TrajectoryDataset.__init__ (dataloader.py:189-226) plus poly_fit (dataloader.py:135-151):
+ * frames = unique(rows[:,0]); for every window of obs_len + pred_len consecutive frames starting at
+ * idx = 0, skip, 2 skip, ... the pedestrians (ascending id) present from its first to its last frame are kept,
+ * coordinates rounded to 4 decimals (np.around); a window is kept when it holds MORE than min_ped of them.
+ * Outputs (all host): traj_host (cap_peds, obs_len + pred_len, 2) float32 "NTC", non_linear_host (cap_peds)
+ * = 1.0 where the quadratic-fit residuals of the last pred_len frames reach `threshold`, peds_in_seq_host
+ * (cap_seq) int32; *n_peds_host / *n_seq_host the counts.  traj_host = null only counts.  n_rows bounds both
+ * counts.  A pedestrian that spans a window with missing / duplicated frames is ET_ERR_BADARG (ValueError in
+ * the reference), as is a frame id that changes under 4-decimal rounding. */
+int et_dataset_windows_host(const double* rows_host, int64_t n_rows, int obs_len, int pred_len, int skip,
+                            double threshold, int min_ped, float* traj_host, float* non_linear_host,
+                            int32_t* peds_in_seq_host, int64_t cap_peds, int64_t cap_seq,
+                            int64_t* n_peds_host, int64_t* n_seq_host);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,11 @@ def main():
     a, m = time_op(lambda: ops.kmeans_assign(data, cent))
     add("kmeans get_labels (labels int64 + maxsims written)", n, 24 + 12, a, m, "point", "includes torch.empty")
 
+    # the whole Lloyd loop in one persistent launch: tol < 0 never converges, so exactly 100 iterations run
+    a, m = time_op(lambda: ops.kmeans_lloyd(data, cent, acc, 100, -1.0, want_labels=False), reps=5, flush=False)
+    add("kmeans whole-fit kernel: per Lloyd iteration (100 iterations, 1 launch, L2-resident)", n, 24, a / 100, m / 100, "point",
+        "et_kmeans_lloyd, in-kernel grid barriers")
+
     def seed():
         np.random.seed(0)
         km.initialize_centroids(data)

@@ -237,7 +237,72 @@ def model_forward():
          **{"sd_" + k: v for k, v in sd.items()})
 
 
+def _synthetic_scene_text(seed, n_frames, n_peds, frame_step=10, drop_frames=(), decimals=6):
+    """A dataset file in the reference's format: pedestrians with contiguous random lifetimes, a few frames
+    missing altogether, coordinates with more than 4 decimals (exercises np.around)."""
+    rng = np.random.RandomState(seed)
+    frames = [f * frame_step for f in range(n_frames) if f not in drop_frames]
+    rows = []
+    for ped in range(1, n_peds + 1):
+        start = rng.randint(0, len(frames) - 2)
+        life = rng.randint(1, 45)
+        p = rng.uniform(-8, 8, size=2)
+        v = rng.uniform(-0.6, 0.6, size=2)
+        curve = rng.normal(0, 0.02, size=2) if ped % 3 == 0 else np.zeros(2)
+        for j, fi in enumerate(range(start, min(start + life, len(frames)))):
+            wiggle = 0.12 * np.sin(0.9 * j + ped) if ped % 4 == 0 else 0.0      # not a quadratic: non-linear flag
+            pos = p + v * j + curve * j * j + wiggle + rng.normal(0, 0.002, size=2)
+            rows.append((frames[fi], float(ped), pos[0], pos[1]))
+    rows.sort(key=lambda r: (r[0], rng.rand()))          # frame-major, pedestrians in arbitrary order inside a frame
+    return "".join(f"{fr:d}\t{ped:.1f}\t{x:.{decimals}f}\t{y:.{decimals}f}\n" for fr, ped, x, y in rows)
+
+
+def dataset():
+    """utils/dataloader.py: TrajectoryDataset / TrajBatchSampler / traj_collate_fn on the ETH test file and on
+    synthetic two-file splits (text inputs are stored with the outputs)."""
+    import tempfile
+    from utils.dataloader import TrajBatchSampler, traj_collate_fn
+
+    out = {}
+
+    def run(tag, files, **kw):
+        with tempfile.TemporaryDirectory() as tmp:
+            for name, text in files.items():
+                with open(os.path.join(tmp, name), "w") as f:
+                    f.write(text)
+            ds = TrajectoryDataset(tmp + "/", **kw)
+            order = os.listdir(tmp)
+        out[f"{tag}_file_order"] = np.array(order)
+        for name, text in files.items():
+            out[f"{tag}_text_{name}"] = np.frombuffer(text.encode(), dtype=np.uint8)
+        out[f"{tag}_obs"] = npy(ds.obs_traj.contiguous())
+        out[f"{tag}_pred"] = npy(ds.pred_traj.contiguous())
+        out[f"{tag}_loss_mask"] = npy(ds.loss_mask)
+        out[f"{tag}_non_linear"] = npy(ds.non_linear_ped)
+        out[f"{tag}_num_peds_in_seq"] = np.asarray(ds.num_peds_in_seq)
+        out[f"{tag}_seq_start_end"] = np.asarray(ds.seq_start_end)
+        return ds
+
+    with open(os.path.join(REF, "datasets/eth/test/biwi_eth.txt")) as f:
+        eth_text = f.read()
+    ds = run("eth", {"biwi_eth.txt": eth_text}, obs_len=8, pred_len=12)
+    # test-phase batching (no shuffle): batch index lists and one collated batch
+    batches = list(TrajBatchSampler(ds, batch_size=32, shuffle=False, drop_last=False))
+    out["eth_batch_sizes"] = np.array([len(b) for b in batches])
+    out["eth_batch_first"] = np.array(batches[0])
+    col = traj_collate_fn([ds[i] for i in batches[3]])
+    out["eth_b3_obs"], out["eth_b3_pred"] = npy(col[0]), npy(col[1])
+    out["eth_b3_scene_mask"], out["eth_b3_seq_start_end"] = npy(col[4]), npy(col[5])
+
+    syn = {"a.txt": _synthetic_scene_text(1, 90, 60, drop_frames=(17, 40)),
+           "b.txt": _synthetic_scene_text(2, 70, 45, frame_step=6, decimals=5)}
+    run("syn", syn, obs_len=8, pred_len=12)
+    run("syn_skip3", syn, obs_len=8, pred_len=12, skip=3)
+    run("syn_short", syn, obs_len=3, pred_len=5, min_ped=0, threshold=0.002)
+    save("dataset.npz", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["eth_test", "eth_init", "descriptor_syn", "kmeans", "metrics", "model_forward"]
+    which = sys.argv[1:] or ["eth_test", "eth_init", "descriptor_syn", "kmeans", "metrics", "model_forward", "dataset"]
     for w in which:
         globals()[w]()

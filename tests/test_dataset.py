@@ -1,0 +1,127 @@
+"""CPU: the native dataset preprocessing (utils/dataloader.py:121-232 in C++ behind the C ABI) against outputs of the
+unmodified reference frozen in tests/golden/dataset.npz (make_golden.py::dataset).  Host-side code: no GPU needed."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset.npz")
+
+
+@pytest.fixture(scope="module")
+def dl():
+    import __graft_entry__ as g
+    g.build()
+    from eigentrajectory_b200 import dataloader
+    return dataloader
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def write_split(tmp_path, gold, tag, names):
+    # the reference lists files with os.listdir; recreate them in the recorded order so that a different directory
+    # order on this machine cannot permute the concatenation
+    d = tmp_path / tag
+    d.mkdir()
+    for name in names:
+        (d / name).write_bytes(gold[f"{tag}_text_{name}"].tobytes())
+    return str(d) + "/"
+
+
+def check_dataset(ds, gold, tag):
+    assert torch.equal(ds.obs_traj, torch.from_numpy(gold[f"{tag}_obs"]))            # bit-exact float32
+    assert torch.equal(ds.pred_traj, torch.from_numpy(gold[f"{tag}_pred"]))
+    assert torch.equal(ds.loss_mask, torch.from_numpy(gold[f"{tag}_loss_mask"]))
+    assert torch.equal(ds.non_linear_ped, torch.from_numpy(gold[f"{tag}_non_linear"]))
+    assert np.array_equal(ds.num_peds_in_seq, gold[f"{tag}_num_peds_in_seq"])
+    assert np.array_equal(np.asarray(ds.seq_start_end), gold[f"{tag}_seq_start_end"])
+    assert len(ds) == len(gold[f"{tag}_num_peds_in_seq"])
+    assert ds.obs_traj.is_contiguous() and ds.obs_traj.dtype == torch.float32
+
+
+def ordered_listdir(monkeypatch, order):
+    real = os.listdir
+    monkeypatch.setattr(os, "listdir", lambda p: list(order) if set(real(p)) == set(order) else real(p))
+
+
+def test_eth_test_split_matches_reference(dl, gold, tmp_path):
+    path = write_split(tmp_path, gold, "eth", ["biwi_eth.txt"])
+    ds = dl.TrajectoryDataset(path, obs_len=8, pred_len=12)
+    check_dataset(ds, gold, "eth")
+    # batching of the test phase and one collated batch
+    batches = list(dl.TrajBatchSampler(ds, batch_size=32, shuffle=False, drop_last=False))
+    assert np.array_equal(np.array([len(b) for b in batches]), gold["eth_batch_sizes"])
+    assert np.array_equal(np.array(batches[0]), gold["eth_batch_first"])
+    col = dl.traj_collate_fn([ds[i] for i in batches[3]])
+    assert torch.equal(col[0], torch.from_numpy(gold["eth_b3_obs"])) and torch.equal(col[1], torch.from_numpy(gold["eth_b3_pred"]))
+    assert torch.equal(col[4], torch.from_numpy(gold["eth_b3_scene_mask"]))
+    assert torch.equal(col[5], torch.from_numpy(gold["eth_b3_seq_start_end"]))
+
+
+@pytest.mark.parametrize("tag,kw", [("syn", dict(obs_len=8, pred_len=12)),
+                                    ("syn_skip3", dict(obs_len=8, pred_len=12, skip=3)),
+                                    ("syn_short", dict(obs_len=3, pred_len=5, min_ped=0, threshold=0.002))])
+def test_synthetic_splits_match_reference(dl, gold, tmp_path, monkeypatch, tag, kw):
+    order = [str(x) for x in gold[f"{tag}_file_order"]]
+    path = write_split(tmp_path, gold, tag, order)
+    ordered_listdir(monkeypatch, order)
+    ds = dl.TrajectoryDataset(path, **kw)
+    check_dataset(ds, gold, tag)
+    assert 0 < float(ds.non_linear_ped.sum()) < len(ds.non_linear_ped)       # both classes occur in the fixture
+
+
+def test_read_file_and_get_dataloader(dl, gold, tmp_path):
+    d = tmp_path / "eth" / "test"
+    d.mkdir(parents=True)
+    (d / "biwi_eth.txt").write_bytes(gold["eth_text_biwi_eth.txt"].tobytes())
+    rows = dl.read_file(str(d / "biwi_eth.txt"))
+    text = gold["eth_text_biwi_eth.txt"].tobytes().decode()
+    want = np.asarray([[float(v) for v in line.strip().split("\t")] for line in text.splitlines()])
+    assert rows.dtype == np.float64 and np.array_equal(rows, want)
+    loader = dl.get_dataloader(str(tmp_path / "eth"), "test", 8, 12, 1)
+    first = next(iter(loader))
+    assert first[0].shape[1:] == (8, 2) and first[1].shape[1:] == (12, 2)
+    assert first[4].dtype == torch.bool and first[4].shape == (first[0].size(0),) * 2
+    n_batches = sum(1 for _ in loader)
+    assert n_batches == len(gold["eth_num_peds_in_seq"])
+
+
+def test_cache_round_trip(dl, gold, tmp_path):
+    path = write_split(tmp_path, gold, "eth", ["biwi_eth.txt"])
+    ds = dl.TrajectoryDataset(path, obs_len=8, pred_len=12)
+    ds.save(str(tmp_path / "eth.etds"))
+    ds2 = dl.TrajectoryDataset.load(str(tmp_path / "eth.etds"))
+    check_dataset(ds2, gold, "eth")
+    assert ds2[5][0].shape == ds[5][0].shape and torch.equal(ds2[5][1], ds[5][1])
+
+
+def test_malformed_inputs_fail_loudly(dl, tmp_path):
+    from eigentrajectory_b200 import ETLibraryError
+    good = "".join(f"{10 * f}\t{p}.0\t{0.1 * f + p:.4f}\t{0.2 * f:.4f}\n" for f in range(25) for p in (1, 2, 3))
+
+    def build(text, **kw):
+        d = tmp_path / f"case{build.n}"
+        build.n += 1
+        d.mkdir()
+        (d / "f.txt").write_text(text)
+        return dl.TrajectoryDataset(str(d) + "/", **kw)
+    build.n = 0
+    ds = build(good)
+    assert len(ds) == 6 and ds.obs_traj.shape == (18, 8, 2)         # 25 frames -> 6 windows of 3 pedestrians
+    with pytest.raises(ETLibraryError):
+        build(good + "\n")                                          # blank line: float('') in the reference
+    with pytest.raises(ETLibraryError):
+        build(good.replace("\t1.0\t", "\tabc\t", 1))                # not a number
+    with pytest.raises(ETLibraryError):
+        build("\n".join(ln for ln in good.splitlines() if not ln.startswith("100\t2.0")) + "\n")   # a gap inside a window
+    with pytest.raises(ETLibraryError):
+        build("")                                                   # empty file
+    # a window needs MORE than min_ped pedestrians (dataloader.py:221)
+    one = "".join(f"{10 * f}\t1.0\t{0.1 * f:.4f}\t0.0\n" for f in range(25))
+    assert len(build(one + "0\t2.0\t5.0\t5.0\n", min_ped=0)) == 6
+    with pytest.raises(ValueError):
+        build(one)                                                  # nothing kept: np.concatenate of nothing, as the reference

@@ -243,12 +243,43 @@ def test_kmeans_fit_free_running(et):
     # explicit centroids + sync_every=1 reproduces the same fit
     km2 = et.BatchKMeans(n_clusters=20)
     km2.sync_every = 1
+    km2.fused = False           # one launch pair per iteration instead of the persistent whole-fit kernel
     labels2 = km2.fit(data, centroids=t(g["init_centroids"]).cuda())
-    assert km2.n_iter_ == km.n_iter_ and int((labels2 != labels).sum()) <= 8
+    assert km2.n_iter_ == km.n_iter_ and torch.equal(labels2, labels) and torch.equal(km2.centroids, km.centroids)
+    assert km2.inertia_ == km.inertia_
     sd = km.state_dict()
     km3 = et.BatchKMeans(n_clusters=20)
     km3.load_state_dict(sd)
     assert torch.equal(km3.centroids, km.centroids)
+
+
+@pytest.mark.parametrize("l,d,k,n,max_iter", [(1, 6, 20, 1_000_000, 7), (1, 6, 20, 50_000, 100), (3, 6, 20, 2049, 100),
+                                               (2, 5, 7, 3000, 100), (1, 8, 32, 4099, 30), (2, 16, 64, 5000, 15),
+                                               (1, 6, 4, 33, 100), (1, 3, 2, 1, 5)])
+def test_kmeans_whole_fit_kernel_equals_stepwise(et, l, d, k, n, max_iter):
+    """et_kmeans_lloyd (persistent kernel, in-kernel grid barriers) == the assign/finalize launch sequence, bit for bit."""
+    gen = torch.Generator().manual_seed(l * 1000 + d * 10 + k)
+    scale = torch.linspace(4.0, 0.3, d)[None, :, None]
+    data = (torch.randn(l, d, n, generator=gen) * scale).contiguous().cuda()
+    cent = data[:, :, torch.randperm(n, generator=gen)[:min(k, n)].cuda()].contiguous()
+    if cent.size(-1) < k:       # fewer points than clusters: pad with shifted copies (empty clusters -> NaN centroids)
+        cent = torch.cat([cent, cent[:, :, :1].expand(l, d, k - cent.size(-1)) + 1.0], dim=-1).contiguous()
+    res = []
+    for fused in (True, False):
+        km = et.BatchKMeans(n_clusters=k, max_iter=max_iter)
+        km.fused = fused
+        labels = km.fit(data, centroids=cent.clone())
+        res.append((labels, km.centroids, km.n_iter_, km.inertia_))
+    (la, ca, ia, ja), (lb, cb, ib, jb) = res
+    assert ia == ib and (ia is None or 1 <= ia <= max_iter)     # None: NaN inertia (an emptied cluster), in both modes
+    assert torch.equal(la, lb)
+    assert torch.equal(ca.isnan(), cb.isnan()) and torch.equal(ca.nan_to_num(0.0), cb.nan_to_num(0.0))
+    assert ja == jb or (ja != ja and jb != jb)
+    # the workspace is reusable: a second fused fit on the same object gives the same answer
+    km = et.BatchKMeans(n_clusters=k, max_iter=max_iter)
+    l1 = km.fit(data, centroids=cent.clone())
+    l2 = km.fit(data, centroids=cent.clone())
+    assert torch.equal(l1, l2) and torch.equal(l1, la)
 
 
 def test_kmeans_update_matches_fp64_and_empty_cluster(et, O):
