@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     const int32_t* __restrict__ status, const int64_t* __restrict__ labels_in, const KmLloyd fit) {
   if (status && status[0] != 0) return;   // converged on an earlier iteration: nothing to do (uniform over the grid)
   constexpr int RECMAX = KMAX * (DMAX + 1);
-  constexpr int NQ = (RECMAX + 31) / 32;
+  constexpr int NJP = (KMAX * (DMAX / 2) + 31) / 32;        // record rows per lane: coordinate pairs ...
+  constexpr int NJS = (KMAX * 2 + 31) / 32;                 // ... and singles (odd coordinate, count)
   constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* cs = reinterpret_cast<float*>(km_smem);            // [DMAX][KMAX]
@@ -232,16 +233,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (EXACT) d = DMAX;                                      // lets the record layout below fold to constants
   const int rec = k * (d + 1);
-  float* lanerec = reinterpret_cast<float*>(blk + RECMAX + 1) + (size_t)warp * rec * 32;   // rec * 32 floats
+  // (blk is padded to an even number of doubles: the records below are read with 128-bit accesses)
+  float* lanerec = reinterpret_cast<float*>(blk + ((RECMAX + 2) & ~1)) + (size_t)warp * rec * 32;   // rec * 32 floats
   const bool whole_fit = fit.cent_out != nullptr;
   const bool accumulate = sums != nullptr || whole_fit;
   const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
   float* lanesingle = lanerec + (size_t)k * npair * 64;
-  // float offset of column `col` (= lane) of record entry (c, r), r in [0, d]
-  auto rec_offset = [&](int c, int r, int col) -> int {
-    return r < 2 * npair ? ((c * npair + (r >> 1)) * 32 + col) * 2 + (r & 1)
-                         : k * npair * 64 + (c * nsingle + (r - 2 * npair)) * 32 + col;
-  };
   __shared__ int nan_centroid;
   __shared__ double red_s[WARPS];
 
@@ -256,39 +253,54 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   const int out_rec = rec + 1;
   const unsigned nblocks = gridDim.x * gridDim.y;
   unsigned phase = 0;
-  double acc[NQ];
+  double accp[NJP][2], accs[NJS];
   double sim_acc = 0.0;
 
-  // fold the 32 lane records into the fp64 registers: lane i owns entries i, i+32, ... (entry e = cluster * (d+1) + r);
-  // it walks the 32 lane columns of each of its entries starting at its own column, always in the same order
-  // (the NQ chains of a lane advance together: NQ independent fp64 additions per step instead of one long chain)
+  // Fold the 32 lane records of this warp: lane i owns record rows i, i+32, ... (a row = the 32 lane columns of one
+  // coordinate pair, or of one single); it sums the columns of a row in fp32 with 128-bit loads and FADD2 -- one
+  // instruction per element instead of a conversion and an fp64 addition each -- starting at a lane-dependent column
+  // (conflict-free, and a fixed order per row), and only the row sums go to the fp64 registers.  fp32 therefore
+  // carries at most 32 * KM_FLUSH_EVERY points; everything above that (warps, blocks, grid, iterations) is fp64.
   auto flush = [&]() {
     __syncwarp();
-    float* row[NQ];
-    int step[NQ];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int e = lane + 32 * q;
-      const int c = e / (d + 1), r = e - c * (d + 1);
-      row[q] = e < rec ? lanerec + rec_offset(c, r, 0) : nullptr;
-      step[q] = r < 2 * npair ? 2 : 1;
-    }
-    double s[NQ];
+    for (int j = 0; j < NJP; ++j) {
+      const int rho = lane + 32 * j;
+      if (rho < k * npair) {
+        ulonglong2* row = reinterpret_cast<ulonglong2*>(lanerec + rho * 64);
+        f32x2_t sa = pack2(0.f, 0.f), sb = sa;
+        const ulonglong2 z = make_ulonglong2(0ull, 0ull);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) s[q] = 0.0;
-#pragma unroll 4
-    for (int cc = 0; cc < 32; ++cc) {
-      const int col = (cc + lane) & 31;
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        if (row[q]) {
-          s[q] += (double)row[q][col * step[q]];
-          row[q][col * step[q]] = 0.f;
+        for (int st = 0; st < 16; ++st) {
+          const int cp = (st + lane) & 15;
+          const ulonglong2 v = row[cp];
+          row[cp] = z;
+          sa = add2(sa, v.x);
+          sb = add2(sb, v.y);
         }
+        float lo, hi;
+        unpack2(add2(sa, sb), lo, hi);
+        accp[j][0] += (double)lo;
+        accp[j][1] += (double)hi;
       }
     }
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] += s[q];
+    for (int j = 0; j < NJS; ++j) {
+      const int sg = lane + 32 * j;
+      if (sg < k * nsingle) {
+        float4* row = reinterpret_cast<float4*>(lanesingle + sg * 32);
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+          const int cp = (st + lane) & 7;
+          const float4 v = row[cp];
+          row[cp] = make_float4(0.f, 0.f, 0.f, 0.f);
+          sa += v.x + v.y;
+          sb += v.z + v.w;
+        }
+        accs[j] += (double)(sa + sb);
+      }
+    }
     __syncwarp();
   };
 
@@ -319,7 +331,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     int64_t* labels_out = whole_fit ? (final_pass ? fit.labels_final : nullptr) : labels;
     float* maxsims_out = whole_fit ? nullptr : maxsims;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    for (int j = 0; j < NJP; ++j) accp[j][0] = accp[j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJS; ++j) accs[j] = 0.0;
     sim_acc = 0.0;
 
     constexpr int PPL = 2;                                   // points per lane and iteration (instruction-level parallelism)
@@ -415,9 +429,21 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     for (int w = 0; w < WARPS; ++w) {
       if (warp == w) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-          const int e = lane + 32 * q;
-          if (e < rec) blk[e] += acc[q];
+        for (int j = 0; j < NJP; ++j) {
+          const int rho = lane + 32 * j;
+          if (rho < k * npair) {
+            const int c = rho / npair, e = c * (d + 1) + 2 * (rho - c * npair);
+            blk[e] += accp[j][0];
+            blk[e + 1] += accp[j][1];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NJS; ++j) {
+          const int sg = lane + 32 * j;
+          if (sg < k * nsingle) {
+            const int c = sg / nsingle;
+            blk[c * (d + 1) + 2 * npair + (sg - c * nsingle)] += accs[j];
+          }
         }
         if (lane == 0) blk[rec] += sim_acc;
       }
@@ -495,7 +521,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
 
 template <int DMAX, int KMAX>
 static size_t km_smem_bytes(int d, int k, int warps, bool accumulate) {
-  return (size_t)(2 * DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)(KMAX * (DMAX + 1) + 1) * sizeof(double) +
+  return (size_t)(2 * DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)((KMAX * (DMAX + 1) + 2) & ~1) * sizeof(double) +
          (accumulate ? (size_t)warps * k * (d + 1) * 32 * sizeof(float) : 0);
 }
 
