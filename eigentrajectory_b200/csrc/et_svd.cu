@@ -21,13 +21,16 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-constexpr int GR_WARPS = 4;
+constexpr int GR_WARPS = 16;                 // one 16-warp block per SM: 148 partial records / barrier arrivals
 constexpr int GR_PITCH = 40;                 // floats per staged pedestrian: 16 obs + 24 pred, conflict-free
 constexpr int GR_NBLK_O = 3, GR_NBLK_P = 6;  // upper-triangular 8x8 blocks of the 16x16 / 24x24 Gram matrices
 constexpr int GR_GO = 16 * 16, GR_GP = 24 * 24;
+constexpr int GR_REC = (GR_NBLK_O + GR_NBLK_P) * 64;   // unique entries a warp accumulates: nine 8x8 blocks
+constexpr size_t GR_SMEM = (size_t)GR_WARPS * 32 * GR_PITCH * sizeof(float);   // staging tiles; reused by the block fold
+static_assert(GR_SMEM >= (size_t)GR_WARPS * GR_REC * sizeof(double), "block fold must fit the staging tiles");
 
-// workspace layout: two uint32 barrier counters (zero on entry, zero again on exit), then at byte 128
-// gridDim.x partial matrices of GR_GO + GR_GP doubles.  Cooperative launch (grid barrier before the fold).
+// workspace layout: two uint32 barrier counters (zero on entry, zero again on exit), then at byte 128 the block
+// partials, entry-major: GR_REC rows of gridDim.x doubles.  Cooperative launch (grid barrier before the fold).
 //
 // Each warp walks its tiles of 32 pedestrians with a one-tile register prefetch: the global loads of tile i+1 are in
 // flight while the DMMA phase of tile i runs, so the fp64 tensor pipe is not left idle behind HBM latency.
@@ -36,11 +39,11 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
                                                            int64_t n, int flags, double* __restrict__ G_obs,
                                                            double* __restrict__ G_pred, unsigned* __restrict__ ticket,
                                                            double* __restrict__ partials) {
-  __shared__ __align__(16) float xs[GR_WARPS][32 * GR_PITCH];
-  __shared__ double acc_s[GR_GO + GR_GP];
+  extern __shared__ __align__(16) unsigned char gr_smem[];
+  float* xs = reinterpret_cast<float*>(gr_smem);   // [GR_WARPS][32 * GR_PITCH]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  float* xw = xs[warp];
+  float* xw = xs + warp * (32 * GR_PITCH);
 
   double co[GR_NBLK_O][2], cp[GR_NBLK_P][2];
 #pragma unroll
@@ -112,48 +115,45 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
     __syncwarp();
   }
 
-  // ---- block reduction (fixed warp order => deterministic) ----
-  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) acc_s[e] = 0.0;
+  // ---- block fold (fixed warp order => deterministic): every warp parks its nine 8x8 blocks in the (now free)
+  // staging area -- lane (g, t4) holds entries 8 g + 2 t4, +1 of each block, i.e. 16 contiguous bytes per lane --
+  // and thread e sums entry e over the warps.  Partials go out entry-major so that the grid fold reads them coalesced.
   __syncthreads();
-  const int bo_r[GR_NBLK_O] = {0, 0, 1}, bo_c[GR_NBLK_O] = {0, 1, 1};
-  const int bp_r[GR_NBLK_P] = {0, 0, 0, 1, 1, 2}, bp_c[GR_NBLK_P] = {0, 1, 2, 1, 2, 2};
-  for (int w = 0; w < GR_WARPS; ++w) {
-    if (warp == w) {
+  double* wacc = reinterpret_cast<double*>(gr_smem);     // [GR_WARPS][GR_REC]
+  {
+    double2* mine = reinterpret_cast<double2*>(wacc + warp * GR_REC) + lane;
 #pragma unroll
-      for (int b = 0; b < GR_NBLK_O; ++b) {
-        const int r = 8 * bo_r[b] + g, c = 8 * bo_c[b] + 2 * t4;
-        acc_s[r * 16 + c] += co[b][0];
-        acc_s[r * 16 + c + 1] += co[b][1];
-      }
+    for (int b = 0; b < GR_NBLK_O; ++b) mine[b * 32] = make_double2(co[b][0], co[b][1]);
 #pragma unroll
-      for (int b = 0; b < GR_NBLK_P; ++b) {
-        const int r = 8 * bp_r[b] + g, c = 8 * bp_c[b] + 2 * t4;
-        acc_s[GR_GO + r * 24 + c] += cp[b][0];
-        acc_s[GR_GO + r * 24 + c + 1] += cp[b][1];
-      }
-    }
-    __syncthreads();
-  }
-  // mirror the strictly-upper blocks into the lower triangle
-  for (int e = threadIdx.x; e < GR_GO; e += blockDim.x) {
-    const int r = e / 16, c = e % 16;
-    if ((r >> 3) > (c >> 3)) acc_s[e] = acc_s[c * 16 + r];
-  }
-  for (int e = threadIdx.x; e < GR_GP; e += blockDim.x) {
-    const int r = e / 24, c = e % 24;
-    if ((r >> 3) > (c >> 3)) acc_s[GR_GO + e] = acc_s[GR_GO + c * 24 + r];
+    for (int b = 0; b < GR_NBLK_P; ++b) mine[(GR_NBLK_O + b) * 32] = make_double2(cp[b][0], cp[b][1]);
   }
   __syncthreads();
-  double* mine = partials + (size_t)blockIdx.x * (GR_GO + GR_GP);
-  for (int e = threadIdx.x; e < GR_GO + GR_GP; e += blockDim.x) mine[e] = acc_s[e];
-  // ---- grid fold: after the barrier every warp of the grid sums a few elements over all block partials ----
+  for (int e = threadIdx.x; e < GR_REC; e += blockDim.x) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int w = 0; w < GR_WARPS; ++w) sacc += wacc[w * GR_REC + e];
+    partials[(size_t)e * gridDim.x + blockIdx.x] = sacc;
+  }
+  // ---- grid fold: after the barrier the warps of the grid each sum one entry over all block partials; strictly
+  // upper 8x8 blocks are mirrored into the lower triangle ----
   grid_barrier(ticket, gridDim.x);
-  const int n_el = pred ? GR_GO + GR_GP : GR_GO;
+  const int n_el = pred ? GR_REC : GR_NBLK_O * 64;
   for (int e = blockIdx.x * GR_WARPS + warp; e < n_el; e += gridDim.x * GR_WARPS) {
-    const double tot = warp_fold(partials, GR_GO + GR_GP, (int)gridDim.x, e, lane);
+    const double tot = warp_fold_contig(partials + (size_t)e * gridDim.x, (int)gridDim.x, lane);
     if (lane == 0) {
-      if (e < GR_GO) G_obs[e] += tot;
-      else G_pred[e - GR_GO] += tot;
+      const int b = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+      if (b < GR_NBLK_O) {
+        const int br = b == 2 ? 1 : 0, bc = b == 0 ? 0 : 1;                  // blocks (0,0), (0,1), (1,1)
+        const int r = 8 * br + rr, c = 8 * bc + cc;
+        G_obs[r * 16 + c] += tot;
+        if (br != bc) G_obs[c * 16 + r] += tot;
+      } else {
+        const int q = b - GR_NBLK_O;                                         // (0,0), (0,1), (0,2), (1,1), (1,2), (2,2)
+        const int br = q < 3 ? 0 : (q < 5 ? 1 : 2), bc = q < 3 ? q : (q < 5 ? q - 2 : 2);
+        const int r = 8 * br + rr, c = 8 * bc + cc;
+        G_pred[r * 24 + c] += tot;
+        if (br != bc) G_pred[c * 24 + r] += tot;
+      }
     }
   }
 }
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(SVS_THREADS) svd_small_kernel(const float* __r
   }
 }
 
-static int gram_grid() { return sm_count() * 4; }
+static int gram_grid() { return sm_count(); }
 
 }  // namespace et
 
@@ -479,7 +479,7 @@ using namespace et;
 
 extern "C" {
 
-size_t et_gram_workspace_bytes(void) { return 128 + (size_t)gram_grid() * (GR_GO + GR_GP) * sizeof(double); }
+size_t et_gram_workspace_bytes(void) { return 128 + (size_t)gram_grid() * GR_REC * sizeof(double); }
 
 int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags, double* G_obs,
             double* G_pred, void* workspace, et_stream_t stream) {
@@ -501,11 +501,19 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
     double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128);
     cudaError_t ce;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(gram_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+      cudaFuncSetAttribute(gram_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+      cudaFuncSetAttribute(gram_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+      cudaFuncSetAttribute(gram_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+      attr_done = true;
+    }
     switch (tune_get(ET_TUNE_GRAM_UNROLL)) {
-      case 1: ce = launch_cooperative(gram_fast<1>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      case 4: ce = launch_cooperative(gram_fast<4>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      case 8: ce = launch_cooperative(gram_fast<8>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      default: ce = launch_cooperative(gram_fast<2>, dim3(grid), dim3(GR_WARPS * 32), 0, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 1: ce = launch_cooperative(gram_fast<1>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 4: ce = launch_cooperative(gram_fast<4>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 8: ce = launch_cooperative(gram_fast<8>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      default: ce = launch_cooperative(gram_fast<2>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
     }
     if (ce != cudaSuccess) return fail(ET_ERR_CUDA, "gram_fast: cooperative launch: %s", cudaGetErrorString(ce));
     return check_launch("gram_fast");
