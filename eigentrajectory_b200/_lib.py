@@ -44,6 +44,7 @@ PROTOTYPES = {
     "et_gram_workspace_bytes": (_sz, []),
     "et_gram": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p]),
     "et_eig_jacobi": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "et_eig_jacobi_pair": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "et_svd_small": (_i, [_p, _p, _i, _l, _i, _i, _p, _p, _p]),
     "et_kmeans_workspace_bytes": (_sz, [_i, _i, _i]),
     "et_kmeans_assign": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p]),

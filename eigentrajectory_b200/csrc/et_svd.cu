@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
       for (int c = 0; c < 10; ++c) raw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  int64_t tile = (int64_t)blockIdx.x * GR_WARPS + warp;
+  // warp-major tile order: the n_tiles % (grid * GR_WARPS) left-over tiles land on the low warps of EVERY block, not on
+  // all warps of the first blocks, so no SM (and no scheduler) carries more than one extra tile
+  int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x;
   fetch(tile);
   for (; tile < n_tiles; tile += wstride) {
     {
@@ -210,24 +212,23 @@ __global__ void __launch_bounds__(GG_THREADS) gram_generic(const float* __restri
 //    Per-pair threshold |g_pq| <= eps * sqrt(g_pp g_qq) (high relative accuracy on PSD matrices;
 //    exact-zero rows/columns -- the normalised last observed frame -- never rotate).
 // =======================================================================================
-constexpr int EIG_MAX_THREADS = 256;
+constexpr int EIG_MAX_THREADS = 288;
 constexpr int EIG_MAX_SWEEPS = 60;
 
-// The solve is latency-bound (a 24 x 24 matrix has 288 work items per phase), so the block is sized to the problem:
-// one warp up to m = 24 (phases separated by __syncwarp), more warps only for larger matrices.
+// The solve is latency-bound (a 24 x 24 matrix has 288 work items per phase) and one warp spends ~3 cycles per
+// instruction on it, so the item loops are spread over a few warps (NT threads: 2-3 items each); a single-warp block
+// separates phases by __syncwarp.
 __device__ __forceinline__ void eig_sync() {
   if (blockDim.x <= 32) __syncwarp();
   else __syncthreads();
 }
 
-// MP != 0: the padded size is a compile-time constant and the block is one warp, so every index computation and the
-// item loops (9 items per lane for 24 x 24) unroll completely.
-template <int MP>
-__global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
-                                                                     float* __restrict__ U, float* __restrict__ S,
-                                                                     double* __restrict__ U64, double* __restrict__ S64,
-                                                                     int* __restrict__ info) {
-  extern __shared__ double sm[];
+// MP != 0: the padded size and the block size NT are compile-time constants, so every index computation and the item
+// loops unroll completely.
+template <int MP, int NT>
+__device__ __forceinline__ void eig_jacobi_body(const double* __restrict__ G, int m, int k, float* __restrict__ U,
+                                                float* __restrict__ S, double* __restrict__ U64,
+                                                double* __restrict__ S64, int* __restrict__ info, double* sm) {
   const int mp = MP ? MP : ((m + 1) & ~1);   // even size; a padding index never rotates
   const int ld = mp + 1;         // odd pitch: column walks (stride ld doubles) are bank-conflict free
   double* A = sm;                // mp x mp, row-major with pitch ld
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
   __shared__ int n_rot, step_rot[2];   // step_rot is double-buffered by step parity (reset one step ahead)
   __shared__ double floor2;            // (1e-18 * largest diagonal entry)^2: rotations below it cannot matter
   int sweeps_done = 0, total_rot = 0;
-  const int tid = threadIdx.x, nthr = MP ? 32 : (int)blockDim.x, half = mp / 2;
+  const int tid = threadIdx.x, nthr = MP ? NT : (int)blockDim.x, half = mp / 2;
 
   for (int e = tid; e < mp * mp; e += nthr) {
     const int r = e / mp, c = e % mp;
@@ -354,6 +355,27 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
     S[j] = (float)sv;
     if (S64) S64[j] = sv;
   }
+}
+
+template <int MP, int NT>
+__global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
+                                                                     float* __restrict__ U, float* __restrict__ S,
+                                                                     double* __restrict__ U64, double* __restrict__ S64,
+                                                                     int* __restrict__ info) {
+  extern __shared__ double sm[];
+  eig_jacobi_body<MP, NT>(G, m, k, U, S, U64, S64, info, sm);
+}
+
+// Both bases of one descriptor (16 x 16 observation and 24 x 24 prediction Gram matrices) in ONE launch: block 0 / 1
+// solve them side by side on two SMs, so the pair costs what the larger solve costs.
+constexpr int EIG_PAIR_THREADS = 288;
+__global__ void __launch_bounds__(EIG_PAIR_THREADS) eig_jacobi_pair_kernel(const double* __restrict__ G_a,
+                                                                           const double* __restrict__ G_b, int k,
+                                                                           float* __restrict__ U_a, float* __restrict__ S_a,
+                                                                           float* __restrict__ U_b, float* __restrict__ S_b) {
+  extern __shared__ double sm[];
+  if (blockIdx.x == 0) eig_jacobi_body<16, EIG_PAIR_THREADS>(G_a, 16, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
+  else eig_jacobi_body<24, EIG_PAIR_THREADS>(G_b, 24, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
 }
 
 // =======================================================================================
@@ -535,21 +557,41 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   const int mp = (m + 1) & ~1;
   const size_t smem = (size_t)(2 * mp * (mp + 1) + mp) * sizeof(double) + (size_t)2 * mp * sizeof(int);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(eig_jacobi_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(ET_ERR_CUDA, "eig_jacobi_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   cudaStream_t st = as_stream(stream);
+  // one work item per thread (measured on B200, 24 x 24: 403 / 211 / 184 / 158 us with 32 / 96 / 144 / 288 threads;
+  // 16 x 16: 117 / 90 / 74 us with 32 / 64 / 128; results bit-identical)
+  const int nt = tune_get(ET_TUNE_EIG_THREADS);      // experiments: 32 = the single-warp variant
   if (mp == 16) {
-    eig_jacobi_kernel<16><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    if (nt == 32) eig_jacobi_kernel<16, 32><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    else eig_jacobi_kernel<16, 128><<<1, 128, smem, st>>>(G, m, k, U, S, U64, S64, info);
   } else if (mp == 24) {
-    eig_jacobi_kernel<24><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    if (nt == 32) eig_jacobi_kernel<24, 32><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    else if (nt == 96) eig_jacobi_kernel<24, 96><<<1, 96, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    else eig_jacobi_kernel<24, 288><<<1, 288, smem, st>>>(G, m, k, U, S, U64, S64, info);
   } else {
     int threads = ((mp / 2) * mp / 9 + 31) / 32 * 32;     // ~9 work items per thread and phase
     if (threads < 32) threads = 32;
     if (threads > EIG_MAX_THREADS) threads = EIG_MAX_THREADS;
-    eig_jacobi_kernel<0><<<1, threads, smem, st>>>(G, m, k, U, S, U64, S64, info);
+    eig_jacobi_kernel<0, 0><<<1, threads, smem, st>>>(G, m, k, U, S, U64, S64, info);
   }
   return check_launch("eig_jacobi_kernel");
+}
+
+int et_eig_jacobi_pair(const double* G_a, int m_a, const double* G_b, int m_b, int k, float* U_a, float* S_a, float* U_b,
+                       float* S_b, et_stream_t stream) {
+  ET_REQUIRE(G_a && G_b && U_a && S_a && U_b && S_b, ET_ERR_BADARG, "et_eig_jacobi_pair: null pointer");
+  ET_REQUIRE(k >= 1 && k <= m_a && k <= m_b, ET_ERR_BADARG, "et_eig_jacobi_pair: k = %d outside [1, min(m)]", k);
+  if (m_a == 16 && m_b == 24) {
+    const size_t smem = (size_t)(2 * 24 * 25 + 24) * sizeof(double) + (size_t)2 * 24 * sizeof(int);
+    eig_jacobi_pair_kernel<<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
+    return check_launch("eig_jacobi_pair_kernel");
+  }
+  int rc = et_eig_jacobi(G_a, m_a, k, U_a, S_a, nullptr, nullptr, nullptr, stream);   // other shapes: two launches
+  if (rc) return rc;
+  return et_eig_jacobi(G_b, m_b, k, U_b, S_b, nullptr, nullptr, nullptr, stream);
 }
 
 int et_svd_small(const float* traj, const int64_t* offsets, int batch, int64_t max_rows, int t, int k, float* U,

@@ -105,8 +105,7 @@ class ETDescriptor(nn.Module):
             U_pred, _ = self._basis(pred_norm_d, self.k)
         else:
             G_obs, G_pred = ops.gram(obs_d, pred_d, tn.ori, tn.rot, tn.sca)
-            U_obs, _ = ops.eig_basis(G_obs, self.k)
-            U_pred, _ = ops.eig_basis(G_pred, self.k)
+            (U_obs, _), (U_pred, _) = ops.eig_basis_pair(G_obs, G_pred, self.k)     # both solves in one launch
         # state / outputs live where the caller's tensors live, as in the reference
         for name in ("traj_ori", "traj_rot", "traj_sca"):
             v = getattr(tn, name)

@@ -485,6 +485,19 @@ def eig_basis(G, k, want64=False, info=None):
     return (U, S, U64, S64) if want64 else (U, S)
 
 
+def eig_basis_pair(G_a, G_b, k):
+    """Both bases of a descriptor in one launch -> ((U_a, S_a), (U_b, S_b)); same results as two ``eig_basis`` calls."""
+    for G in (G_a, G_b):
+        assert G.is_cuda and G.dtype == torch.float64 and G.dim() == 2 and G.size(0) == G.size(1)
+    G_a, G_b = G_a.contiguous(), G_b.contiguous()
+    ma, mb = G_a.size(0), G_b.size(0)
+    U_a, S_a = torch.empty((ma, k), device=G_a.device), torch.empty((k,), device=G_a.device)
+    U_b, S_b = torch.empty((mb, k), device=G_a.device), torch.empty((k,), device=G_a.device)
+    check(load().et_eig_jacobi_pair(ptr(G_a), ma, ptr(G_b), mb, k, ptr(U_a), ptr(S_a), ptr(U_b), ptr(S_b),
+                                    stream_of(G_a.device)), "et_eig_jacobi_pair")
+    return (U_a, S_a), (U_b, S_b)
+
+
 SVD_SMALL_SMEM_BYTES = 200 * 1024
 
 

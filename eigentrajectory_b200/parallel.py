@@ -36,6 +36,9 @@ class CudaBackend:
     def eig(self, G, k):
         return ops.eig_basis(G, k)
 
+    def eig_pair(self, G_a, G_b, k):
+        return ops.eig_basis_pair(G_a, G_b, k)
+
     def new_workspace(self, l, d, k, device):
         return ops.KMeansWorkspace(l, d, k, device)
 
@@ -76,8 +79,11 @@ def sharded_basis(obs_shard, pred_shard, k, ori=True, rot=True, sca=True, group=
     _all_reduce(packed, group)
     G_obs = packed[:no].reshape(G_obs.shape).contiguous()
     G_pred = packed[no:no + np_].reshape(G_pred.shape).contiguous()
-    U_obs, S_obs = backend.eig(G_obs, k)
-    U_pred, S_pred = backend.eig(G_pred, k)
+    if hasattr(backend, "eig_pair"):
+        (U_obs, S_obs), (U_pred, S_pred) = backend.eig_pair(G_obs, G_pred, k)     # both solves in one launch
+    else:
+        U_obs, S_obs = backend.eig(G_obs, k)
+        U_pred, S_pred = backend.eig(G_pred, k)
     return U_obs, S_obs, U_pred, S_pred
 
 

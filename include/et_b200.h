@@ -67,7 +67,8 @@ int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_
 
 /* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
  * Results never depend on them. */
-enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_GRAM_UNROLL = 2, ET_TUNE_COUNT = 8 };
+enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_GRAM_UNROLL = 2, ET_TUNE_EIG_THREADS = 3,
+       ET_TUNE_COUNT = 8 };
 int et_tune(int knob, int value);
 
 /* ---- normaliser: EigenTrajectory/normalizer.py ------------------------------------- */
@@ -182,6 +183,11 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
  * info (optional, device int32[2]) receives {sweeps executed, rotations applied}. */
 int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64, double* S64,
                   int* info, et_stream_t stream);
+/* The two eigen-solves of one descriptor (ETDescriptor.parameter_initialization, descriptor.py:134-135: observation and
+ * prediction bases) in one launch, side by side on two SMs; (m_a, m_b) = (16, 24) takes the fused kernel, any other
+ * pair of sizes is two et_eig_jacobi launches.  Results are bit-identical to et_eig_jacobi. */
+int et_eig_jacobi_pair(const double* G_a, int m_a, const double* G_b, int m_b, int k, float* U_a,
+                       float* S_a, float* U_b, float* S_b, et_stream_t stream);
 /* Batched small-N SVD: one-sided (Hestenes) Jacobi on shared-memory resident tall-skinny
  * matrices.  Problem b is the (n_b x 2T) matrix of the trajectories
  * traj[offsets[b] .. offsets[b+1]) (already normalised).  offsets is a DEVICE int64 array

@@ -171,6 +171,29 @@ def test_gram_linearity_and_sharding_property(et, O):
     assert torch.equal(Go, Go2) and torch.equal(Gp, Gp2)
 
 
+def test_eig_pair_equals_two_solves(et, O):
+    """et_eig_jacobi_pair (both bases in one launch, multi-warp blocks) is bit-identical to two et_eig_jacobi calls."""
+    obs, pred = O.synthetic_trajectories(50_000, seed=4)
+    Go, Gp = et.ops.gram(obs.cuda(), pred.cuda(), True, True, True)
+    (Ua, Sa), (Ub, Sb) = et.ops.eig_basis_pair(Go, Gp, 6)
+    Ua1, Sa1 = et.ops.eig_basis(Go, 6)
+    Ub1, Sb1 = et.ops.eig_basis(Gp, 6)
+    assert torch.equal(Ua, Ua1) and torch.equal(Sa, Sa1) and torch.equal(Ub, Ub1) and torch.equal(Sb, Sb1)
+    # other shapes fall back to two launches
+    G5 = torch.randn(10, 10, dtype=torch.float64, device="cuda")
+    G5 = G5 @ G5.T
+    (U1, S1), (U2, S2) = et.ops.eig_basis_pair(G5, Gp, 4)
+    assert torch.equal(U1, et.ops.eig_basis(G5, 4)[0]) and torch.equal(U2, et.ops.eig_basis(Gp, 4)[0])
+    # the single-warp variant (tuning knob) gives the same bits as the default multi-warp blocks
+    lib = et.load_library()
+    lib.et_tune(3, 32)
+    try:
+        Ub32, Sb32 = et.ops.eig_basis(Gp, 6)
+    finally:
+        lib.et_tune(3, 0)
+    assert torch.equal(Ub32, Ub1) and torch.equal(Sb32, Sb1)
+
+
 def test_gram_generic_shapes(et, O):
     obs, pred = O.synthetic_trajectories(3001, seed=2, t_obs=5, t_pred=7)
     st = O.norm_params(obs.double())
