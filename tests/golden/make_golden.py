@@ -302,7 +302,55 @@ def dataset():
     save("dataset.npz", **out)
 
 
+def eth_eval():
+    """The evaluation loop of ETTrainer.test (utils/trainer.py:172-195) on the ETH test split, on CPU: reference
+    dataloader (batch_size=1) -> EigenTrajectory.forward through the hook seam (stub predictor, bases / anchors of
+    model_forward.npz) -> ADE / FDE / TCC / COL per pedestrian -> AverageMeter means."""
+    import tempfile
+    from utils.dataloader import get_dataloader
+    from utils.metrics import AverageMeter
+
+    mf = np.load(os.path.join(HERE, "model_forward.npz"))
+    ds = np.load(os.path.join(HERE, "dataset.npz"))
+    W = torch.from_numpy(mf["W"])
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.W = torch.nn.Parameter(W.clone())
+
+        def forward(self, x):
+            return (self.W @ x).reshape(6, 20, -1).permute(0, 2, 1)
+
+    hook = types.SimpleNamespace(
+        model_forward_pre_hook=lambda C, o, info=None: torch.cat([C, o], dim=0),
+        model_forward=lambda x, m: m(x),
+        model_forward_post_hook=lambda y, info=None: y)
+    model = EigenTrajectory(Stub(), hook, HP)
+    sd = {k[3:]: torch.from_numpy(mf[k]) for k in mf.files if k.startswith("sd_")}
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys
+    model.eval()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "test"))
+        with open(os.path.join(tmp, "test", "biwi_eth.txt"), "wb") as f:
+            f.write(ds["eth_text_biwi_eth.txt"].tobytes())
+        loader = get_dataloader(tmp, "test", 8, 12, batch_size=1)
+        funcs = {"ADE": compute_batch_ade, "FDE": compute_batch_fde, "TCC": compute_batch_tcc, "COL": compute_batch_col}
+        meters = {k: AverageMeter() for k in funcs}
+        with torch.no_grad():
+            for batch in loader:
+                obs, pred = batch[:2]
+                out = model(obs)
+                for k, fn in funcs.items():
+                    meters[k].extend(fn(out["recon_traj"], pred))
+    arrs = {f"per_ped_{k}": np.concatenate(m.data, axis=0) for k, m in meters.items()}
+    arrs.update({f"mean_{k}": np.float64(m.mean()) for k, m in meters.items()})
+    print({k: float(v) for k, v in arrs.items() if k.startswith("mean_")})
+    save("eth_eval.npz", **arrs)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["eth_test", "eth_init", "descriptor_syn", "kmeans", "metrics", "model_forward", "dataset"]
+    which = sys.argv[1:] or ["eth_test", "eth_init", "descriptor_syn", "kmeans", "metrics", "model_forward", "dataset", "eth_eval"]
     for w in which:
         globals()[w]()
