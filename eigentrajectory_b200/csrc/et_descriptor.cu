@@ -422,6 +422,11 @@ __global__ void __launch_bounds__(PR_THREADS, MINB) project_reconstruct_tma(cons
     fence_barrier_init();
   }
   __syncthreads();   // barriers are live: the producer starts loading while the consumers stage the bases
+  // Programmatic dependent launch: the launch that follows us in the stream may make its blocks resident (and run its
+  // own prologue up to this point) as ours retire; nothing of OURS below may run before everything that precedes us in
+  // the stream is complete and visible -- the bases, the trajectories and the output buffers are global memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (warp < PR_CONSUMER_WARPS) {
     stage_basis<16, 6>(Uo, U_obs, threadIdx.x, PR_CONSUMER_WARPS * 32);
     stage_basis<24, 6>(Up, U_pred, threadIdx.x, PR_CONSUMER_WARPS * 32);
@@ -805,7 +810,20 @@ static int launch_pr_tma_c(const float* obs, const float* pred, int64_t n, const
   const int n_tiles = (int)((n + PR_TILE - 1) / PR_TILE);
   int grid = sm_count() * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<grid, PR_THREADS, smem, stream>>>(maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred, ori, rot, sca);
+  // launched with programmatic stream serialization: back-to-back calls overlap their launch latency and prologue with
+  // the previous call's tail (the kernel orders itself with griddepcontrol.wait); ET_TUNE_PDL = 1 switches it off
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(PR_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tune_get(ET_TUNE_PDL) == 1 ? 0 : 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, n, n_tiles, U_obs, U_pred, flags, C_obs, C_pred, ori, rot, sca);
+  if (le != cudaSuccess) return fail(ET_ERR_CUDA, "project_reconstruct_tma: launch: %s", cudaGetErrorString(le));
   return check_launch(RECON ? "project_reconstruct_tma" : "project_reconstruct_tma(project)");
 }
 

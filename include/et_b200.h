@@ -68,7 +68,7 @@ int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_
 /* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
  * Results never depend on them. */
 enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_GRAM_UNROLL = 2, ET_TUNE_EIG_THREADS = 3,
-       ET_TUNE_COUNT = 8 };
+       ET_TUNE_PDL = 4, ET_TUNE_COUNT = 8 };
 int et_tune(int knob, int value);
 
 /* ---- normaliser: EigenTrajectory/normalizer.py ------------------------------------- */
