@@ -9,7 +9,7 @@ Same class and function names as the reference's ``EigenTrajectory`` package and
 Everything numerical runs in ``libet_b200.so`` (hand-written CUDA behind a C ABI, see
 ``include/et_b200.h``); importing this package without the built library raises on first use.
 """
-from . import ops  # noqa: F401
+from . import dataloader, ops  # noqa: F401
 from ._lib import ETLibraryError, load as load_library, launch_count  # noqa: F401
 from .anchor import ETAnchor  # noqa: F401
 from .descriptor import ETDescriptor  # noqa: F401
@@ -21,5 +21,5 @@ from .normalizer import TrajNorm  # noqa: F401
 from .utils import DotDict  # noqa: F401
 
 __all__ = ["EigenTrajectory", "ETDescriptor", "ETAnchor", "TrajNorm", "BatchKMeans", "compute_batch_ade",
-           "compute_batch_fde", "compute_batch_ade_fde", "compute_batch_tcc", "compute_batch_col", "compute_batch_metric", "DotDict", "ops", "load_library", "launch_count",
+           "compute_batch_fde", "compute_batch_ade_fde", "compute_batch_tcc", "compute_batch_col", "compute_batch_metric", "DotDict", "ops", "dataloader", "load_library", "launch_count",
            "ETLibraryError"]

@@ -523,19 +523,16 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
     double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128);
     cudaError_t ce;
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(gram_fast<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
-      cudaFuncSetAttribute(gram_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
-      cudaFuncSetAttribute(gram_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
-      cudaFuncSetAttribute(gram_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
-      attr_done = true;
-    }
+    auto launch = [&](auto kern) {      // the attribute is per device: set it on every call (cheap)
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
+      if (e != cudaSuccess) return e;
+      return launch_cooperative(kern, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts);
+    };
     switch (tune_get(ET_TUNE_GRAM_UNROLL)) {
-      case 1: ce = launch_cooperative(gram_fast<1>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      case 4: ce = launch_cooperative(gram_fast<4>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      case 8: ce = launch_cooperative(gram_fast<8>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
-      default: ce = launch_cooperative(gram_fast<2>, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts); break;
+      case 1: ce = launch(gram_fast<1>); break;
+      case 4: ce = launch(gram_fast<4>); break;
+      case 8: ce = launch(gram_fast<8>); break;
+      default: ce = launch(gram_fast<2>); break;
     }
     if (ce != cudaSuccess) return fail(ET_ERR_CUDA, "gram_fast: cooperative launch: %s", cudaGetErrorString(ce));
     return check_launch("gram_fast");

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Round-end style verification on one B200: all GPU tests, smoke, both bench arms, per-kernel table, ncu launch list and
+# full captures.  Everything lands in gpurun_out/ (copied into profiles/ by hand afterwards).  $1 = tag
+TAG=${1:-r01b}
+mkdir -p gpurun_out
+timeout -k 5 900 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider > gpurun_out/t_all_$TAG.log 2>&1; echo "gpu tests exit $?"; tail -n 3 gpurun_out/t_all_$TAG.log | cut -c1-300
+timeout -k 5 200 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -n 1 gpurun_out/smoke_$TAG.log
+timeout -k 5 400 python bench.py > gpurun_out/bench_default_$TAG.log 2>&1; echo "bench exit $?"; tail -n 1 gpurun_out/bench_default_$TAG.log | cut -c1-2000
+timeout -k 5 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference_$TAG.log 2>&1; echo "bench reference exit $?"; tail -n 1 gpurun_out/bench_reference_$TAG.log | cut -c1-400
+timeout -k 5 900 python scripts/bench_kernels.py --cpu --out gpurun_out/kernels_$TAG.json > gpurun_out/kernels_$TAG.log 2>&1; echo "kernels exit $?"; python - <<PY
+import json
+for line in open("gpurun_out/kernels_$TAG.log"):
+    try: r=json.loads(line)
+    except Exception: print(line.strip()[:300]); continue
+    if "avg_ms" in r: print(f"{r['op'][:78]:78s} {1e3*r['avg_ms']:9.1f} us  {r['achieved_gbs']:8.1f} GB/s  {100*r['frac_of_measured_hbm_peak']:5.1f}%")
+    elif "seconds" in r: print(f"CPU {r['op'][:70]:70s} {1e3*r['seconds']:9.1f} ms ({r['cores']} cores)")
+PY
+timeout -k 5 300 python scripts/bench_forward.py > gpurun_out/forward_latency_$TAG.log 2>&1; echo "forward latency exit $?"; tail -n 4 gpurun_out/forward_latency_$TAG.log | cut -c1-300
+# launch list of the bench command (cold-cache, serialised: compare SHARES)
+timeout -k 5 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
+  python bench.py --steps 20 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_under_ncu_$TAG.log 2>&1
+echo "launch list exit $?"
+# full capture of the headline kernel (3 launches) and of the other hot kernels
+timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex:project_reconstruct -s 5 -c 3 -f \
+  -o gpurun_out/prof_pr_$TAG python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_pr_$TAG.log 2>&1
+echo "ncu headline exit $?"
+timeout -k 5 900 ncu --set full --clock-control none --import-source on \
+  -k regex:'gram_fast|kmeans_assign|ade_fde_fast|reconstruct_fast|reconstruct_bwd_fast|eig_jacobi|svd_small|kmeans_seed_step' \
+  -s 20 -c 30 -f -o gpurun_out/prof_ops_$TAG python scripts/exp/run_ops_once.py > gpurun_out/ncu_ops_$TAG.log 2>&1
+echo "ncu ops exit $?"; tail -2 gpurun_out/ncu_ops_$TAG.log
