@@ -674,6 +674,27 @@ __global__ void fill_u64_kernel(unsigned long long* p, int count, unsigned long 
   if (e < count) p[e] = v;
 }
 
+// Row-shard seeding helpers.  A local candidate key (order-preserving similarity bits << 32 | local index) becomes a
+// GLOBAL key that a signed 64-bit MIN all-reduce orders correctly: the index is shifted by the shard's row offset and
+// the top bit is flipped (unsigned order -> signed order); "no candidate" (empty shard) is INT64_MAX.
+__global__ void kmeans_seed_globalize_kernel(unsigned long long* __restrict__ key, int l, unsigned long long row_offset) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= l) return;
+  const unsigned long long k = key[e];
+  key[e] = (k == ~0ull) ? 0x7fffffffffffffffull : ((k + row_offset) ^ 0x8000000000000000ull);
+}
+
+// coords (l,d) float64 = coordinates of the winning global column if this shard owns it, else 0 (the caller sums over ranks)
+__global__ void kmeans_seed_fetch_kernel(const float* __restrict__ data, int l, int d, int64_t n, int64_t row_offset,
+                                         const long long* __restrict__ gkey, double* __restrict__ coords) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= l * d) return;
+  const int li = e / d, r = e % d;
+  const int64_t gidx = (int64_t)(((unsigned long long)gkey[li] ^ 0x8000000000000000ull) & 0xffffffffull);
+  const int64_t local = gidx - row_offset;
+  coords[e] = (local >= 0 && local < n) ? (double)__ldg(data + ((int64_t)li * d + r) * n + local) : 0.0;
+}
+
 __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l, int d, int64_t n, int k,
                                           const unsigned long long* __restrict__ scratch, float* __restrict__ centroids) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -876,6 +897,26 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   }
   kmeans_seed_gather_kernel<<<(l * d * k_clusters + 255) / 256, 256, 0, st>>>(data, l, d, n, k_clusters, scratch, centroids);
   return check_launch("kmeans_seed_gather_kernel");
+}
+
+int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
+                             int64_t row_offset, long long* gkey_out, et_stream_t stream) {
+  ET_REQUIRE(row_offset >= 0 && row_offset + n <= ((int64_t)1 << 32), ET_ERR_UNSUPPORTED,
+             "et_kmeans_seed_candidate: global indices must stay below 2^32");
+  int rc = et_kmeans_seed_step(data, centroids, l, d, n, k_clusters, ncols, reinterpret_cast<unsigned long long*>(gkey_out), stream);
+  if (rc) return rc;
+  kmeans_seed_globalize_kernel<<<(l + 255) / 256, 256, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(gkey_out), l,
+                                                                            (unsigned long long)row_offset);
+  return check_launch("kmeans_seed_globalize_kernel");
+}
+
+int et_kmeans_seed_fetch(const float* data, int l, int d, int64_t n, int64_t row_offset, const long long* gkey,
+                         double* coords, et_stream_t stream) {
+  int rc = km_check(l, d, n, 1);
+  if (rc) return rc;
+  ET_REQUIRE(gkey && coords && (n == 0 || data), ET_ERR_BADARG, "et_kmeans_seed_fetch: null pointer");
+  kmeans_seed_fetch_kernel<<<(l * d + 255) / 256, 256, 0, as_stream(stream)>>>(data, l, d, n, row_offset, gkey, coords);
+  return check_launch("kmeans_seed_fetch_kernel");
 }
 
 int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,

@@ -629,6 +629,25 @@ def kmeans_seed_step(data, centroids, ncols):
     return raw.to(torch.uint32).view(torch.float32), idx
 
 
+def kmeans_seed_candidate(data, centroids, ncols, row_offset, out=None):
+    """Global, signed-orderable candidate key (l,) int64 of a row shard (see et_kmeans_seed_candidate)."""
+    l, d, n = data.shape
+    k = centroids.size(-1)
+    key = out if out is not None else torch.empty((l,), dtype=torch.int64, device=data.device)
+    check(load().et_kmeans_seed_candidate(ptr(data), ptr(centroids), l, d, n, k, int(ncols), int(row_offset), ptr(key),
+                                          stream_of(data.device)), "et_kmeans_seed_candidate")
+    return key
+
+
+def kmeans_seed_fetch(data, row_offset, gkey, out=None):
+    """(l,d) float64 coordinates of the elected column on the owning rank, zeros elsewhere."""
+    l, d, n = data.shape
+    coords = out if out is not None else torch.empty((l, d), dtype=torch.float64, device=data.device)
+    check(load().et_kmeans_seed_fetch(ptr(data), l, d, n, int(row_offset), ptr(gkey), ptr(coords), stream_of(data.device)),
+          "et_kmeans_seed_fetch")
+    return coords
+
+
 # ----------------------------------------------------------------------------------------
 # metrics (utils/metrics.py)
 # ----------------------------------------------------------------------------------------

@@ -51,6 +51,12 @@ class CudaBackend:
     def labels(self, data, cent):
         return ops.kmeans_assign(data, cent, want_labels=True, want_maxsims=False)[1]
 
+    def seed_candidate(self, data, cent, ncols, row_offset, out=None):
+        return ops.kmeans_seed_candidate(data, cent, ncols, row_offset, out=out)
+
+    def seed_fetch(self, data, row_offset, gkey, out=None):
+        return ops.kmeans_seed_fetch(data, row_offset, gkey, out=out)
+
     def seed_step(self, data, cent, ncols):
         return ops.kmeans_seed_step(data, cent, ncols)
 
@@ -110,6 +116,20 @@ def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset
         return pts.to(data_shard.dtype)
 
     first = torch.full((l,), int(first_global_index), dtype=torch.int64, device=dev)
+    if hasattr(backend, "seed_candidate"):      # (every rank must take the same branch: the collectives differ)
+        # device-only step: candidate key -> ONE int64 MIN all-reduce -> owner's coordinates -> ONE SUM all-reduce
+        # (six small launches and two collectives per step, nothing decoded on the host)
+        gkey = first ^ torch.iinfo(torch.int64).min           # key of "global column first", similarity bits zero
+        coords = torch.empty((l, d), dtype=torch.float64, device=dev)
+        for i in range(n_clusters):
+            if i > 0:
+                gkey = backend.seed_candidate(data_shard, cent, i, row_offset, gkey)
+                if world > 1:
+                    dist.all_reduce(gkey, op=dist.ReduceOp.MIN, group=group)
+            backend.seed_fetch(data_shard, row_offset, gkey, coords)
+            _all_reduce(coords, group)
+            cent[:, :, i].copy_(coords)
+        return cent
     cent[:, :, 0] = fetch(first)
     big = torch.iinfo(torch.int64).max
     for i in range(1, n_clusters):

@@ -253,6 +253,17 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
 int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d, int64_t n,
                         int k_clusters, int ncols, unsigned long long* key_out, et_stream_t stream);
 
+/* The two halves of a row-sharded farthest-point step without host round trips: et_kmeans_seed_candidate =
+ * et_kmeans_seed_step with the key made GLOBAL and signed-orderable (index + row_offset in the low 32 bits, top bit
+ * flipped; an empty shard proposes INT64_MAX), so that ONE int64 MIN all-reduce over the ranks elects the winner;
+ * et_kmeans_seed_fetch then writes the winner's coordinates (l,d) as float64 on the rank that owns the column and zeros
+ * elsewhere, so that ONE SUM all-reduce hands them to every rank.  row_offset + n <= 2^32. */
+int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, int d, int64_t n,
+                             int k_clusters, int ncols, int64_t row_offset, long long* gkey_out,
+                             et_stream_t stream);
+int et_kmeans_seed_fetch(const float* data, int l, int d, int64_t n, int64_t row_offset,
+                         const long long* gkey, double* coords, et_stream_t stream);
+
 /* ---- metrics: utils/metrics.py ---------------------------------------------------------- */
 /* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass, optionally with
  * compute_batch_tcc (metrics.py:105-130) from the same read of pred.
