@@ -721,7 +721,23 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
   if (e != cudaSuccess || per_sm < 1) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: occupancy query failed");
   if (per_sm > 8) per_sm = 8;
   int64_t cap = (int64_t)sm_count() * per_sm / l;     // all l * grid.x blocks must be co-resident
-  if (cap < 1) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d exceeds the co-resident block budget", l);
+  if (cap < 1) {
+    // more batch entries than co-resident blocks: the whole-fit kernel cannot run (its convergence test spans all
+    // entries); single passes are cut into launches of as many entries as fit, one block each
+    if (fit.cent_out)
+      return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d exceeds the co-resident block budget of the whole-fit kernel", l);
+    const int lc = sm_count() * per_sm;
+    for (int l0 = 0; l0 < l; l0 += lc) {
+      const int ll = l - l0 < lc ? l - l0 : lc;
+      auto off = [&](auto* p, int64_t stride) { return p ? p + (int64_t)l0 * stride : p; };
+      int rc = km_launch_k<DMAX, KMAX, WARPS, EXACT, KPAD>(off(data, (int64_t)d * n), off(centroids, (int64_t)d * k), ll, d, n, k,
+                                                          off(labels, n), off(maxsims, n), off(sums, (int64_t)d * k),
+                                                          off(counts, k), off(simsum, 1), workspace, status, off(labels_in, n),
+                                                          fit, st);
+      if (rc) return rc;
+    }
+    return ET_OK;
+  }
   int64_t gx = (n + 2 * KM_THREADS_L - 1) / (2 * KM_THREADS_L);     // two points per lane and iteration
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -759,7 +775,7 @@ static int km_launch(const float* data, const float* centroids, int l, int d, in
   // accumulating launches of the reference shape: ONE 12-warp block per SM while its lane-private records fit shared
   // memory -- a third of the partial records and grid-barrier arrivals of the 3 x 4-warp configuration
   if constexpr (EXACT) {
-    if ((sums != nullptr || fit.cent_out != nullptr) && km_smem_bytes<DMAX, KMAX>(d, k, 12, true) <= 224 * 1024)
+    if ((sums != nullptr || fit.cent_out != nullptr) && l <= sm_count() && km_smem_bytes<DMAX, KMAX>(d, k, 12, true) <= 224 * 1024)
       return km_launch_w<DMAX, KMAX, 12, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
                                                 status, labels_in, fit, st);
   }

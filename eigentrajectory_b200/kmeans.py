@@ -145,7 +145,7 @@ class BatchKMeans(nn.Module):
     def _lloyd(self, x, centroids, acc):
         """Run Lloyd iterations from ``centroids`` on the device.  Returns (labels, centroids, n_iter, error, inertia)."""
         l, d, n = x.shape
-        if self.fused and not self.verbose and self.max_iter >= 1:
+        if self.fused and not self.verbose and self.max_iter >= 1 and l <= ops.KMEANS_FUSED_MAX_BATCH:
             # one persistent cooperative launch for the whole loop (no host round trip per iteration); the single
             # host read below is the result the caller needs anyway
             labels, final = ops.kmeans_lloyd(x, centroids.contiguous(), acc, self.max_iter, self.tol)

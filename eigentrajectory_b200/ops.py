@@ -574,6 +574,10 @@ def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None
     return maxsims, labels
 
 
+KMEANS_FUSED_MAX_BATCH = 32     # batch entries l up to which BatchKMeans.fit uses the persistent whole-fit kernel (every entry needs
+                                # co-resident blocks; larger batches run one launch pair per iteration)
+
+
 def kmeans_lloyd(data, centroids, acc, max_iter, tol, want_labels=True):
     """The whole Lloyd loop of ``BatchKMeans.fit`` in one persistent launch (no host sync inside).
 

@@ -305,6 +305,33 @@ def test_kmeans_whole_fit_kernel_equals_stepwise(et, l, d, k, n, max_iter):
     assert torch.equal(l1, l2) and torch.equal(l1, la)
 
 
+def test_kmeans_large_batch_like_the_reference_demo(et, O):
+    """kmeans.py:275-279 clusters x = randn(13, 29, 2, 1000): 377 independent problems, more than fit one launch."""
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(13, 29, 2, 1000, generator=gen)
+    cent = x[..., :20].contiguous()
+    km = et.BatchKMeans(n_clusters=20, max_iter=3)
+    ms, lb = km.get_labels(x.cuda(), cent.cuda())
+    o_ms, o_lb = O.kmeans_assign(x.reshape(-1, 2, 1000), cent.reshape(-1, 2, 20))
+    assert lb.shape == (13, 29, 1000) and torch.equal(lb.cpu().reshape(-1, 1000), o_lb)
+    assert torch.equal(ms.cpu().reshape(-1, 1000), o_ms)
+    labels = km.fit(x.cuda().contiguous(), centroids=cent.cuda())
+    assert labels.shape == (13, 29, 1000) and km.centroids.shape == (13, 29, 2, 20)
+    c = O.kmeans_update(x.reshape(-1, 2, 1000), o_lb, 20)                    # first update of the same loop
+    c1 = km.compute_centroids(x.cuda(), lb)
+    assert rel_max(c1.cpu().reshape(-1, 2, 20).nan_to_num(0.0), c.nan_to_num(0.0)) < TOL
+    # more entries than co-resident blocks: the library cuts the batch into several launches
+    y = torch.randn(1300, 3, 257, generator=gen)
+    cy = y[..., :5].contiguous()
+    km5 = et.BatchKMeans(n_clusters=5, max_iter=2)
+    ms, lb = km5.get_labels(y.cuda(), cy.cuda())
+    o_ms, o_lb = O.kmeans_assign(y, cy)
+    assert torch.equal(lb.cpu(), o_lb) and torch.equal(ms.cpu(), o_ms)
+    c5 = km5.compute_centroids(y.cuda(), lb)
+    assert rel_max(c5.cpu().nan_to_num(0.0), O.kmeans_update(y, o_lb, 5).nan_to_num(0.0)) < TOL
+    assert km5.fit(y.cuda(), centroids=cy.cuda()).shape == (1300, 257)
+
+
 def test_kmeans_update_matches_fp64_and_empty_cluster(et, O):
     gen = torch.Generator().manual_seed(3)
     data = torch.randn(1, 6, 100_000, generator=gen).contiguous()
