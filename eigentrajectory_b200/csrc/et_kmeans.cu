@@ -180,7 +180,51 @@ struct KmLloyd {
   int32_t* status;          // [2] {converged, iterations done}
   double* simsum_last;      // (l) sum of best similarities of the last assignment
   int64_t* labels_final;    // (l,N) optional
+  // Row-sharded fit over peer memory (world > 1): every rank runs this kernel on its rows; after the local grid fold
+  // the ranks exchange their folded records by direct stores into each other's exchange buffers (NVLink / NVSwitch
+  // peer mappings) and a per-iteration flag, then every rank adds the `world` records in rank order -- the all-reduce
+  // of the reference-free sharding scheme, done inside the kernel, no NCCL call and no host in the loop.
+  int rank, world;
+  unsigned char* const* xchg;   // DEVICE array [world]: base of every rank's exchange buffer as mapped on THIS rank
+  unsigned stamp_base;          // flags of this call are stamp_base (ready) and stamp_base + 1 + iteration
 };
+
+// Exchange buffer of one rank: uint32 ready[world] at byte 0, uint32 flag[2][world] at byte 128, then at byte 256
+// double slot[2][world][l * (K (d+1) + 1)] (two parities: iteration i + 1 writes the other half while a slow peer may
+// still read iteration i).
+constexpr int KM_XCHG_HEADER = 256;
+constexpr int KM_XCHG_MAX_WORLD = 16;
+__device__ __forceinline__ unsigned* xchg_ready(unsigned char* base) { return reinterpret_cast<unsigned*>(base); }
+__device__ __forceinline__ unsigned* xchg_flag(unsigned char* base, int parity, int world) {
+  return reinterpret_cast<unsigned*>(base + 128) + parity * world;
+}
+__device__ __forceinline__ double* xchg_slot(unsigned char* base, int parity, int world, int r, size_t slot_doubles) {
+  return reinterpret_cast<double*>(base + KM_XCHG_HEADER) + ((size_t)parity * world + r) * slot_doubles;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Spin until all `world` stamps at flags[0..world) have reached `stamp` (wrap-safe); a peer that never arrives traps
+// the kernel after ~10 s instead of hanging the device.
+__device__ __forceinline__ void xchg_wait_all(const unsigned* flags, int world, unsigned stamp) {
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int r = 0; r < world; ++r) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys(flags + r) - stamp) < 0) {
+      if ((++spins & 0x3ffu) == 0) {          // look at the clock every 1024 polls only
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 10000000000ull) __trap();
+      }
+    }
+  }
+}
 
 // Reusable grid barrier for the whole-fit mode: ctr[0] counts arrivals monotonically (barrier number `phase`, 1-based,
 // completes at phase * nblocks).  km_barrier_exit() restores the zero state once every block has left its last spin.
@@ -237,6 +281,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   float* lanerec = reinterpret_cast<float*>(blk + ((RECMAX + 2) & ~1)) + (size_t)warp * rec * 32;   // rec * 32 floats
   const bool whole_fit = fit.cent_out != nullptr;
   const bool accumulate = sums != nullptr || whole_fit;
+  if (whole_fit && fit.world > 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    // tell every rank that this rank has entered the call (so it has finished reading the previous call's slots)
+    for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_ready(fit.xchg[p]) + fit.rank, fit.stamp_base);
+  }
   const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
   float* lanesingle = lanerec + (size_t)k * npair * 64;
   __shared__ int nan_centroid;
@@ -458,7 +506,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
       const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
       if (lane == 0) {
-        if (whole_fit) {
+        if (whole_fit && fit.world > 1) {
+          // sharded fit: this rank's folded entry goes straight into every rank's slot (its own included)
+          if (it == 0) xchg_wait_all(xchg_ready(fit.xchg[fit.rank]), fit.world, fit.stamp_base);   // peers are in this call
+          const size_t slot = (size_t)gridDim.y * out_rec;
+          for (int p = 0; p < fit.world; ++p)
+            xchg_slot(fit.xchg[p], it & 1, fit.world, fit.rank, slot)[(size_t)l * out_rec + e] = tot;
+          __threadfence_system();
+        } else if (whole_fit) {
           fit.totals[(size_t)l * out_rec + e] = tot;
         } else if (e < rec) {
           const int c = e / (d + 1), r = e % (d + 1);
@@ -474,11 +529,32 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     // ---- whole-fit mode: division, error and convergence test, identically in every block (compute_centroids'
     // division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` kmeans.py:239) ----
     km_barrier(barrier_ctr + 2, nblocks, ++phase);
+    const bool sharded = fit.world > 1;
+    const size_t slot = (size_t)gridDim.y * out_rec;
+    if (sharded) {
+      // all of this rank's entries are in every peer's slot (system-scope fences above, grid barrier here): raise our
+      // flag on every rank, then wait until every rank's flag for this iteration is up in OUR buffer
+      const unsigned stamp = fit.stamp_base + 1u + (unsigned)it;
+      if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        __threadfence_system();
+        for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_flag(fit.xchg[p], it & 1, fit.world) + fit.rank, stamp);
+      }
+      if (tid == 0) xchg_wait_all(xchg_flag(fit.xchg[fit.rank], it & 1, fit.world), fit.world, stamp);
+      __syncthreads();
+    }
     const double* tl = fit.totals + (size_t)l * out_rec;
+    // folded total of record entry idx of this batch entry: local scratch, or the ranks' records added in rank order
+    auto total_at = [&](int idx) -> double {
+      if (!sharded) return __ldcg(tl + idx);
+      double t = 0.0;
+      for (int r = 0; r < fit.world; ++r)
+        t += __ldcg(xchg_slot(fit.xchg[fit.rank], it & 1, fit.world, r, slot) + (size_t)l * out_rec + idx);
+      return t;
+    };
     double e2 = 0.0;
     for (int e = tid; e < d * k; e += THREADS) {
       const int r = e / k, c = e - r * k;
-      const float v = (float)(__ldcg(tl + c * (d + 1) + r) / __ldcg(tl + c * (d + 1) + d));   // 0/0 -> NaN as the reference
+      const float v = (float)(total_at(c * (d + 1) + r) / total_at(c * (d + 1) + d));   // 0/0 -> NaN as the reference
       csn[r * KMAX + c] = v;
       const double df = (double)cs[r * KMAX + c] - (double)v;
       e2 += df * df;
@@ -502,7 +578,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     if (blockIdx.x == 0) {
       if (final_pass) {
         for (int e = tid; e < d * k; e += THREADS) fit.cent_out[(int64_t)l * d * k + e] = csn[(e / k) * KMAX + (e % k)];
-        if (tid == 0 && fit.simsum_last) fit.simsum_last[l] = __ldcg(tl + rec);
+        if (tid == 0 && fit.simsum_last) fit.simsum_last[l] = total_at(rec);
       }
       if (l == 0 && tid == 0 && final_pass) {
         if (fit.err) fit.err[0] = err;
@@ -871,6 +947,40 @@ int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int
   fit.labels_final = labels;
   return km_dispatch(data, centroids, l, d, n, k_clusters, nullptr, nullptr, nullptr, nullptr, nullptr, workspace, nullptr, nullptr,
                      fit, as_stream(stream));
+}
+
+size_t et_kmeans_exchange_bytes(int l, int d, int k_clusters, int world) {
+  if (l < 1 || d < 1 || k_clusters < 1 || world < 1 || world > KM_XCHG_MAX_WORLD) return 0;
+  return (size_t)KM_XCHG_HEADER + (size_t)2 * world * l * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
+}
+
+int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, int d, int64_t n_local, int k_clusters,
+                            int max_iter, double tol, float* centroids_out, int64_t* labels, double* err, int32_t* status,
+                            double* simsum_last, void* workspace, int rank, int world, void* const* exchange_peers,
+                            unsigned stamp_base, et_stream_t stream) {
+  int rc = km_check(l, d, n_local, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(centroids && centroids_out && workspace && exchange_peers && (n_local == 0 || data), ET_ERR_BADARG,
+             "et_kmeans_lloyd_sharded: null pointer");
+  ET_REQUIRE(max_iter >= 1, ET_ERR_BADARG, "et_kmeans_lloyd_sharded: max_iter = %d < 1", max_iter);
+  ET_REQUIRE(world >= 2 && world <= KM_XCHG_MAX_WORLD && rank >= 0 && rank < world, ET_ERR_BADARG,
+             "et_kmeans_lloyd_sharded: rank %d / world %d outside [2, %d]", rank, world, KM_XCHG_MAX_WORLD);
+  ET_REQUIRE(l <= 32, ET_ERR_UNSUPPORTED, "et_kmeans_lloyd_sharded: batch l = %d > 32", l);
+  KmLloyd fit{};
+  fit.max_iter = max_iter;
+  fit.tol = tol;
+  fit.cent_out = centroids_out;
+  fit.err = err;
+  fit.status = status;
+  fit.simsum_last = simsum_last;
+  fit.labels_final = labels;
+  fit.rank = rank;
+  fit.world = world;
+  fit.xchg = reinterpret_cast<unsigned char* const*>(exchange_peers);
+  fit.stamp_base = stamp_base;
+  // an empty shard still takes part in every exchange: give the kernel a valid (never dereferenced) data pointer
+  return km_dispatch(data ? data : centroids, centroids, l, d, n_local, k_clusters, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     workspace, nullptr, nullptr, fit, as_stream(stream));
 }
 
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n, int k_clusters,

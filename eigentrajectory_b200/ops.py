@@ -593,6 +593,21 @@ def kmeans_lloyd(data, centroids, acc, max_iter, tol, want_labels=True):
     return labels, out
 
 
+def kmeans_lloyd_sharded(data, centroids, acc, max_iter, tol, rank, world, peers, stamp_base, want_labels=True):
+    """Row-sharded whole-fit kernel with the per-iteration exchange over peer memory (see et_kmeans_lloyd_sharded).
+
+    ``peers``: int64 device tensor (world,) of exchange-buffer addresses as mapped in this process."""
+    l, d, n = data.shape
+    k = centroids.size(-1)
+    out = torch.empty((l, d, k), device=centroids.device)
+    labels = torch.empty((l, n), dtype=torch.int64, device=centroids.device) if want_labels else None
+    check(load().et_kmeans_lloyd_sharded(ptr(data) if n > 0 else None, ptr(centroids), l, d, n, k, int(max_iter), float(tol),
+                                         ptr(out), ptr(labels) if n > 0 else None, ptr(acc.err), ptr(acc.status),
+                                         ptr(acc.simsum_last), ptr(acc.ws), int(rank), int(world), ptr(peers),
+                                         int(stamp_base) & 0xFFFFFFFF, stream_of(centroids.device)), "et_kmeans_lloyd_sharded")
+    return labels, out
+
+
 def kmeans_accumulate(data, labels, acc):
     """Masked sums / counts of compute_centroids for given labels (added into ``acc``)."""
     l, d, n = data.shape

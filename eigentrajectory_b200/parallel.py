@@ -152,6 +152,69 @@ def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset
     return cent
 
 
+class PeerExchange:
+    """Exchange buffers of the in-kernel all-reduce of ``et_kmeans_lloyd_sharded``: one symmetric-memory allocation per
+    rank, mapped into every other rank of the node (NVLink / NVSwitch peer access), plus the call counter that keeps
+    the flag stamps monotonic.  Needs one process per GPU on one node and a NCCL process group."""
+
+    _cache = {}
+
+    def __init__(self, l, d, k, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._lib import load
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(load().et_kmeans_exchange_bytes(l, d, k, self.world))
+        if nbytes == 0:
+            raise RuntimeError(f"peer exchange supports at most 16 ranks (world = {self.world})")
+        self.buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        self.peers = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.stamp = 1
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                 # every buffer is zero before anybody stores into it
+
+    @classmethod
+    def get(cls, l, d, k, device, group=None):
+        key = (l, d, k, str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(l, d, k, device, group)
+        return cls._cache[key]
+
+    def next_stamp(self, max_iter):
+        s = self.stamp
+        self.stamp += max_iter + 2
+        return s
+
+
+def peer_exchange_available(device, group=None):
+    """True when the fused (peer-memory) sharded fit can run: CUDA tensors, NCCL group, more than one rank."""
+    if not (dist.is_available() and dist.is_initialized()) or torch.device(device).type != "cuda":
+        return False
+    if dist.get_world_size(group) < 2 or dist.get_backend(group) != "nccl":
+        return False
+    return True
+
+
+def sharded_kmeans_fit_fused(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, group=None):
+    """``sharded_kmeans_fit`` with the whole Lloyd loop AND its per-iteration all-reduce inside one persistent kernel per
+    rank (``et_kmeans_lloyd_sharded``): the ranks exchange their folded records through peer memory, no NCCL call and
+    no host round trip per iteration.  Same return values; centroids and iteration count are identical on all ranks by
+    construction (every rank adds the same records in rank order)."""
+    l, d, n_local = data_shard.shape
+    dev = centroids.device
+    ex = PeerExchange.get(l, d, n_clusters, dev, group)
+    acc = ops.KMeansWorkspace(l, d, n_clusters, dev)
+    labels, final = ops.kmeans_lloyd_sharded(data_shard, centroids.contiguous(), acc, max_iter, tol, ex.rank, ex.world,
+                                             ex.peers, ex.next_stamp(max_iter))
+    _, n_iter = (int(v) for v in acc.status.tolist())
+    if labels is None:
+        labels = torch.zeros((l, 0), dtype=torch.int64, device=dev)
+    inertia = float(-(acc.simsum_last / n_total).mean())
+    return labels, final, n_iter, inertia
+
+
 def sharded_kmeans_fit(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, sync_every=8, group=None,
                        backend=None):
     """Lloyd iterations (kmeans.py:200-259, n_redo = 1) over row shards: per iteration one fused

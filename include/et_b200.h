@@ -222,6 +222,23 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
 int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
                     int max_iter, double tol, float* centroids_out, int64_t* labels, double* err,
                     int32_t* status, double* simsum_last, void* workspace, et_stream_t stream);
+/* et_kmeans_lloyd over ROW SHARDS on several GPUs of one node, with the per-iteration exchange fused into the kernel:
+ * every rank runs the persistent kernel on its n_local rows; after the local grid fold it stores its folded record
+ * (d*K + K + 1 doubles per batch entry) directly into every rank's exchange buffer through peer mappings
+ * (NVLink / NVSwitch), raises a per-iteration flag there, waits for the other ranks' flags in its own buffer and adds
+ * the `world` records in rank order -- the all-reduce of SURVEY section 8e inside the kernel: no NCCL call, no host
+ * round trip, identical centroids / convergence decision on every rank by construction.
+ * exchange_peers: DEVICE array of `world` pointers, entry r = rank r's exchange buffer as mapped in THIS process
+ * (et_kmeans_exchange_bytes() bytes each, zero-filled once before the first call, e.g. a torch symmetric-memory
+ * allocation).  stamp_base: a number that grows by at least max_iter + 2 from one call to the next on the same
+ * buffers (the same on every rank).  labels / simsum_last cover the local rows / the global sum.  world <= 16, l <= 32;
+ * n_local may be 0.  A rank that never arrives traps the kernel after ~10 s instead of hanging it. */
+size_t et_kmeans_exchange_bytes(int l, int d, int k_clusters, int world);
+int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, int d, int64_t n_local,
+                            int k_clusters, int max_iter, double tol, float* centroids_out,
+                            int64_t* labels, double* err, int32_t* status, double* simsum_last,
+                            void* workspace, int rank, int world, void* const* exchange_peers,
+                            unsigned stamp_base, et_stream_t stream);
 /* Accumulation half of compute_centroids (kmeans.py:160-184) for caller-supplied labels
  * (l,N) int64; labels outside [0,K) are ignored.  sums / counts / workspace as above. */
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n,

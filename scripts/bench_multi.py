@@ -68,6 +68,12 @@ def main():
             dist.all_reduce(acc.flat)
         ops.kmeans_finalize(acc, cent0, nxt)
     res["kmeans_iter_ms"] = timed(km_iter, args.reps)
+    if world > 1 and P.peer_exchange_available(dev):
+        # whole sharded fit in one persistent kernel per rank, all-reduce over peer memory inside the kernel
+        iters = 200
+        res["kmeans_fused_iter_ms"] = timed(lambda: P.sharded_kmeans_fit_fused(C, 20, world * n, cent0, max_iter=iters, tol=-1.0),
+                                            5) / iters
+        res["points_per_s_kmeans_fused_iter"] = world * n / (res["kmeans_fused_iter_ms"] * 1e-3)
     out = (torch.empty_like(obs), torch.empty_like(pred), torch.empty((6, n), device=dev), torch.empty((6, n), device=dev))
     res["project_reconstruct_ms"] = timed(lambda: ops.project_reconstruct(obs, pred, Uo, Up, out=out), args.reps)
     res["traj_per_s_basis"] = world * n / (res["basis_ms"] * 1e-3)

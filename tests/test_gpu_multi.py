@@ -48,6 +48,14 @@ def _worker(rank, world, port, use_nccl, out):
         res["cent_err"] = float((cent - km.centroids).abs().max() / km.centroids.abs().max())
         res["iters"] = (n_iter, km.n_iter_)
         res["cent"] = cent.cpu()
+        # the same fit with the all-reduce fused into the persistent kernel (peer memory; needs NCCL + one GPU per rank)
+        if use_nccl and P.peer_exchange_available(dev):
+            for rep in range(2):                                 # twice: the exchange buffers and stamps are reused
+                fl, fc, fi, fin = P.sharded_kmeans_fit_fused(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25)
+            res["fused_equal"] = bool(torch.equal(fl, labels) and torch.equal(fc, cent) and fi == n_iter
+                                      and abs(fin - inertia) <= 1e-12 * abs(inertia))
+        else:
+            res["fused_equal"] = None
         # sharded metric mean
         rec = ops.reconstruct(torch.zeros(6, b - a, 20, device=dev), Up, ops.norm_params(obs[a:b].to(dev)))
         ade, fde = ops.ade_fde(rec, pred[a:b].to(dev))
@@ -74,6 +82,7 @@ def test_sharded_basis_kmeans_metrics_world2():
         assert r["init_equal"]
         assert r["label_mismatch"] <= 4 and r["cent_err"] < 1e-4
         assert r["iters"][0] == r["iters"][1]
+        assert r["fused_equal"] in (None, True)
     assert torch.equal(r0["U_pred"], r1["U_pred"]) and torch.equal(r0["cent"], r1["cent"])
     assert abs(r0["ade_mean"] - r1["ade_mean"]) < 1e-12
     assert abs(r0["ade_mean"] - r0["ade_mean_ref"]) < 1e-6 * abs(r0["ade_mean_ref"])
