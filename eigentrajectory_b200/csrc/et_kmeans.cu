@@ -11,8 +11,12 @@
 //           sums ((acc0 + acc1) + acc2) + acc3 where acc0 also takes the remainder rows; a tensor of 4..7
 //           columns sums its first four columns sequentially            (torch 2.11 CPU, measured)
 //   label = arg-max, lowest index on ties, NaN wins (torch.max).
-// The update half accumulates without atomics in lane-private fp32 records (<= 64 points each) that are folded into
-// float64 in a fixed order, so centroid sums carry fp64 accuracy and are run-to-run reproducible.
+// The similarity scan runs on packed fp32 pairs (FFMA2 / FADD2: two centroids per instruction, every half an ordinary
+// IEEE operation).  The update half accumulates without atomics in lane-private fp32 records (<= 64 points each) that
+// are folded per warp in fp32 row sums and above the warp in float64, always in the same order: centroid sums are
+// run-to-run reproducible and far more accurate than the reference's fp32 sum over all N.
+// et_kmeans_lloyd runs the whole Lloyd loop in one persistent cooperative launch; et_kmeans_lloyd_sharded adds the
+// multi-GPU exchange over peer memory inside the same kernel.
 #include "et_common.cuh"
 
 namespace et {
@@ -255,8 +259,9 @@ __device__ __forceinline__ void km_barrier_exit(unsigned* ctr, unsigned nblocks)
 // memory.  Coordinates are kept as fp32 pairs laid out [cluster][pair][lane] (a warp's 64-bit read-modify-write covers
 // 256 contiguous bytes: conflict-free, and one FADD2 updates two coordinates), the odd coordinate (if any) and the
 // count as singles [cluster][single][lane].  A lane adds at most KM_FLUSH_EVERY points into its record before the warp
-// folds the 32 lane records into float64 registers in a fixed order, so totals carry fp64 accuracy and are
-// reproducible.  KPAD: compile-time padded cluster count of the packed scan (0 = run time).
+// folds its 32 lane records (fp32 row sums, then fp64: see flush below) in a fixed order, so totals are reproducible
+// and fp32 never carries more than 32 * KM_FLUSH_EVERY points.  KPAD: compile-time padded cluster count of the packed
+// scan (0 = run time).
 template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
