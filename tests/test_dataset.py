@@ -90,6 +90,28 @@ def test_read_file_and_get_dataloader(dl, gold, tmp_path):
     assert n_batches == len(gold["eth_num_peds_in_seq"])
 
 
+def test_native_nonlinear_flag_agrees_with_numpy_polyfit(dl, gold):
+    """The builder's residual (orthonormal-basis projection in long double) and the mirror of the reference's
+    poly_fit (np.polyfit, dataloader.py:135-151) take the same decision on every pedestrian of the fixtures."""
+    for tag, pred_len, thr in (("syn", 12, 0.02), ("eth", 12, 0.02), ("syn_short", 5, 0.002)):
+        full = np.concatenate([gold[f"{tag}_obs"], gold[f"{tag}_pred"]], axis=1).astype(np.float64)   # (N, T, 2)
+        want = gold[f"{tag}_non_linear"]
+        got = np.array([dl.poly_fit(tr.T, pred_len, thr) for tr in full[:400]])
+        assert np.array_equal(got, want[:400]), tag
+
+
+def test_space_delimiter_and_skip(dl, tmp_path):
+    d = tmp_path / "sp"
+    d.mkdir()
+    rows = "".join(f"{10 * f} {p}.0 {0.1 * f + p:.3f} {0.2 * f:.3f}\n" for f in range(30) for p in (1, 2, 3))
+    (d / "f.txt").write_text(rows)
+    ds = dl.TrajectoryDataset(str(d) + "/", obs_len=8, pred_len=12, skip=2, delim="space")
+    # 30 frames -> num_sequences = ceil(11 / 2) = 6 windows starting at frames 0, 2, .., 10 (+ the empty one at 12)
+    assert len(ds) == 6 and ds.obs_traj.shape == (18, 8, 2) and ds.pred_traj.shape == (18, 12, 2)
+    assert torch.allclose(ds.obs_traj[3, :, 0], torch.tensor([0.1 * f + 1 for f in range(2, 10)], dtype=torch.float32))
+    assert float(ds.non_linear_ped.sum()) == 0.0 and torch.equal(ds.loss_mask, torch.ones(18, 20))
+
+
 def test_cache_round_trip(dl, gold, tmp_path):
     path = write_split(tmp_path, gold, "eth", ["biwi_eth.txt"])
     ds = dl.TrajectoryDataset(path, obs_len=8, pred_len=12)
