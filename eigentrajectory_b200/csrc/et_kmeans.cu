@@ -235,11 +235,13 @@ __device__ __forceinline__ void xchg_wait_all(const unsigned* flags, int world, 
 __device__ __forceinline__ void km_barrier(unsigned* ctr, unsigned nblocks, unsigned phase) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(&ctr[0], 1u);
+    // release-arrive / acquire-poll at gpu scope (cumulative over the block's writes ordered by the bar.sync above)
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     const unsigned target = phase * nblocks;
-    while (*reinterpret_cast<volatile unsigned*>(&ctr[0]) < target) __nanosleep(20);
-    __threadfence();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }

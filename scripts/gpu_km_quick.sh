@@ -1,0 +1,23 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -k 5 400 python -m pytest tests/test_gpu_svd_kmeans_metrics.py -m gpu -q --timeout 240 -p no:cacheprovider -k "kmeans" > gpurun_out/t_km.log 2>&1; echo "kmeans tests exit $?"; tail -n 2 gpurun_out/t_km.log | cut -c1-200
+python - <<'PY'
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.getcwd())
+import eigentrajectory_b200 as et
+from eigentrajectory_b200 import ops
+dev = torch.device("cuda")
+gen = torch.Generator().manual_seed(1234)
+data = (torch.randn(1, 6, 1_000_000, generator=gen) * torch.tensor([20., 4., 1., .8, .3, .25])[None, :, None]).contiguous().to(dev)
+km = et.BatchKMeans(n_clusters=20); np.random.seed(0)
+cent = km.initialize_centroids(data)
+acc = ops.KMeansWorkspace(1, 6, 20, dev)
+for _ in range(2): ops.kmeans_lloyd(data, cent, acc, 100, -1.0, want_labels=False)
+torch.cuda.synchronize()
+ts = []
+for _ in range(7):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.kmeans_lloyd(data, cent, acc, 100, -1.0, want_labels=False); e1.record(); e1.synchronize()
+    ts.append(e0.elapsed_time(e1) * 10)
+print("whole-fit kernel: us per Lloyd iteration", [round(t, 2) for t in ts])
+PY
