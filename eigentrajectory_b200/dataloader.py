@@ -30,59 +30,41 @@ _MAGIC = b"ETDS0001"
 
 
 def get_dataloader(data_dir, phase, obs_len, pred_len, batch_size, device=None):
-    r"""Get dataloader for a specific phase (dataloader.py:10-36).
+    """Loader of one split (the reference's ``get_dataloader``, dataloader.py:10-36).
 
-    Args:
-        data_dir (str): path to the dataset directory
-        phase (str): phase of the data, one of 'train', 'val', 'test'
-        obs_len (int): length of observed trajectory
-        pred_len (int): length of predicted trajectory
-        batch_size (int): batch size
-        device: optional; keep the dataset tensors on this device (no pinned-memory staging then)
-    """
+    ``data_dir/phase/`` is preprocessed natively; training shuffles the scenes and drops an incomplete last batch,
+    validation / test keep file order.  ``batch_size`` counts pedestrians (see :class:`TrajBatchSampler`); with
+    ``batch_size <= 1`` every batch is one scene.  ``device``: keep the split resident on that device."""
     assert phase in ['train', 'val', 'test']
-
-    data_set = data_dir + '/' + phase + '/'
-    shuffle = True if phase == 'train' else False
-    drop_last = True if phase == 'train' else False
-
-    dataset_phase = TrajectoryDataset(data_set, obs_len=obs_len, pred_len=pred_len, device=device)
-    sampler_phase = None
+    training = phase == 'train'
+    dataset = TrajectoryDataset(f"{data_dir}/{phase}/", obs_len=obs_len, pred_len=pred_len, device=device)
+    sampler = None
     if batch_size > 1:
-        sampler_phase = TrajBatchSampler(dataset_phase, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last)
-    on_device = dataset_phase.obs_traj.is_cuda
-    loader_phase = DataLoader(dataset_phase, collate_fn=traj_collate_fn, batch_sampler=sampler_phase,
-                              pin_memory=not on_device)
-    return loader_phase
+        sampler = TrajBatchSampler(dataset, batch_size=batch_size, shuffle=training, drop_last=training)
+    # device-resident tensors need no pinned staging
+    return DataLoader(dataset, collate_fn=traj_collate_fn, batch_sampler=sampler, pin_memory=not dataset.obs_traj.is_cuda)
 
 
 def traj_collate_fn(data):
-    r"""Collate function for the dataloader (dataloader.py:39-66).
+    """Concatenate scenes into one batch (dataloader.py:39-66).
 
-    Returns obs (num_ped, obs_len, 2), pred (num_ped, pred_len, 2), non_linear_ped (num_ped,),
-    loss_mask (num_ped, obs_len + pred_len), scene_mask (num_ped, num_ped) bool, seq_start_end (num_seq, 2).
-    """
-    obs_seq_list, pred_seq_list, non_linear_ped_list, loss_mask_list, _, _ = zip(*data)
-
-    _len = [len(seq) for seq in obs_seq_list]
-    cum_start_idx = [0] + np.cumsum(_len).tolist()
-    seq_start_end = [[start, end] for start, end in zip(cum_start_idx, cum_start_idx[1:])]
-    seq_start_end = torch.LongTensor(seq_start_end)
-    device = obs_seq_list[0].device
-    scene_mask = torch.zeros(sum(_len), sum(_len), dtype=torch.bool, device=device)
-    for idx, (start, end) in enumerate(seq_start_end.tolist()):
-        scene_mask[start:end, start:end] = 1
-
-    out = [torch.cat(obs_seq_list, dim=0), torch.cat(pred_seq_list, dim=0),
-           torch.cat(non_linear_ped_list, dim=0), torch.cat(loss_mask_list, dim=0), scene_mask, seq_start_end]
-    return tuple(out)
+    Returns (obs (P, obs_len, 2), pred (P, pred_len, 2), non_linear_ped (P,), loss_mask (P, obs_len + pred_len),
+    scene_mask (P, P) bool -- block diagonal, True inside a scene --, seq_start_end (n_scenes, 2) int64)."""
+    obs, pred, non_linear, loss_mask = (list(column) for column in list(zip(*data))[:4])
+    sizes = [scene.size(0) for scene in obs]
+    ends = np.cumsum(sizes)
+    seq_start_end = torch.as_tensor(np.stack([ends - np.asarray(sizes), ends], axis=1).reshape(-1, 2), dtype=torch.int64)
+    blocks = [torch.ones((m, m), dtype=torch.bool, device=obs[0].device) for m in sizes]
+    scene_mask = torch.block_diag(*blocks)
+    return (torch.cat(obs, dim=0), torch.cat(pred, dim=0), torch.cat(non_linear, dim=0), torch.cat(loss_mask, dim=0),
+            scene_mask, seq_start_end)
 
 
 class TrajBatchSampler(Sampler):
-    r"""Samples batched elements by yielding a mini-batch of indices (dataloader.py:69-118).
+    """Batches of scene indices holding at least ``batch_size`` pedestrians each (dataloader.py:69-118).
 
-    A batch is closed as soon as it holds at least ``batch_size`` pedestrians.
-    """
+    Scenes are taken in order (or in a fresh random permutation when ``shuffle``); a batch is emitted as soon as its
+    pedestrian count reaches ``batch_size``; the left-over scenes form a last, smaller batch unless ``drop_last``."""
 
     def __init__(self, data_source, batch_size=64, shuffle=False, drop_last=False, generator=None):
         self.data_source = data_source
@@ -91,38 +73,33 @@ class TrajBatchSampler(Sampler):
         self.drop_last = drop_last
         self.generator = generator
 
+    def _order(self):
+        n_scenes = len(self.data_source)
+        if not self.shuffle:
+            return list(range(n_scenes))
+        gen = self.generator
+        if gen is None:                      # a fresh seed per epoch, drawn from the global torch generator
+            gen = torch.Generator()
+            gen.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
+        return torch.randperm(n_scenes, generator=gen).tolist()
+
     def __iter__(self):
-        assert len(self.data_source) == len(self.data_source.num_peds_in_seq)
-
-        if self.shuffle:
-            if self.generator is None:
-                generator = torch.Generator()
-                generator.manual_seed(int(torch.empty((), dtype=torch.int64).random_().item()))
-            else:
-                generator = self.generator
-            indices = torch.randperm(len(self.data_source), generator=generator).tolist()
-        else:
-            indices = list(range(len(self.data_source)))
-        num_peds_indices = self.data_source.num_peds_in_seq[indices]
-
-        batch = []
-        total_num_peds = 0
-        for idx, num_peds in zip(indices, num_peds_indices):
-            batch.append(idx)
-            total_num_peds += num_peds
-            if total_num_peds >= self.batch_size:
-                yield batch
-                batch = []
-                total_num_peds = 0
-        if len(batch) > 0 and not self.drop_last:
-            yield batch
+        peds = self.data_source.num_peds_in_seq
+        assert len(self.data_source) == len(peds)
+        pending, count = [], 0
+        for scene in self._order():
+            pending.append(scene)
+            count += peds[scene]
+            if count >= self.batch_size:
+                yield pending
+                pending, count = [], 0
+        if pending and not self.drop_last:
+            yield pending
 
     def __len__(self):
-        # Approximated number of batches (the order can be shuffled, so this number can vary from run to run).
-        if self.drop_last:
-            return sum(self.data_source.num_peds_in_seq) // self.batch_size
-        else:
-            return (sum(self.data_source.num_peds_in_seq) + self.batch_size - 1) // self.batch_size
+        # an estimate: the real number depends on how the (possibly shuffled) scenes fill the batches
+        total = sum(self.data_source.num_peds_in_seq)
+        return total // self.batch_size if self.drop_last else -(-total // self.batch_size)
 
 
 def _delim_char(delim):
@@ -152,16 +129,17 @@ def read_file(_path, delim='\t'):
 
 
 def poly_fit(traj, traj_len, threshold):
-    """1.0 if the last ``traj_len`` frames of ``traj`` (2, T) are non-linear, else 0.0 (dataloader.py:135-151).
-
-    Host helper kept for API parity; the dataset builder evaluates the same criterion natively."""
-    t = np.linspace(0, traj_len - 1, traj_len)
-    res_x = np.polyfit(t, traj[0, -traj_len:], 2, full=True)[1]
-    res_y = np.polyfit(t, traj[1, -traj_len:], 2, full=True)[1]
-    if res_x + res_y >= threshold:
-        return 1.0
-    else:
-        return 0.0
+    """1.0 when the last ``traj_len`` frames of ``traj`` (2, T) are not fitted by a quadratic in time to within
+    ``threshold`` (sum of the squared residuals of x and y), else 0.0 -- the reference's non-linearity flag
+    (dataloader.py:135-151).  Host helper for API parity; the dataset builder applies the same rule natively."""
+    t = np.arange(traj_len, dtype=np.float64)
+    design = np.stack([t * t, t, np.ones_like(t)], axis=1)
+    total = 0.0
+    for axis in (0, 1):
+        y = np.asarray(traj[axis, -traj_len:], dtype=np.float64)
+        coef = np.linalg.lstsq(design, y, rcond=None)[0]
+        total += float(((design @ coef - y) ** 2).sum())
+    return 1.0 if total >= threshold else 0.0
 
 
 def build_windows(rows, obs_len=8, pred_len=12, skip=1, threshold=0.02, min_ped=1):
@@ -187,20 +165,15 @@ def build_windows(rows, obs_len=8, pred_len=12, skip=1, threshold=0.02, min_ped=
 
 
 class TrajectoryDataset(Dataset):
-    """Dataloder for the Trajectory datasets (dataloader.py:154-241)."""
+    """All complete pedestrian windows of a split as (N, T, 2) tensors (the reference's class of the same name,
+    dataloader.py:154-241), built by the native windowing code."""
 
     def __init__(self, data_dir, obs_len=8, pred_len=12, skip=1, threshold=0.02, min_ped=1, delim='\t', device=None):
-        """
-        Args:
-        - data_dir: Directory containing dataset files in the format <frame_id> <ped_id> <x> <y>
-        - obs_len: Number of time-steps in input trajectories
-        - pred_len: Number of time-steps in output trajectories
-        - skip: Number of frames to skip while making the dataset
-        - threshold: Minimum error to be considered for non-linear traj when using a linear predictor
-        - min_ped: Minimum number of pedestrians that should be in a sequence
-        - delim: Delimiter in the dataset files
-        - device: optional device the tensors are kept on (default: host, as the reference)
-        """
+        """Every file of ``data_dir`` holds rows ``<frame_id> <ped_id> <x> <y>``.  A window is ``obs_len + pred_len``
+        consecutive frames, windows start every ``skip`` frames; a window is kept when MORE than ``min_ped``
+        pedestrians are present in all of its frames; ``threshold`` is the residual above which a future counts as
+        non-linear; ``delim`` is a character, 'tab' or 'space'; ``device`` (optional) is where the tensors are kept
+        (default: host memory, like the reference)."""
         super(TrajectoryDataset, self).__init__()
 
         self.data_dir = data_dir

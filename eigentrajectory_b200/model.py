@@ -59,18 +59,12 @@ class EigenTrajectory(nn.Module):
         Note:
             This function should be called once before training the model.
         """
-        # Mask out static trajectory
-        mask = self._moving_mask(obs_traj)
-        obs_m_traj, pred_m_traj = obs_traj[mask], pred_traj[mask]
-        obs_s_traj, pred_s_traj = obs_traj[~mask], pred_traj[~mask]
-
-        # Descriptor initialization
-        data_m = self.ET_m_descriptor.parameter_initialization(obs_m_traj, pred_m_traj)
-        data_s = self.ET_s_descriptor.parameter_initialization(obs_s_traj, pred_s_traj)
-
-        # Anchor generation
-        self.ET_m_anchor.anchor_generation(*data_m)
-        self.ET_s_anchor.anchor_generation(*data_s)
+        moving = self._moving_mask(obs_traj)
+        for rows, descriptor, anchor in ((moving, self.ET_m_descriptor, self.ET_m_anchor),
+                                         (~moving, self.ET_s_descriptor, self.ET_s_anchor)):
+            # eigen-bases of the group, then its anchors from the normalised futures in that basis
+            pred_norm, U_pred = descriptor.parameter_initialization(obs_traj[rows], pred_traj[rows])
+            anchor.anchor_generation(pred_norm, U_pred)
 
     def forward(self, obs_traj, pred_traj=None, addl_info=None):
         r"""The forward function of the EigenTrajectory model (model.py:58-125)
@@ -80,58 +74,60 @@ class EigenTrajectory(nn.Module):
         """
         if self._can_fuse():
             return self._forward_fused(obs_traj, pred_traj, addl_info)
-        n_ped = obs_traj.size(0)
-        dev = obs_traj.device
+        return self._forward_grouped(obs_traj, pred_traj, addl_info)
 
-        # Filter out static trajectory
-        mask = self._moving_mask(obs_traj)
-        obs_m_traj, obs_s_traj = obs_traj[mask], obs_traj[~mask]
-        pred_m_traj_gt = pred_traj[mask] if pred_traj is not None else None
-        pred_s_traj_gt = pred_traj[~mask] if pred_traj is not None else None
+    @staticmethod
+    def _merge(moving, part_m, part_s, shape, axis):
+        """Tensor of ``shape`` whose slices along ``axis`` come from ``part_m`` where ``moving`` is set and from
+        ``part_s`` elsewhere (the scatter the reference writes out for every quantity, model.py:84-117)."""
+        full = part_m.new_zeros(shape)
+        sel = [slice(None)] * len(shape)
+        sel[axis] = moving
+        full[tuple(sel)] = part_m
+        sel[axis] = ~moving
+        full[tuple(sel)] = part_s
+        return full
 
-        # Projection (fused normalise + U^T x; stores the normaliser state of each group)
-        C_m_obs, C_m_pred_gt = self.ET_m_descriptor.projection(obs_m_traj, pred_m_traj_gt)
-        C_s_obs, C_s_pred_gt = self.ET_s_descriptor.projection(obs_s_traj, pred_s_traj_gt)
-        C_obs = torch.zeros((self.k, n_ped), dtype=torch.float, device=dev)
-        C_obs[:, mask], C_obs[:, ~mask] = C_m_obs, C_s_obs  # KN
+    def _forward_grouped(self, obs_traj, pred_traj, addl_info):
+        """``forward`` in the reference's group-by-group structure: gather the moving / static pedestrians, run each
+        group through its own descriptor and anchor, scatter back; the losses are tensor algebra (model.py:73-123)."""
+        n = obs_traj.size(0)
+        moving = self._moving_mask(obs_traj)
+        static = ~moving
+        have_gt = pred_traj is not None
+        desc = {True: self.ET_m_descriptor, False: self.ET_s_descriptor}
+        anchor = {True: self.ET_m_anchor, False: self.ET_s_anchor}
 
-        # Absolute coordinate
-        obs_m_ori = self.ET_m_descriptor.traj_normalizer.traj_ori.squeeze(dim=1).T
-        obs_s_ori = self.ET_s_descriptor.traj_normalizer.traj_ori.squeeze(dim=1).T
-        obs_ori = torch.zeros((2, n_ped), dtype=torch.float, device=dev)
-        obs_ori[:, mask], obs_ori[:, ~mask] = obs_m_ori, obs_s_ori
-        obs_ori -= obs_ori.mean(dim=1, keepdim=True)  # move scene to origin
+        # projection of each group (fused normalise + U^T x; each descriptor keeps its group's normaliser state)
+        coef_obs, coef_gt, origin = {}, {}, {}
+        for grp, rows in ((True, moving), (False, static)):
+            coef_obs[grp], coef_gt[grp] = desc[grp].projection(obs_traj[rows], pred_traj[rows] if have_gt else None)
+            origin[grp] = desc[grp].traj_normalizer.traj_ori.squeeze(dim=1).T
+        C_obs = self._merge(moving, coef_obs[True], coef_obs[False], (self.k, n), 1)              # (k, N)
+        obs_ori = self._merge(moving, origin[True], origin[False], (2, n), 1)
+        obs_ori -= obs_ori.mean(dim=1, keepdim=True)                                             # scene-centred
 
-        # Trajectory prediction (plugin seam, unchanged)
-        input_data = self.hook_func.model_forward_pre_hook(C_obs, obs_ori, addl_info)
-        output_data = self.hook_func.model_forward(input_data, self.baseline_model)
-        C_pred_refine = self.hook_func.model_forward_post_hook(output_data, addl_info)
+        # predictor plugin: the three bridge calls of model.py:93-95, untouched
+        hooks = self.hook_func
+        C_refined = hooks.model_forward_post_hook(
+            hooks.model_forward(hooks.model_forward_pre_hook(C_obs, obs_ori, addl_info), self.baseline_model), addl_info)
 
-        # Anchor refinement + reconstruction in one kernel per group
-        C_m_in, C_s_in = C_pred_refine[:, mask], C_pred_refine[:, ~mask]
-        pred_m_traj_recon = self.ET_m_descriptor.reconstruction(C_m_in, anchor=self.ET_m_anchor.C_anchor)
-        pred_s_traj_recon = self.ET_s_descriptor.reconstruction(C_s_in, anchor=self.ET_s_anchor.C_anchor)
-        pred_traj_recon = torch.zeros((self.s, n_ped, self.t_pred, self.dim), dtype=torch.float, device=dev)
-        pred_traj_recon[:, mask], pred_traj_recon[:, ~mask] = pred_m_traj_recon, pred_s_traj_recon
+        # anchor refinement + reconstruction, one kernel per group
+        refined = {True: C_refined[:, moving], False: C_refined[:, static]}
+        recon = {g: desc[g].reconstruction(refined[g], anchor=anchor[g].C_anchor) for g in (True, False)}
+        recon_traj = self._merge(moving, recon[True], recon[False], (self.s, n, self.t_pred, self.dim), 1)
+        output = {"recon_traj": recon_traj}
+        if not have_gt:
+            return output
 
-        output = {"recon_traj": pred_traj_recon}
-
-        if pred_traj is not None:
-            C_pred = torch.zeros((self.k, n_ped, self.s), dtype=torch.float, device=dev)
-            C_pred[:, mask], C_pred[:, ~mask] = self.ET_m_anchor(C_m_in), self.ET_s_anchor(C_s_in)
-
-            # Low-rank approximation for gt trajectory
-            C_pred_gt = torch.zeros((self.k, n_ped), dtype=torch.float, device=dev)
-            C_pred_gt[:, mask], C_pred_gt[:, ~mask] = C_m_pred_gt, C_s_pred_gt
-            C_pred_gt = C_pred_gt.detach()
-
-            # Loss calculation
-            error_coefficient = (C_pred - C_pred_gt.unsqueeze(dim=-1)).norm(p=2, dim=0)
-            error_displacement = (pred_traj_recon - pred_traj.unsqueeze(dim=0)).norm(p=2, dim=-1)
-            output["loss_eigentraj"] = error_coefficient.min(dim=-1)[0].mean()
-            output["loss_euclidean_ade"] = error_displacement.mean(dim=-1).min(dim=0)[0].mean()
-            output["loss_euclidean_fde"] = error_displacement[:, :, -1].min(dim=0)[0].mean()
-
+        # losses (model.py:119-123): coefficient error, ADE and FDE, each min over the S samples then mean over N
+        C_pred = self._merge(moving, anchor[True](refined[True]), anchor[False](refined[False]), (self.k, n, self.s), 1)
+        C_gt = self._merge(moving, coef_gt[True], coef_gt[False], (self.k, n), 1).detach()
+        err_coef = (C_pred - C_gt.unsqueeze(dim=-1)).norm(p=2, dim=0)                             # (N, S)
+        err_disp = (recon_traj - pred_traj.unsqueeze(dim=0)).norm(p=2, dim=-1)                    # (S, N, T)
+        output["loss_eigentraj"] = err_coef.min(dim=-1)[0].mean()
+        output["loss_euclidean_ade"] = err_disp.mean(dim=-1).min(dim=0)[0].mean()
+        output["loss_euclidean_fde"] = err_disp[:, :, -1].min(dim=0)[0].mean()
         return output
 
     def _forward_fused(self, obs_traj, pred_traj=None, addl_info=None):
