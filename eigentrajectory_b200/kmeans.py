@@ -18,17 +18,13 @@ def _as_ldn(t):
 
 
 class BatchKMeans(nn.Module):
-    r"""Run multiple independent K-means algorithms in parallel.
+    """A batch of independent k-means problems clustered side by side (the reference's class of the same name,
+    kmeans.py:7-272): data ``(..., d, N)``, centroids ``(..., d, K)``, one problem per leading index.
 
-    Args:
-        n_clusters (int): Number of clusters
-        max_iter (int): Maximum number of iterations (default: 100)
-        tol (float): Tolerance (default: 0.0001)
-        n_redo (int): Number of time k-means will be run with differently initialized centroids.
-            the centroids with the lowest inertia will be selected as a final result. (default: 1)
-        init_mode (str): Initialization method.
-            'random': randomly chose initial centroids from input data.
-            'kmeans++': use the (deterministic farthest-point) k-means++ of the reference. (default: 'kmeans++')
+    ``n_clusters``: K.  ``n_redo``: restarts from different seeds, the fit with the lowest inertia wins (default 1).
+    ``max_iter`` (100) and ``tol`` (1e-4): Lloyd stops after ``max_iter`` updates or once the squared centroid shift,
+    summed over the whole batch, is ``<= tol``.  ``init_mode``: ``'kmeans++'`` (default) = the reference's
+    deterministic farthest-point rule from a random first point, ``'random'`` = K distinct random points.
 
     ``fused`` (default): the whole Lloyd loop of ``fit`` runs in ONE persistent cooperative kernel
     (``et_kmeans_lloyd``: grid barriers instead of relaunches, convergence test on the device).
@@ -54,28 +50,27 @@ class BatchKMeans(nn.Module):
         self.register_buffer("centroids", None)
 
     def load_state_dict(self, state_dict, **kwargs):
-        r"""Override the default load_state_dict() to load custom buffers (kmeans.py:32-43)."""
-        for k, v in state_dict.items():
-            if "." not in k:
-                assert hasattr(self, k), f"attribute {k} does not exist"
-                delattr(self, k)
-                self.register_buffer(k, v)
-
-        for name, module in self.named_children():
-            sd = {k.replace(name + ".", ""): v for k, v in state_dict.items() if k.startswith(name + ".")}
-            module.load_state_dict(sd)
+        """``centroids`` is a buffer that does not exist before the first fit, so a plain ``load_state_dict`` would
+        reject it: top-level entries are (re-)registered as buffers, dotted ones go to the child modules
+        (kmeans.py:32-43)."""
+        own = {key: value for key, value in state_dict.items() if "." not in key}
+        for key, value in own.items():
+            assert hasattr(self, key), f"attribute {key} does not exist"
+            delattr(self, key)
+            self.register_buffer(key, value)
+        for child_name, child in self.named_children():
+            prefix = child_name + "."
+            child.load_state_dict({key[len(prefix):]: value for key, value in state_dict.items() if key.startswith(prefix)})
 
     # ---- small static helpers: tensor algebra on (l,d,K)-sized or already reduced data ----
     @staticmethod
     def calculate_error(a, b):
-        r"""Compute L2 error between a and b"""
-        diff = a - b
-        diff.pow_(2)
-        return diff.sum()
+        """Squared Euclidean distance between two centroid sets, summed over everything (kmeans.py:45-51)."""
+        return (a - b).square_().sum()
 
     @staticmethod
     def calculate_inertia(a):
-        r"""Compute inertia of a"""
+        """Inertia from best similarities: similarities are negative squared distances (kmeans.py:53-57)."""
         return (-a).mean()
 
     @staticmethod
@@ -85,11 +80,10 @@ class BatchKMeans(nn.Module):
         Utility kept for API parity (kmeans.py:59-76); it materialises the full matrix with tensor
         algebra on whatever device its inputs live.  The clustering itself never calls it: get_labels
         fuses similarity, arg-max and the centroid accumulation in one CUDA kernel."""
-        y = a.transpose(-2, -1) @ b
-        y.mul_(2)
-        y.sub_(a.pow(2).sum(dim=-2)[..., :, None])
-        y.sub_(b.pow(2).sum(dim=-2)[..., None, :])
-        return y
+        sq_a, sq_b = a.pow(2).sum(dim=-2), b.pow(2).sum(dim=-2)
+        sim = torch.matmul(a.transpose(-2, -1), b)
+        sim.mul_(2).sub_(sq_a.unsqueeze(-1)).sub_(sq_b.unsqueeze(-2))      # same in-place order as the reference
+        return sim
 
     # ---- seeding (kmeans.py:78-141) ----
     def kmeanspp(self, data):
@@ -100,20 +94,19 @@ class BatchKMeans(nn.Module):
         return ops.back_to(cent.reshape(*lead, x.size(1), self.n_clusters), data)
 
     def initialize_centroids(self, data):
-        r"""Initialize centroids with init_mode specified in __init__"""
-        n_data = data.size(-1)
-        if self.init_mode == "random":
-            random_index = np.random.choice(n_data, size=[self.n_clusters], replace=False)
-            centroids = data[..., torch.as_tensor(random_index, device=data.device)].clone()
-            if self.verbose:
-                print("centroids are randomly initialized.")
-        elif self.init_mode == "kmeans++":
-            centroids = self.kmeanspp(data).clone()
-            if self.verbose:
-                print("centroids are initialized with kmeans++.")
+        """Starting centroids ``(..., d, K)`` according to ``init_mode`` (kmeans.py:114-141)."""
+        if self.init_mode == "kmeans++":
+            start = self.kmeanspp(data).clone()
+            how = "with kmeans++"
+        elif self.init_mode == "random":
+            pick = np.random.choice(data.size(-1), size=[self.n_clusters], replace=False)
+            start = data[..., torch.as_tensor(pick, device=data.device)].clone()
+            how = "randomly"
         else:
             raise NotImplementedError
-        return centroids
+        if self.verbose:
+            print(f"centroids are initialized {how}.")
+        return start
 
     # ---- one Lloyd half-step each (kmeans.py:143-198) ----
     def get_labels(self, data, centroids):
@@ -176,15 +169,9 @@ class BatchKMeans(nn.Module):
         return labels, final.clone(), n_iter, acc.err.clone(), inertia
 
     def fit(self, data, centroids=None):
-        r"""Perform K-means clustering, and return final labels
-
-        Args:
-            data (torch.Tensor): data to be clustered, shape (l, d_vector, n_data)
-            centroids (torch.Tensor): initial centroids, shape (l, d_vector, n_clusters)
-
-        Returns:
-            best_labels (torch.Tensor): final labels, shape (l, n_data)
-        """
+        """Cluster ``data (l, d, N)`` and return the labels ``(l, N)`` of the best restart; the winning centroids
+        are kept in the ``centroids`` buffer.  ``centroids (l, d, K)``, if given, seed the first restart
+        (kmeans.py:200-259)."""
         assert data.is_contiguous(), "use .contiguous()"
         x, lead = _as_ldn(data)
         l, d, n = x.shape

@@ -1,59 +1,61 @@
-"""TrajNorm -- drop-in for ``EigenTrajectory/normalizer.py:4-62`` running on libet_b200.so."""
+"""TrajNorm -- the per-pedestrian trajectory normaliser, API-compatible with the reference's
+``EigenTrajectory/normalizer.py:4-62`` and computed by ``libet_b200.so``.
+
+State of a batch of N pedestrians, derived from the observed frames ``obs (N, T_obs, 2)``:
+  * ``traj_ori (N,1,2)``  the last observed position (translation),
+  * ``traj_rot (N,2,2)``  ``[[c,-s],[s,c]]`` with ``(c, s)`` the heading of ``obs[-1] - obs[-3]`` (rotation),
+  * ``traj_sca (N,1,1)``  ``2 / |obs[-1] - obs[-3]|`` (scale; ``inf`` for a pedestrian that did not move, as in the
+    reference).
+``normalize`` maps ``x -> ((x - ori) @ rot) * sca``, ``denormalize`` inverts it; each stage is optional.
+
+The heading is taken as ``d/|d|`` instead of ``cos/sin(atan2(d))`` (<= 3e-7 absolute difference; the zero vector gives
+the identity rotation exactly as ``atan2(0, 0) = 0`` does).
+"""
 from __future__ import annotations
 
 from . import ops
 
+_STATE = ("traj_ori", "traj_rot", "traj_sca")
+
 
 class TrajNorm:
-    r"""Normalize trajectory with shape (num_peds, length_of_time, 2)
+    """Translation / rotation / scale normaliser for trajectories of shape ``(num_peds, length_of_time, 2)``.
 
-    Args:
-        ori (bool): Whether to normalize the trajectory with the origin
-        rot (bool): Whether to normalize the trajectory with the rotation
-        sca (bool): Whether to normalize the trajectory with the scale
-
-    Same public surface as the reference (``ori/rot/sca`` flags and the stored per-batch state
-    ``traj_ori (N,1,2)``, ``traj_rot (N,2,2)``, ``traj_sca (N,1,1)``).  The rotation is obtained as
-    ``d/|d|`` instead of ``cos/sin(atan2(d))`` (<= 3e-7 absolute difference; the zero vector maps
-    to the identity exactly as ``atan2(0, 0) = 0`` does).
-    """
+    ``ori``, ``rot``, ``sca`` switch the three stages on or off (all on by default)."""
 
     def __init__(self, ori=True, rot=True, sca=True):
         self.ori, self.rot, self.sca = ori, rot, sca
-        self.traj_ori, self.traj_rot, self.traj_sca = None, None, None
+        for name in _STATE:
+            setattr(self, name, None)
+
+    def _enabled(self):
+        return self.ori, self.rot, self.sca
 
     def calculate_params(self, traj):
-        r"""Calculate the normalization parameters (normalizer.py:17-28)"""
-        o, r, s = ops.norm_params(traj, self.ori, self.rot, self.sca)
-        if self.ori:
-            self.traj_ori = o
-        if self.rot:
-            self.traj_rot = r
-        if self.sca:
-            self.traj_sca = s
+        """Derive the state of this batch from its observed frames (normalizer.py:17-28); stages that are switched
+        off keep whatever state they had."""
+        fresh = ops.norm_params(traj, *self._enabled())
+        for name, on, value in zip(_STATE, self._enabled(), fresh):
+            if on:
+                setattr(self, name, value)
 
     def get_params(self):
-        r"""Get the normalization parameters"""
-        return self.ori, self.rot, self.sca, self.traj_ori, self.traj_rot, self.traj_sca
+        """``(ori, rot, sca, traj_ori, traj_rot, traj_sca)``: flags and state, for hand-over to another instance."""
+        return (*self._enabled(), *(getattr(self, name) for name in _STATE))
 
     def set_params(self, ori, rot, sca, traj_ori, traj_rot, traj_sca):
-        r"""Set the normalization parameters"""
+        """Adopt flags and state obtained from :meth:`get_params`."""
         self.ori, self.rot, self.sca = ori, rot, sca
         self.traj_ori, self.traj_rot, self.traj_sca = traj_ori, traj_rot, traj_sca
 
     def state(self):
-        """(ori, rot, sca) with disabled stages as None -- what the fused kernels take."""
-        return (self.traj_ori if self.ori else None, self.traj_rot if self.rot else None,
-                self.traj_sca if self.sca else None)
+        """``(ori, rot, sca)`` tensors with disabled stages as ``None`` -- the form the fused kernels take."""
+        return tuple(getattr(self, name) if on else None for name, on in zip(_STATE, self._enabled()))
 
     def normalize(self, traj):
-        r"""Normalize the trajectory (normalizer.py:42-51)"""
-        if not (self.ori or self.rot or self.sca):
-            return traj
-        return ops.normalize(traj, *self.state())
+        """``((traj - ori) @ rot) * sca`` over the enabled stages (normalizer.py:42-51)."""
+        return ops.normalize(traj, *self.state()) if any(self._enabled()) else traj
 
     def denormalize(self, traj):
-        r"""Denormalize the trajectory (normalizer.py:53-62)"""
-        if not (self.ori or self.rot or self.sca):
-            return traj
-        return ops.denormalize(traj, *self.state())
+        """``((traj / sca) @ rot^T) + ori`` over the enabled stages (normalizer.py:53-62)."""
+        return ops.denormalize(traj, *self.state()) if any(self._enabled()) else traj
