@@ -392,39 +392,52 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     sim_acc = 0.0;
 
     constexpr int PPL = 2;                                   // points per lane and iteration (instruction-level parallelism)
-    const int64_t stride = (int64_t)gridDim.x * (WARPS * 32 * PPL);
+    // 32-bit point indices (km_check keeps N + one grid stride below 2^32): one 32-bit compare per point instead of
+    // compare pairs; the compile-time-d kernels are only dispatched while d * N < 2^32, so the element offset r * N + i
+    // is 32-bit arithmetic too and a load costs one IMAD + one IMAD.WIDE (no 64-bit address chains)
+    const uint32_t n32 = (uint32_t)n;
+    const uint32_t stride = gridDim.x * (uint32_t)(WARPS * 32 * PPL);
+    const uint32_t seq_limit = (n >= 4 && n < 8) ? 4u : 32u * (n32 / 32u);    // col_is_sequential(i, n) == i < seq_limit
+    const float* dl_pin = dl;
+    asm volatile("" : "+l"(dl_pin));     // opaque: keeps the batch entry's base in a register pair instead of re-deriving
+                                         // data + l * d * n (64-bit multiplies) in front of every load
+    auto load_coord = [&](int r, uint32_t i) -> float {
+      if constexpr (EXACT) return __ldg(dl_pin + (uint32_t)((uint32_t)r * n32 + i));
+      else return __ldg(dl + (int64_t)r * n + i);
+    };
+    int64_t* lab_out = labels_out ? labels_out + (int64_t)l * n : nullptr;
+    float* sim_out = maxsims_out ? maxsims_out + (int64_t)l * n : nullptr;
+    const int64_t* lab_in = labels_in ? labels_in + (int64_t)l * n : nullptr;
     int since_flush = 0;
     // all lanes of a warp iterate together (the loop bound is warp-uniform)
+    const uint32_t base0 = ((uint32_t)blockIdx.x * WARPS + warp) * (32 * PPL);
     float a_next[PPL][DMAX];
-    {
-      const int64_t b0 = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL);
 #pragma unroll
-      for (int u = 0; u < PPL; ++u) {
-        const int64_t i0 = b0 + u * 32 + lane;
+    for (int u = 0; u < PPL; ++u) {
+      const uint32_t i0 = base0 + u * 32 + lane;
 #pragma unroll
-        for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && i0 < n) ? __ldg(dl + (int64_t)r * n + i0) : 0.f;
-      }
+      for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && i0 < n32) ? load_coord(r, i0) : 0.f;
     }
-    for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * (32 * PPL); base < n; base += stride) {
+    for (uint32_t base = base0; base < n32; base += stride) {
       float a[PPL][DMAX];
-      int64_t idx[PPL];
+      uint32_t idx[PPL];
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
         idx[u] = base + u * 32 + lane;
 #pragma unroll
         for (int r = 0; r < DMAX; ++r) a[u][r] = a_next[u][r];
         // software prefetch of the next batch: its loads are in flight while this one is scored
-        const int64_t in = idx[u] + stride;
+        const uint32_t in = idx[u] + stride;
 #pragma unroll
-        for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
+        for (int r = 0; r < DMAX; ++r) a_next[u][r] = ((EXACT || r < d) && in < n32) ? load_coord(r, in) : 0.f;
       }
       float best[PPL];
       int label[PPL];
-      if (labels_in) {   // compute_centroids with caller-supplied labels: accumulation only
+      if (lab_in) {   // compute_centroids with caller-supplied labels: accumulation only
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
           best[u] = 0.f;
-          const int64_t li = idx[u] < n ? labels_in[(int64_t)l * n + idx[u]] : -1;
+          const int64_t li = idx[u] < n32 ? lab_in[idx[u]] : -1;
           label[u] = (li >= 0 && li < k) ? (int)li : -1;
         }
       } else {
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
         bool finite = !nan_possible;
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
-          anorm[u] = sumsq_torch_order<DMAX>(a[u], d, col_is_sequential(idx[u], n));
+          anorm[u] = sumsq_torch_order<DMAX>(a[u], d, idx[u] < seq_limit);
           finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
         }
         if (finite) {
@@ -445,9 +458,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
       }
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
-        if (idx[u] < n) {
-          if (labels_out) labels_out[(int64_t)l * n + idx[u]] = label[u];
-          if (maxsims_out) maxsims_out[(int64_t)l * n + idx[u]] = best[u];
+        if (idx[u] < n32) {
+          if (lab_out) lab_out[idx[u]] = label[u];
+          if (sim_out) sim_out[idx[u]] = best[u];
           if (acc_pass && label[u] >= 0) {
             f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * 32 + lane;
 #pragma unroll
@@ -874,7 +887,7 @@ static int km_launch(const float* data, const float* centroids, int l, int d, in
 static int km_dispatch(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                        float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
                        const int32_t* status, const int64_t* labels_in, const KmLloyd& fit, cudaStream_t st) {
-  if (d == 6 && k <= 32)
+  if (d == 6 && k <= 32 && 6 * n < ((int64_t)1 << 32))      // compile-time d with 32-bit element offsets
     return km_launch<6, 32, true>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace, status,
                                   labels_in, fit, st);
   if (d <= 8 && k <= 32)
@@ -905,7 +918,8 @@ static int km_check(int l, int d, int64_t n, int k) {
   if (l < 1 || l > 65535) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d outside [1, 65535]", l);
   if (d < 1 || d > ET_MAX_KM_DIM) return fail(ET_ERR_UNSUPPORTED, "k-means: d = %d outside [1, %d]", d, ET_MAX_KM_DIM);
   if (k < 1 || k > ET_MAX_CLUSTERS) return fail(ET_ERR_UNSUPPORTED, "k-means: K = %d outside [1, %d]", k, ET_MAX_CLUSTERS);
-  if (n < 0 || n >= ((int64_t)1 << 32)) return fail(ET_ERR_UNSUPPORTED, "k-means: N = %lld outside [0, 2^32)", (long long)n);
+  if (n < 0 || n >= ((int64_t)1 << 32) - ((int64_t)1 << 21))       // 32-bit point indices + one grid stride must not wrap
+    return fail(ET_ERR_UNSUPPORTED, "k-means: N = %lld outside [0, 2^32 - 2^21)", (long long)n);
   return ET_OK;
 }
 
