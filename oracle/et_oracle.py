@@ -339,3 +339,58 @@ def synthetic_trajectories(n, seed=0, t_obs=8, t_pred=12, dtype=torch.float32):
     vel = torch.stack([v * ang.cos(), v * ang.sin()], dim=-1) + torch.randn(n, T, 2, generator=g) * 0.03
     traj = (p0 + vel.cumsum(dim=1)).to(dtype)
     return traj[:, :t_obs].contiguous(), traj[:, t_obs:].contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# Dataset preprocessing  (utils/dataloader.py)
+# --------------------------------------------------------------------------------------
+
+
+def dataset_parse(text, delim="\t"):
+    """``read_file`` (``utils/dataloader.py:121-132``): every line stripped, split on ``delim``, fields through
+    ``float()``.  Returns an (n_rows, 4) float64 array."""
+    return np.asarray([[float(tok) for tok in line.strip().split(delim)] for line in text.splitlines()], dtype=np.float64)
+
+
+def dataset_windows(rows, obs_len=8, pred_len=12, skip=1, threshold=0.02, min_ped=1):
+    """The per-file body of ``TrajectoryDataset.__init__`` (``utils/dataloader.py:189-226``) and ``poly_fit``
+    (``:135-151``), restated with numpy group operations instead of per-pedestrian masks.
+
+    rows (n, 4) float64 ``frame, ped, x, y`` -> (traj (N, T, 2) float32, non_linear (N,) float32,
+    num_peds_in_seq (n_seq,) int64).  A window = ``T = obs_len + pred_len`` consecutive distinct frames starting at
+    frame index 0, skip, 2*skip, ...; a pedestrian is kept when its first / last rows in the window sit on the
+    window's first / last frame (it must then have exactly T rows); coordinates are rounded with ``np.around(.., 4)``;
+    a window is kept when MORE than ``min_ped`` pedestrians are."""
+    T = obs_len + pred_len
+    frames = np.unique(rows[:, 0])
+    fidx = np.searchsorted(frames, rows[:, 0])
+    order = np.argsort(fidx, kind="stable")                      # frame-major, file order inside a frame
+    rows, fidx = rows[order], fidx[order]
+    n_seq = int(np.ceil((len(frames) - T + 1) / skip))
+    t = np.linspace(0, pred_len - 1, pred_len)
+    trajs, flags, counts = [], [], []
+    for start in range(0, n_seq * skip + 1, skip):
+        sel = (fidx >= start) & (fidx < start + T)
+        if not sel.any():
+            raise ValueError("need at least one array to concatenate")
+        win, wf = rows[sel], fidx[sel]
+        peds, inv = np.unique(win[:, 1], return_inverse=True)
+        kept, kept_flags = [], []
+        for p in range(len(peds)):                               # ascending pedestrian id, as np.unique orders them
+            mine = np.flatnonzero(inv == p)
+            if wf[mine[-1]] - wf[mine[0]] + 1 != T:
+                continue
+            if len(mine) != T:
+                raise ValueError("could not broadcast input array")      # what numpy raises in the reference
+            xy = np.around(win[mine, 2:4], decimals=4).T         # (2, T)
+            kept.append(xy)
+            res = sum(np.polyfit(t, xy[axis, -pred_len:], 2, full=True)[1] for axis in (0, 1))
+            kept_flags.append(1.0 if res >= threshold else 0.0)
+        if len(kept) > min_ped:
+            trajs.append(np.stack(kept))                         # (P, 2, T)
+            flags += kept_flags
+            counts.append(len(kept))
+    if not trajs:
+        return (np.zeros((0, T, 2), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.int64))
+    traj = np.concatenate(trajs, axis=0).transpose(0, 2, 1).astype(np.float32)
+    return traj, np.asarray(flags, dtype=np.float32), np.asarray(counts, dtype=np.int64)

@@ -112,6 +112,43 @@ def test_space_delimiter_and_skip(dl, tmp_path):
     assert float(ds.non_linear_ped.sum()) == 0.0 and torch.equal(ds.loss_mask, torch.ones(18, 20))
 
 
+def test_oracle_restatement_matches_reference_and_native_fuzz(dl, gold):
+    """The numpy restatement in oracle/ is pinned to the reference's outputs (fixtures), then serves as the checker for
+    the native builder on random scenes: ragged lifetimes, missing frames, several skips and window lengths."""
+    from oracle import et_oracle as O
+    for tag, kw in (("eth", dict(obs_len=8, pred_len=12)), ("syn_short", dict(obs_len=3, pred_len=5, min_ped=0, threshold=0.002))):
+        parts = []
+        for name in [str(x) for x in gold[f"{tag}_file_order"]]:
+            text = gold[f"{tag}_text_{name}"].tobytes().decode()
+            parts.append(O.dataset_windows(O.dataset_parse(text), **kw))
+        traj = np.concatenate([p[0] for p in parts])
+        assert np.array_equal(traj[:, :kw["obs_len"]], gold[f"{tag}_obs"]) and np.array_equal(traj[:, kw["obs_len"]:], gold[f"{tag}_pred"])
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), gold[f"{tag}_non_linear"])
+        assert np.array_equal(np.concatenate([p[2] for p in parts]), gold[f"{tag}_num_peds_in_seq"])
+    rng = np.random.RandomState(5)
+    for case in range(12):
+        n_frames, n_peds = int(rng.randint(6, 60)), int(rng.randint(1, 25))
+        frames = np.sort(rng.choice(np.arange(0, 3 * n_frames), size=n_frames, replace=False)) * 10
+        rows = []
+        for ped in range(n_peds):
+            a = int(rng.randint(0, n_frames))
+            b = int(min(n_frames, a + rng.randint(1, 40)))
+            p0, v = rng.uniform(-5, 5, 2), rng.uniform(-0.5, 0.5, 2)
+            for j, f in enumerate(frames[a:b]):
+                pos = p0 + v * j + (0.1 * np.sin(j) if ped % 3 == 0 else 0.0) + rng.normal(0, 1e-3, 2)
+                rows.append((float(f), float(ped + 1), pos[0], pos[1]))
+        rng.shuffle(rows)
+        rows = np.asarray(sorted(rows, key=lambda r: r[0]), dtype=np.float64)
+        kw = dict(obs_len=int(rng.randint(1, 9)), pred_len=int(rng.randint(4, 13)), skip=int(rng.randint(1, 4)),
+                  threshold=0.02, min_ped=int(rng.randint(0, 3)))
+        if len(np.unique(rows[:, 0])) < 2:
+            continue
+        want = O.dataset_windows(rows, **kw)
+        got = dl.build_windows(rows, **kw)
+        for g, w in zip(got, want):
+            assert np.array_equal(np.asarray(g), w), (case, kw)
+
+
 def test_cache_round_trip(dl, gold, tmp_path):
     path = write_split(tmp_path, gold, "eth", ["biwi_eth.txt"])
     ds = dl.TrajectoryDataset(path, obs_len=8, pred_len=12)
