@@ -43,6 +43,7 @@ PROTOTYPES = {
     "et_forward_losses_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p]),
     "et_gram_workspace_bytes": (_sz, []),
     "et_gram": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p]),
+    "et_gram_init": (_i, [_p, _p, _l, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "et_eig_jacobi": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "et_eig_jacobi_pair": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "et_svd_small": (_i, [_p, _p, _i, _l, _i, _i, _p, _p, _p]),

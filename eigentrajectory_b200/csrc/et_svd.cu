@@ -38,7 +38,9 @@ template <int UNROLL>
 __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restrict__ obs, const float* __restrict__ pred,
                                                            int64_t n, int flags, double* __restrict__ G_obs,
                                                            double* __restrict__ G_pred, unsigned* __restrict__ ticket,
-                                                           double* __restrict__ partials) {
+                                                           double* __restrict__ partials, float* __restrict__ pred_norm,
+                                                           float* __restrict__ ori, float* __restrict__ rot,
+                                                           float* __restrict__ sca) {
   extern __shared__ __align__(16) unsigned char gr_smem[];
   float* xs = reinterpret_cast<float*>(gr_smem);   // [GR_WARPS][32 * GR_PITCH]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,9 +87,17 @@ __global__ void __launch_bounds__(GR_WARPS * 32) gram_fast(const float* __restri
         x[4 * c] = raw[c].x; x[4 * c + 1] = raw[c].y; x[4 * c + 2] = raw[c].z; x[4 * c + 3] = raw[c].w;
       }
       if (flags && tile * 32 + lane < n) {
-        const AffineFwd af = make_affine_fwd(make_norm_state(x[14], x[15], x[10], x[11]), flags);
+        const NormState nst = make_norm_state(x[14], x[15], x[10], x[11]);
+        const AffineFwd af = make_affine_fwd(nst, flags);
 #pragma unroll
         for (int t = 0; t < 20; ++t) affine_fwd(x[2 * t], x[2 * t + 1], af);
+        // parameter_initialization's other outputs from the same pass: normaliser state and the normalised futures
+        if (ori || rot || sca) store_norm_state(ori, rot, sca, tile * 32 + lane, nst, flags);
+      }
+      if (pred_norm && tile * 32 + lane < n) {
+        float4* po = reinterpret_cast<float4*>(pred_norm + (tile * 32 + lane) * 24);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) stg_stream(po + c, make_float4(x[16 + 4 * c], x[17 + 4 * c], x[18 + 4 * c], x[19 + 4 * c]));
       }
       float4* row = reinterpret_cast<float4*>(xw + lane * GR_PITCH);
 #pragma unroll
@@ -505,6 +515,16 @@ size_t et_gram_workspace_bytes(void) { return 128 + (size_t)gram_grid() * GR_REC
 
 int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags, double* G_obs,
             double* G_pred, void* workspace, et_stream_t stream) {
+  return et_gram_init(obs, pred, n, t_obs, t_pred, flags, G_obs, G_pred, nullptr, nullptr, nullptr, nullptr, workspace, stream);
+}
+
+int et_gram_init(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags, double* G_obs,
+                 double* G_pred, float* pred_norm, float* ori, float* rot, float* sca, void* workspace,
+                 et_stream_t stream) {
+  ET_REQUIRE(!pred_norm || pred, ET_ERR_BADARG, "et_gram_init: pred_norm requested without pred");
+  ET_REQUIRE(!pred_norm || aligned16(pred_norm), ET_ERR_ALIGN, "et_gram_init: pred_norm must be 16-byte aligned");
+  ET_REQUIRE(!rot || aligned16(rot), ET_ERR_ALIGN, "et_gram_init: rot must be 16-byte aligned");
+  const bool extras = pred_norm || ori || rot || sca;
   ET_REQUIRE(n >= 0, ET_ERR_BADARG, "et_gram: n < 0");
   ET_REQUIRE(t_obs >= 1 && t_obs <= ET_MAX_T && (!pred || (t_pred >= 1 && t_pred <= ET_MAX_T)), ET_ERR_UNSUPPORTED,
              "et_gram: T outside [1, %d]", ET_MAX_T);
@@ -526,7 +546,8 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     auto launch = [&](auto kern) {      // the attribute is per device: set it on every call (cheap)
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GR_SMEM);
       if (e != cudaSuccess) return e;
-      return launch_cooperative(kern, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts);
+      return launch_cooperative(kern, dim3(grid), dim3(GR_WARPS * 32), GR_SMEM, st, obs, pred, n, flags, G_obs, G_pred, ctr, parts,
+                                pred_norm, ori, rot, sca);
     };
     switch (tune_get(ET_TUNE_GRAM_UNROLL)) {
       case 1: ce = launch(gram_fast<1>); break;
@@ -536,6 +557,11 @@ int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pre
     }
     if (ce != cudaSuccess) return fail(ET_ERR_CUDA, "gram_fast: cooperative launch: %s", cudaGetErrorString(ce));
     return check_launch("gram_fast");
+  }
+  if (extras) {     // other shapes: the state and the normalised futures come from the stand-alone kernels
+    int rc = et_norm_params(obs, n, t_obs, flags, ori, rot, sca, stream);
+    if (rc) return rc;
+    if (pred_norm && (rc = et_normalize(pred, n, t_pred, flags, ori, rot, sca, pred_norm, stream))) return rc;
   }
   const int to2 = 2 * t_obs, tp2 = pred ? 2 * t_pred : 0;
   const size_t smem = (size_t)GG_CHUNK * (to2 + tp2) * sizeof(float);

@@ -96,18 +96,22 @@ class ETDescriptor(nn.Module):
         pass (normalise + both fp64 Gram matrices) followed by two tiny eigen-solves."""
         tn = self.traj_normalizer
         obs_d, pred_d = ops.to_dev(obs_traj), ops.to_dev(pred_traj)
-        tn.calculate_params(obs_d)
-        pred_norm_d = tn.normalize(pred_d)
-        n = obs_d.size(0)
         method = self.svd_method
         if method == "auto":
             method = "gram"
         if method == "jacobi":
+            tn.calculate_params(obs_d)
+            pred_norm_d = tn.normalize(pred_d)
             U_obs, _ = self._basis(tn.normalize(obs_d), self.k)
             U_pred, _ = self._basis(pred_norm_d, self.k)
         else:
-            G_obs, G_pred = ops.gram(obs_d, pred_d, tn.ori, tn.rot, tn.sca)
-            (U_obs, _), (U_pred, _) = ops.eig_basis_pair(G_obs, G_pred, self.k)     # both solves in one launch
+            # one pass over the data: normaliser state, normalised futures and both Gram matrices; then one launch
+            # for both eigen-solves
+            G_obs, G_pred, pred_norm_d, state = ops.gram_init(obs_d, pred_d, tn.ori, tn.rot, tn.sca)
+            for name, on, value in zip(("traj_ori", "traj_rot", "traj_sca"), (tn.ori, tn.rot, tn.sca), state):
+                if on:
+                    setattr(tn, name, value)
+            (U_obs, _), (U_pred, _) = ops.eig_basis_pair(G_obs, G_pred, self.k)
         # state / outputs live where the caller's tensors live, as in the reference
         for name in ("traj_ori", "traj_rot", "traj_sca"):
             v = getattr(tn, name)

@@ -469,6 +469,27 @@ def gram(obs, pred=None, ori=False, rot=False, sca=False, G_obs=None, G_pred=Non
     return G_obs, (G_pred if p is not None else None)
 
 
+def gram_init(obs, pred, ori=True, rot=True, sca=True):
+    """The data pass of ``ETDescriptor.parameter_initialization`` in one launch: both float64 Gram matrices, the
+    normaliser state of every row and the normalised futures.
+
+    Returns (G_obs, G_pred, pred_norm (N,T_pred,2), (ori|None, rot|None, sca|None)) on the compute device."""
+    x = to_dev(obs)
+    n, t_obs = _ntc(x)
+    p = to_dev(pred).to(x.device)
+    t_pred = p.size(1)
+    dev = x.device
+    G_obs = torch.zeros((2 * t_obs, 2 * t_obs), dtype=torch.float64, device=dev)
+    G_pred = torch.zeros((2 * t_pred, 2 * t_pred), dtype=torch.float64, device=dev)
+    pred_norm = torch.empty_like(p)
+    o = torch.empty((n, 1, 2), device=dev) if ori else None
+    r = torch.empty((n, 2, 2), device=dev) if rot else None
+    s = torch.empty((n, 1, 1), device=dev) if sca else None
+    check(load().et_gram_init(ptr(x), ptr(p), n, t_obs, t_pred, norm_flags(ori, rot, sca), ptr(G_obs), ptr(G_pred),
+                              ptr(pred_norm), ptr(o), ptr(r), ptr(s), ptr(_gram_workspace(dev)), stream_of(dev)), "et_gram_init")
+    return G_obs, G_pred, pred_norm, (o, r, s)
+
+
 def eig_basis(G, k, want64=False, info=None):
     """Leading-k eigenpairs of a float64 Gram matrix -> (U (m,k) fp32, S (k) fp32[, U64, S64]).
 

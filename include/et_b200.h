@@ -176,6 +176,13 @@ int et_forward_losses_bwd(const float* C, const float* anchor_m, const float* an
 size_t et_gram_workspace_bytes(void);
 int et_gram(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags,
             double* G_obs, double* G_pred, void* workspace, et_stream_t stream);
+/* The data pass of ETDescriptor.parameter_initialization (descriptor.py:116-135) in ONE launch on the (8, 12) fast
+ * path: et_gram plus, from the same read of the trajectories, the normaliser state of every row (ori / rot / sca as
+ * et_norm_params writes them; each optional) and the normalised futures pred_norm (N, T_pred, 2) (optional) that the
+ * anchor step consumes.  Other shapes compose et_norm_params + et_normalize + et_gram. */
+int et_gram_init(const float* obs, const float* pred, int64_t n, int t_obs, int t_pred, int flags,
+                 double* G_obs, double* G_pred, float* pred_norm, float* ori, float* rot, float* sca,
+                 void* workspace, et_stream_t stream);
 /* Symmetric eigen-solve of G (m x m, float64, m <= 64) by parallel-ordered cyclic Jacobi;
  * returns the k leading left singular vectors U (m,k) row-major float32 and singular
  * values S (k) = sqrt(lambda).  Column signs are canonical: the largest-magnitude

@@ -194,6 +194,26 @@ def test_eig_pair_equals_two_solves(et, O):
     assert torch.equal(Ub32, Ub1) and torch.equal(Sb32, Sb1)
 
 
+@pytest.mark.parametrize("shape", [(100_003, 8, 12), (777, 5, 7)])
+@pytest.mark.parametrize("flags", [(True, True, True), (True, True, False), (False, False, False)])
+def test_gram_init_single_pass_equals_separate_kernels(et, O, shape, flags):
+    """et_gram_init: state, normalised futures and both Gram matrices from one read of the data."""
+    n, to, tp = shape
+    obs, pred = O.synthetic_trajectories(n, seed=6, t_obs=to, t_pred=tp)
+    obs, pred = obs.cuda(), pred.cuda()
+    Go, Gp, pn, state = et.ops.gram_init(obs, pred, *flags)
+    Go1, Gp1 = et.ops.gram(obs, pred, *flags)
+    if (to, tp) == (8, 12):          # the fast path folds in a fixed order: bit-identical
+        assert torch.equal(Go, Go1) and torch.equal(Gp, Gp1)
+    else:                            # the generic kernel accumulates with fp64 atomics
+        assert rel_max(Go.cpu(), Go1.cpu()) < 1e-12 and rel_max(Gp.cpu(), Gp1.cpu()) < 1e-12
+    st1 = et.ops.norm_params(obs, *flags)
+    for a, b in zip(state, st1):
+        assert (a is None and b is None) or torch.equal(a, b)
+    want = et.ops.normalize(pred, *st1) if any(flags) else pred
+    assert rel_max(pn.cpu(), want.cpu()) < 1e-6
+
+
 def test_gram_generic_shapes(et, O):
     obs, pred = O.synthetic_trajectories(3001, seed=2, t_obs=5, t_pred=7)
     st = O.norm_params(obs.double())
