@@ -11,7 +11,6 @@ structure group by group with the loss reductions as tensor algebra.
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from .anchor import ETAnchor

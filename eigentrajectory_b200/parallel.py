@@ -13,7 +13,6 @@ backend is the CUDA library.
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
