@@ -7,7 +7,16 @@ SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(SRCS))
 LIB       := eigentrajectory_b200/libet_b200.so
 
-all: $(LIB)
+ORACLE_LIB := oracle/_build/libet_oracle.so
+
+all: $(LIB) $(ORACLE_LIB)
+
+# plain-C restatement of the bit-exact part of the oracle (test infrastructure; never linked into the product)
+$(ORACLE_LIB): oracle/et_oracle_kmeans.c
+	@mkdir -p oracle/_build
+	gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC -o $@ $< -lm
+
+oracle: $(ORACLE_LIB)
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/et_b200.h
 	@mkdir -p $(OBJDIR)
@@ -17,6 +26,6 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared -cudart static -o $@ $(OBJS)
 
 clean:
-	rm -rf $(OBJDIR) $(LIB)
+	rm -rf $(OBJDIR) $(LIB) oracle/_build
 
-.PHONY: all clean
+.PHONY: all clean oracle

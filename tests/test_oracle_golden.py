@@ -1,4 +1,6 @@
 """CPU: the oracle restatement vs outputs frozen from the UNMODIFIED reference (tests/golden)."""
+import os
+
 import numpy as np
 import torch
 
@@ -80,6 +82,49 @@ def test_kmeans_trace_bit_exact():
         ms, lb = O.kmeans_assign(t(g[f"edge{n}_data"]), t(g[f"edge{n}_cent"]))
         assert torch.equal(lb, t(g[f"edge{n}_labels"]))
         assert torch.equal(ms, t(g[f"edge{n}_maxsims"]))
+
+
+def test_plain_c_kmeans_assign_bit_exact():
+    """oracle/et_oracle_kmeans.c (gcc, no contraction) against the reference's lock-step trace, its ragged-size
+    fixtures, and the torch restatement on other (d, K, N) shapes of the summation-order rule -- all bit for bit."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", root, "oracle"], check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(os.path.join(root, "oracle", "_build", "libet_oracle.so"))
+    vp = ctypes.c_void_p
+    lib.et_oracle_kmeans_assign.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, vp, vp]
+    lib.et_oracle_kmeans_assign.restype = None
+
+    def c_assign(data, cent):
+        data, cent = data.contiguous().float(), cent.contiguous().float()
+        l, d, n = data.shape
+        labels = torch.empty((l, n), dtype=torch.int64)
+        sims = torch.empty((l, n), dtype=torch.float32)
+        lib.et_oracle_kmeans_assign(data.data_ptr(), cent.data_ptr(), l, d, n, cent.size(-1), labels.data_ptr(), sims.data_ptr())
+        return sims, labels
+
+    g = load_golden("kmeans")
+    data = t(g["data"])
+    for it in range(12):
+        ms, lb = c_assign(data, t(g["trace_centroids"][it]))
+        assert torch.equal(lb, t(g["trace_labels"][it]).long()), it
+        assert torch.equal(ms, t(g["trace_maxsims"][it])), it
+    for n in (1, 31, 33, 1000):
+        ms, lb = c_assign(t(g[f"edge{n}_data"]), t(g[f"edge{n}_cent"]))
+        assert torch.equal(lb, t(g[f"edge{n}_labels"])) and torch.equal(ms, t(g[f"edge{n}_maxsims"]))
+    gen = torch.Generator().manual_seed(11)
+    for d, k, n in ((2, 5, 1000), (3, 7, 777), (6, 40, 5000), (8, 33, 4099), (16, 64, 3000), (5, 20, 6), (6, 4, 100), (6, 20, 70)):
+        x, c = torch.randn(2, d, n, generator=gen), torch.randn(2, d, k, generator=gen)
+        ms, lb = c_assign(x, c)
+        o_ms, o_lb = O.kmeans_assign(x, c)
+        assert torch.equal(lb, o_lb) and torch.equal(ms, o_ms), (d, k, n)
+    # NaN centroid (an emptied cluster): torch.max lets the first NaN win
+    x, c = torch.randn(1, 6, 50, generator=gen), torch.randn(1, 6, 20, generator=gen)
+    c[0, :, 7] = float("nan")
+    ms, lb = c_assign(x, c)
+    o_ms, o_lb = O.kmeans_assign(x, c)
+    assert torch.equal(lb, o_lb) and bool(torch.isnan(ms).all()) and bool((lb == 7).all())
 
 
 def test_metrics_bit_exact():
