@@ -9,7 +9,7 @@ LIB       := eigentrajectory_b200/libet_b200.so
 
 ORACLE_LIB := oracle/_build/libet_oracle.so
 
-all: $(LIB) $(ORACLE_LIB)
+all: $(LIB) $(ORACLE_LIB) oracle-ref
 
 # plain-C restatement of the bit-exact part of the oracle (test infrastructure; never linked into the product)
 $(ORACLE_LIB): oracle/et_oracle_kmeans.c
@@ -17,6 +17,11 @@ $(ORACLE_LIB): oracle/et_oracle_kmeans.c
 	gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC -o $@ $< -lm
 
 oracle: $(ORACLE_LIB)
+
+# the unmodified reference staged for the GPU box (no-op where /root/reference does not exist: the prebuilt copy is used)
+REFERENCE ?= /root/reference
+oracle-ref:
+	@if [ -d $(REFERENCE)/EigenTrajectory ]; then oracle/make_ref.sh $(REFERENCE) > /dev/null; fi
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/et_b200.h
 	@mkdir -p $(OBJDIR)
@@ -26,6 +31,6 @@ $(LIB): $(OBJS)
 	$(NVCC) -shared -cudart static -o $@ $(OBJS)
 
 clean:
-	rm -rf $(OBJDIR) $(LIB) oracle/_build
+	rm -rf $(OBJDIR) $(LIB) oracle/_build oracle/_ref
 
-.PHONY: all clean oracle
+.PHONY: all clean oracle oracle-ref

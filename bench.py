@@ -1,11 +1,16 @@
 #!/usr/bin/env python
-"""Headline benchmark: descriptor project -> reconstruct (BASELINE.json config 2).
+"""Headline benchmark: descriptor project -> reconstruct (BASELINE.json config 2), plus the config-5 stages.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one fused pass normalise -> C = U^T x -> x^ = U C -> denormalise over one batch of
 1e6 synthetic pedestrians x (8 + 12) frames x 2-D per GPU, k = 6, coefficients materialised
 (368 algorithmic bytes per trajectory).  Prints ONE JSON line (rank 0).
+
+Beside the headline numbers the line carries ``stages``: the stages of the path that DO need an exchange when the rows
+are sharded (BASELINE.json config 5, 1.25e6 rows per GPU): eigen-basis (Gram pass + one all-reduce + eigen-solve),
+farthest-point seeding, and one k-means Lloyd iteration with the all-reduce done by NCCL and by the fused peer-memory
+kernel -- each checked for parity (sharded == unsharded basis, fused == NCCL == oracle labels) before it is timed.
 """
 import argparse
 import json
@@ -20,6 +25,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_PER_GPU = 1_000_000
+N_STAGE_PER_GPU = 1_250_000                       # config 5: 1e7 rows over 8 GPUs
 K_RANK, T_OBS, T_PRED = 6, 8, 12
 BYTES_PER_TRAJ = 64 + 96 + 64 + 96 + 48          # read obs+pred, write rec_obs+rec_pred, write C_obs+C_pred
 METRIC = "trajectories/sec descriptor project+reconstruct"
@@ -27,13 +33,29 @@ UNIT = "trajectories/s"
 N_SETS = 3                                        # rotating buffer sets, each (368 MB) larger than the 126 MB L2
 
 
+def make_config(n, world):
+    """The workload description; identical in both arms (`--impl ours` and `--impl reference`)."""
+    return {"workload": "configs[1]: synthetic 1e6 pedestrians x (8+12) x 2-D per GPU, k=6, project+reconstruct S=1 "
+                        "(ori+rot+sca normaliser), coefficients materialised (368 B/trajectory)",
+            "n_per_gpu_per_step": n, "n_gpus": world,
+            "l2": f"{N_SETS} rotating buffer sets of {n * BYTES_PER_TRAJ / 1e6:.0f} MB each (> 126 MB L2)",
+            "parallelism": f"row-sharded x{world}, no data-path collective"}
+
+
 def measured_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel from the committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel from the newest committed ncu
+    capture (profiles/r*_traffic.json, written by scripts/collect_profiles.py from an `ncu --set full` run).  It is a
+    STATIC number of that capture, not re-measured by this run: `traffic_source` says which build it came from."""
+    best = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return float(json.load(f)["traffic_bytes_per_launch"])
+        for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+            if name.endswith("_traffic.json"):
+                best = name
+        with open(os.path.join(ROOT, "profiles", best)) as f:
+            d = json.load(f)
+        return float(d["traffic_bytes_per_launch"]), f"static ncu capture profiles/{best} ({d.get('source', 'ncu --set full')})"
     except Exception:
-        return None
+        return None, None
 
 
 def peaks():
@@ -95,44 +117,184 @@ def physical_gpu_index(local):
     return local
 
 
-def cpu_project_reconstruct_throughput(n, reps, threads):
-    """The reference's CPU torch path (oracle restatement of descriptor.py:144-176 at S=1), all host threads."""
-    from oracle import et_oracle as O     # the only place bench.py touches the oracle: as the CPU baseline
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own descriptor code (oracle/_ref, staged by oracle/make_ref.sh) or, if that is not staged,
+# the oracle port.  This is the one place bench.py executes anything under oracle/.
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_round_trip(n, threads):
+    """Returns (step, kind, what): ``step()`` runs the reference's CPU path of one project -> reconstruct pass over the
+    full n-trajectory batch (descriptor.py:144-160 projection, :75-89 to_Euclidean_space, normalizer.py:53-62)."""
     torch.set_num_threads(threads)
+    from oracle import et_oracle as O
+    from oracle import ref_loader
     obs, pred = O.synthetic_trajectories(n, seed=0)
+    if ref_loader.available():
+        ET = ref_loader.load("EigenTrajectory")
+        from EigenTrajectory.descriptor import ETDescriptor as RefDescriptor
+        hp = {"obs_len": T_OBS, "pred_len": T_PRED, "k": K_RANK, "num_samples": 20, "traj_dim": 2, "obs_svd": True,
+              "pred_svd": True}
+        desc = RefDescriptor(type("HP", (), hp)())
+        with torch.no_grad():
+            desc.parameter_initialization(obs, pred)          # torch.linalg.svd of the same data (untimed)
+
+            def step():
+                C_obs, C_pred = desc.projection(obs, pred)
+                rec_obs = desc.denormalize_trajectory(desc.to_Euclidean_space(C_obs, desc.U_obs_trunc))
+                rec_pred = desc.denormalize_trajectory(desc.to_Euclidean_space(C_pred, desc.U_pred_trunc))
+                return rec_obs, rec_pred, C_obs, C_pred
+        del ET
+        return step, "reference", "the reference's own ETDescriptor.projection + to_Euclidean_space + denormalize (oracle/_ref)"
     ref = O.parameter_initialization(obs, pred, K_RANK)
     Uo, Up = ref["U_obs"].contiguous(), ref["U_pred"].contiguous()
-    O.project_reconstruct(obs, pred, Uo, Up)          # warm-up
-    times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.project_reconstruct(obs, pred, Uo, Up)
-        times.append(time.perf_counter() - t0)
-    return times
+    return (lambda: O.project_reconstruct(obs, pred, Uo, Up)), "port", "oracle/et_oracle.py project_reconstruct (torch CPU ops)"
+
+
+def cpu_times(n, reps, warmup, threads):
+    step, kind, what = cpu_round_trip(n, threads)
+    with torch.no_grad():
+        for _ in range(max(warmup, 1)):
+            step()
+        times = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            step()
+            times.append(time.perf_counter() - t0)
+    return times, kind, what, torch.get_num_threads()
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        pass
-    times = cpu_project_reconstruct_throughput(N_PER_GPU, max(args.steps, 1), threads)
+    n = args.n
+    times, kind, what, used = cpu_times(n, max(args.steps, 1), min(args.warmup, 3), threads)
     total = sum(times)
-    value = N_PER_GPU * len(times) / total
+    value = n * len(times) / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic 1e6 pedestrians x (8+12) x 2-D, k=6, project+reconstruct S=1 "
-                               "(ori+rot+sca normaliser), coefficients materialised", "n_per_step": N_PER_GPU},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{len(times)} x the full 1e6-trajectory batch, torch CPU ops of the reference's path "
-                                   f"(oracle/et_oracle.py project_reconstruct), {threads} threads"},
+        "config": make_config(n, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind,
+                         "sample": f"{len(times)} x the full {n}-trajectory batch of one GPU: {what}, {used} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# config-5 stages (the ones with an exchange), parity-checked and timed at every N
+# ------------------------------------------------------------------------------------------------------------------
+def run_stages(et, dist, dev, rank, world, n_rows, reps):
+    from eigentrajectory_b200 import ops, parallel as P
+    from eigentrajectory_b200.synthetic import synthetic_trajectories
+    from oracle import et_oracle as O                      # checker only: parity assertions before anything is timed
+
+    def tmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def timed(fn, count, inner=1):
+        for _ in range(2):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(count):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return tmax(e0.elapsed_time(e1) / (count * inner))
+
+    obs, pred = (x.to(dev) for x in synthetic_trajectories(n_rows, seed=1000 + rank))
+    a = rank * n_rows
+    n_total = world * n_rows
+    parity = {}
+
+    # ---- parity 1: sharded basis (local Gram, ONE all-reduce, replicated eigen-solve) == unsharded basis ----
+    Uo, So, Up, Sp = P.sharded_basis(obs, pred, K_RANK)
+    if world > 1:
+        all_obs = torch.empty((n_total, T_OBS, 2), device=dev)
+        all_pred = torch.empty((n_total, T_PRED, 2), device=dev)
+        dist.all_gather_into_tensor(all_obs, obs)
+        dist.all_gather_into_tensor(all_pred, pred)
+    else:
+        all_obs, all_pred = obs, pred
+    G_o, G_p = ops.gram(all_obs, all_pred, True, True, True)                         # one device, all rows
+    g_o, g_p = ops.gram(obs, pred, True, True, True)
+    packed = torch.cat([g_o.reshape(-1), g_p.reshape(-1)])
+    if world > 1:
+        dist.all_reduce(packed)
+    gram_rel = float(((packed - torch.cat([G_o.reshape(-1), G_p.reshape(-1)])).abs().max() / G_p.abs().max()))
+    (U1o, S1o), (U1p, S1p) = ops.eig_basis_pair(G_o, G_p, K_RANK)
+    proj = float((Up.double() @ Up.double().T - U1p.double() @ U1p.double().T).norm())
+    parity["gram_sharded_vs_unsharded_rel"] = gram_rel
+    parity["basis_projector_dist"] = proj
+    assert gram_rel <= 1e-12, f"sharded Gram differs from the unsharded one: {gram_rel:.3e}"
+    assert proj <= 1e-6 and float((Sp - S1p).abs().max() / S1p.max()) <= 1e-6, "sharded basis differs from the unsharded one"
+    del all_obs, all_pred
+
+    # ---- parity 2: k-means over the sharded coefficients: NCCL path == fused peer-memory path == oracle labels ----
+    C = ops.project(obs, pred, Uo, Up)[1].unsqueeze(0).contiguous()                  # (1, 6, n_rows) of this rank
+    first = 12345
+    cent0 = P.sharded_farthest_init(C, 20, first, a)
+    m = 6
+    lab_n, cent_n, it_n, inertia_n = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m, tol=-1.0)
+    _, cent_before, _, _ = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m - 1, tol=-1.0)
+    _, o_lab = O.kmeans_assign(C.cpu(), cent_before.cpu())                           # the reference's arithmetic on this shard
+    mism_nccl = int((lab_n.cpu() != o_lab).sum())
+    fused_ok = world > 1 and P.peer_exchange_available(dev)
+    mism_fused, fused_equal = None, None
+    if fused_ok:
+        lab_f, cent_f, it_f, inertia_f = P.sharded_kmeans_fit_fused(C, 20, n_total, cent0, max_iter=m, tol=-1.0)
+        mism_fused = int((lab_f.cpu() != o_lab).sum())
+        fused_equal = bool(torch.equal(lab_f, lab_n) and torch.equal(cent_f, cent_n) and it_f == it_n)
+    elif world == 1:
+        km = et.BatchKMeans(n_clusters=20, max_iter=m, tol=-1.0)
+        lab_f = km.fit(C, centroids=cent0)                                            # the persistent whole-fit kernel
+        mism_fused = int((lab_f.cpu() != o_lab).sum())
+        fused_equal = bool(torch.equal(lab_f, lab_n) and torch.equal(km.centroids, cent_n))
+    flags = torch.tensor([mism_nccl, mism_fused or 0, 0 if fused_equal in (True, None) else 1], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flags)
+    parity["kmeans_label_mismatch_vs_oracle_nccl"] = int(flags[0])
+    parity["kmeans_label_mismatch_vs_oracle_fused"] = int(flags[1]) if mism_fused is not None else None
+    parity["kmeans_fused_equals_nccl_bitwise"] = (int(flags[2]) == 0) if fused_equal is not None else None
+    assert int(flags[0]) == 0 and int(flags[1]) == 0 and int(flags[2]) == 0, f"k-means parity failed: {parity}"
+
+    # ---- timing (CUDA events on the launching stream, max over ranks) ----
+    st = {"rows_per_gpu": n_rows, "rows_total": n_total, "kmeans": "d=6, K=20 on the C_pred coefficients of the rows"}
+    st["basis_ms"] = timed(lambda: P.sharded_basis(obs, pred, K_RANK), reps)
+    st["gram_pass_ms"] = timed(lambda: ops.gram(obs, pred, True, True, True), reps)
+    st["seed_ms"] = timed(lambda: P.sharded_farthest_init(C, 20, first, a), 3)
+    acc = ops.KMeansWorkspace(1, 6, 20, dev)
+    nxt = torch.empty_like(cent0)
+
+    def km_iter():
+        ops.kmeans_assign(C, cent0, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum)
+        if world > 1:
+            dist.all_reduce(acc.flat)
+        ops.kmeans_finalize(acc, cent0, nxt)
+    st["kmeans_iter_nccl_ms"] = timed(km_iter, reps)
+    iters = 100
+    if fused_ok:
+        st["kmeans_iter_fused_ms"] = timed(lambda: P.sharded_kmeans_fit_fused(C, 20, n_total, cent0, max_iter=iters, tol=-1.0),
+                                           3, iters)
+    elif world == 1:
+        km = et.BatchKMeans(n_clusters=20, max_iter=iters, tol=-1.0)
+        st["kmeans_iter_fused_ms"] = timed(lambda: km.fit(C, centroids=cent0), 3, iters)
+    else:
+        st["kmeans_iter_fused_ms"] = None
+    best = min(v for v in (st["kmeans_iter_nccl_ms"], st["kmeans_iter_fused_ms"]) if v)
+    st["kmeans_points_per_s"] = n_total / (best * 1e-3)
+    st["basis_traj_per_s"] = n_total / (st["basis_ms"] * 1e-3)
+    st["parity"] = parity
+    return st
 
 
 def main():
@@ -145,6 +307,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="trajectories per GPU per step")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the config-5 stages (basis / seeding / k-means iteration)")
+    ap.add_argument("--stage-rows", type=int, default=N_STAGE_PER_GPU, help="rows per GPU of the config-5 stages")
     ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic stream serialization (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -165,6 +329,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    et.ops.bind_host_memory_to_device(dev)          # NUMA: this process's pinned buffers live next to its GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -254,43 +419,57 @@ def main():
         dt = time.perf_counter() - t0
         if j >= 3:
             e2e_times.append(dt)
-    e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    e2e_local = sum(e2e_times) / len(e2e_times)
+    e2e_t = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = world * n / float(e2e_t.item())
     assert not ro.is_cuda and ro.shape == host_obs.shape
+    # per-rank PCIe rate (both directions summed) so that host-side contention at N > 1 is visible in the line
+    rates = torch.zeros(world, dtype=torch.float64, device=dev)
+    rates[rank] = n * 368 / e2e_local / 1e9
+    if world > 1:
+        dist.all_reduce(rates)
+    del ro, rp, co, cp
+
+    stages = None
+    if not args.no_stages:
+        stages = run_stages(et, dist, dev, rank, world, args.stage_rows, reps=20)
 
     if rank == 0:
         peak, peak_src = peaks()
         avg_ms = total_ms / args.steps            # this rank's timed region: K launches back to back
         achieved = n * BYTES_PER_TRAJ / (avg_ms * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic() if (args.variant in (0, 2) and n == N_PER_GPU) else (None, None)
+        cfg = make_config(n, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: synthetic 1e6 pedestrians x (8+12) x 2-D per GPU, k=6, fused project+reconstruct "
-                                   "S=1 (ori+rot+sca normaliser), coefficients materialised (368 B/trajectory)",
-                       "n_per_gpu_per_step": n, "kernel_variant": args.variant,
-                       "l2": f"{N_SETS} rotating buffer sets of {n * BYTES_PER_TRAJ / 1e6:.0f} MB each (> 126 MB L2)",
-                       "parallelism": f"row-sharded x{world}, no data-path collective"},
+            "config": cfg,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic() if (args.variant in (0, 2) and n == N_PER_GPU) else None, "kernel": "project_reconstruct_tma" if args.variant != 1 else "project_reconstruct_direct",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "project_reconstruct_tma" if args.variant != 1 else "project_reconstruct_direct",
                          "algorithmic_bytes_per_launch": n * BYTES_PER_TRAJ, "avg_launch_ms": avg_ms,
-                         "min_launch_ms": min(per_launch_ms), "peak_source": peak_src,
+                         "min_launch_ms": min(per_launch_ms), "peak_source": peak_src, "kernel_variant": args.variant,
                          "launch": "programmatic dependent launch" if not args.no_pdl else "plain stream order"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 208,
-                    "api": "ETDescriptor.project_reconstruct(host tensors)", "ms_per_step": 1e3 * float(e2e_t.item())},
+                    "api": "ETDescriptor.project_reconstruct(host tensors)", "ms_per_step": 1e3 * float(e2e_t.item()),
+                    "pcie_gbs_per_rank": [round(float(v), 2) for v in rates.tolist()],
+                    "host_numa": et.ops.host_numa_summary()},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
         }
+        if stages is not None:
+            line["stages"] = stages
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            times = cpu_project_reconstruct_throughput(n, 5, threads)
-            line["cpu_baseline"] = {"value": n / min(times), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"best of 5 passes over the full {n}-trajectory batch "
-                                              f"(oracle/et_oracle.py project_reconstruct, torch CPU, {threads} threads)"}
+            times, kind, what, used = cpu_times(n, 5, 1, threads)
+            line["cpu_baseline"] = {"value": n / min(times), "unit": UNIT, "cores": used, "kind": kind,
+                                    "sample": f"best of 5 passes over the full {n}-trajectory batch ({what}, {used} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import torch
 
@@ -99,7 +100,16 @@ def require_cuda():
         raise ETLibraryError("eigentrajectory_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
 
 
+_guard = threading.local()
+
+
 def check(rc, what):
+    """Raise on a non-zero return code.  Also ends the device guard opened by :func:`stream_of` for this call."""
+    prev = getattr(_guard, "prev", None)
+    if prev is not None:
+        _guard.prev = None
+        if prev >= 0:
+            torch.cuda.set_device(prev)
     if rc != 0:
         msg = load().et_last_error().decode("utf-8", "replace")
         raise ETLibraryError(f"{what} failed with code {rc}: {msg}")
@@ -111,7 +121,20 @@ def ptr(t):
 
 
 def stream_of(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """Current stream of ``device`` as a ``cudaStream_t`` -- and makes ``device`` the CURRENT CUDA device until the
+    matching :func:`check` (every call site reads ``check(lib.fn(..., stream_of(dev)), name)``: the arguments are
+    evaluated before the call, ``check`` runs after it).  The library sizes its grids, sets kernel attributes and
+    launches (cooperatively) on the current device, so a tensor on ``cuda:1`` must not be processed while ``cuda:0``
+    is current; the caller's current device is restored afterwards."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_device()
+    if idx != cur:
+        torch.cuda.set_device(idx)
+        _guard.prev = cur
+    else:
+        _guard.prev = -1
+    return C.c_void_p(torch.cuda.current_stream(idx).cuda_stream)
 
 
 def launch_count():

@@ -18,32 +18,30 @@ from .descriptor import ETDescriptor
 
 
 class EigenTrajectory(nn.Module):
-    r"""The EigenTrajectory model
+    """Predictor-agnostic EigenTrajectory wrapper (same constructor and ``state_dict`` keys as the reference's class,
+    model.py:7-32).
 
-    Args:
-        baseline_model (nn.Module): The baseline model
-        hook_func (dict): The bridge functions for the baseline model
-        hyper_params (DotDict): The hyper-parameters
+    ``baseline_model``: the predictor network behind the hook seam.  ``hook_func``: its three bridge functions
+    (``model_forward_pre_hook``, ``model_forward``, ``model_forward_post_hook``).  ``hyper_params``: DotDict with
+    ``obs_len, pred_len, k, num_samples, traj_dim, static_dist, obs_svd, pred_svd``.
+
+    Two descriptor / anchor pairs are kept: ``ET_m_*`` for moving pedestrians (scale normalisation on) and ``ET_s_*``
+    for static ones (scale off); ``static_dist`` decides the group per pedestrian.
     """
 
     def __init__(self, baseline_model, hook_func, hyper_params):
         super().__init__()
-
-        self.baseline_model = baseline_model
-        self.hook_func = hook_func
-        self.hyper_params = hyper_params
-        self.t_obs, self.t_pred = hyper_params.obs_len, hyper_params.pred_len
-        self.obs_svd, self.pred_svd = hyper_params.obs_svd, hyper_params.pred_svd
-        self.k = hyper_params.k
-        self.s = hyper_params.num_samples
-        self.dim = hyper_params.traj_dim
-        self.static_dist = hyper_params.static_dist
-
-        self.ET_m_descriptor = ETDescriptor(hyper_params=hyper_params, norm_sca=True)
-        self.ET_s_descriptor = ETDescriptor(hyper_params=hyper_params, norm_sca=False)
-        self.ET_m_anchor = ETAnchor(hyper_params=hyper_params)
-        self.ET_s_anchor = ETAnchor(hyper_params=hyper_params)
-        self.fused = True
+        hp = hyper_params
+        self.baseline_model, self.hook_func, self.hyper_params = baseline_model, hook_func, hp
+        self.t_obs, self.t_pred = hp.obs_len, hp.pred_len
+        self.obs_svd, self.pred_svd = hp.obs_svd, hp.pred_svd
+        self.k, self.s, self.dim, self.static_dist = hp.k, hp.num_samples, hp.traj_dim, hp.static_dist
+        # registration order fixes the state_dict key order: m-descriptor, s-descriptor, m-anchor, s-anchor
+        self.ET_m_descriptor = ETDescriptor(hyper_params=hp, norm_sca=True)
+        self.ET_s_descriptor = ETDescriptor(hyper_params=hp, norm_sca=False)
+        self.ET_m_anchor = ETAnchor(hyper_params=hp)
+        self.ET_s_anchor = ETAnchor(hyper_params=hp)
+        self.fused = True          # mask-free forward (two or three launches); False: the reference's gather / scatter shape
 
     def _can_fuse(self):
         tm, ts = self.ET_m_descriptor.traj_normalizer, self.ET_s_descriptor.traj_normalizer
@@ -137,15 +135,19 @@ class EigenTrajectory(nn.Module):
         C_obs, C_pred_gt, state, moving = ops.forward_project(
             obs_traj, pred_traj, dm.U_obs_trunc, ds.U_obs_trunc, dm.U_pred_trunc, ds.U_pred_trunc, self.static_dist)
         C_obs, C_pred_gt = ops.back_to(C_obs, obs_traj), ops.back_to(C_pred_gt, obs_traj)
+        # each group's normaliser sees its rows of the per-scene state exactly as after the reference's projection()
+        # calls (model.py:80-81) -- as a deferred selection, so no boolean gather happens unless the state is read
+        dm.traj_normalizer.set_deferred(state, moving)
+        ds.traj_normalizer.set_deferred(state, ~moving)
 
-        # Absolute coordinate
+        # predictor input: last observed positions relative to the centre of the scene (model.py:88-90)
         obs_ori = ops.back_to(state[0], obs_traj).squeeze(dim=1).T.clone()
-        obs_ori -= obs_ori.mean(dim=1, keepdim=True)  # move scene to origin
+        obs_ori -= obs_ori.mean(dim=1, keepdim=True)
 
-        # Trajectory prediction (plugin seam, unchanged)
-        input_data = self.hook_func.model_forward_pre_hook(C_obs, obs_ori, addl_info)
-        output_data = self.hook_func.model_forward(input_data, self.baseline_model)
-        C_pred_refine = self.hook_func.model_forward_post_hook(output_data, addl_info)
+        # the three bridge calls of the plugin seam, as the reference makes them (model.py:93-95)
+        hooks = self.hook_func
+        C_pred_refine = hooks.model_forward_post_hook(
+            hooks.model_forward(hooks.model_forward_pre_hook(C_obs, obs_ori, addl_info), self.baseline_model), addl_info)
         if C_pred_refine.size(2) != self.s:
             C_pred_refine = C_pred_refine[:, :, :self.s]
 

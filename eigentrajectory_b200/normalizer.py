@@ -18,15 +18,49 @@ from . import ops
 _STATE = ("traj_ori", "traj_rot", "traj_sca")
 
 
+def _state_property(name):
+    slot = "_" + name
+
+    def get(self):
+        self._materialise()
+        return getattr(self, slot)
+
+    def put(self, value):
+        self._materialise()            # an explicit assignment to one field must not be overwritten later
+        setattr(self, slot, value)
+
+    return property(get, put)
+
+
 class TrajNorm:
     """Translation / rotation / scale normaliser for trajectories of shape ``(num_peds, length_of_time, 2)``.
 
-    ``ori``, ``rot``, ``sca`` switch the three stages on or off (all on by default)."""
+    ``ori``, ``rot``, ``sca`` switch the three stages on or off (all on by default).
+
+    ``traj_ori`` / ``traj_rot`` / ``traj_sca`` are plain public attributes for the caller.  Internally they may be held
+    as a *deferred row selection* (:meth:`set_deferred`): the fused ``EigenTrajectory.forward`` computes the state of
+    every pedestrian of the scene in one kernel and hands each group's normaliser (full state, row mask) -- the
+    boolean gather, which needs a host synchronisation, only happens if somebody actually reads the state."""
+
+    traj_ori, traj_rot, traj_sca = (_state_property(n) for n in _STATE)
 
     def __init__(self, ori=True, rot=True, sca=True):
         self.ori, self.rot, self.sca = ori, rot, sca
+        self._deferred = None
         for name in _STATE:
-            setattr(self, name, None)
+            setattr(self, "_" + name, None)
+
+    def set_deferred(self, full_state, rows):
+        """State of this normaliser := ``full_state[i][rows]`` for the enabled stages, gathered on first use."""
+        self._deferred = (full_state, rows)
+
+    def _materialise(self):
+        if self._deferred is None:
+            return
+        (full, rows), self._deferred = self._deferred, None
+        for name, on, value in zip(_STATE, self._enabled(), full):
+            if on and value is not None:
+                setattr(self, "_" + name, value[rows])
 
     def _enabled(self):
         return self.ori, self.rot, self.sca

@@ -78,21 +78,53 @@ def _apply_norm(fn_name, traj, ori, rot, sca):
     return back_to(out, traj)
 
 
+def _wants_grad(t):
+    return t is not None and t.requires_grad and torch.is_grad_enabled()
+
+
+class _AffineMap(torch.autograd.Function):
+    """``normalize`` / ``denormalize`` with autograd with respect to the trajectory (the reference's tensor algebra is
+    differentiable there, normalizer.py:42-62).  Both maps are affine in ``traj``; the vector-Jacobian product of one is
+    the linear part of the other with the scale inverted: d normalize = (g * sca) @ R^T, d denormalize = (g @ R) / sca.
+    The normaliser state is treated as a constant (it is derived from the observed frames once per batch)."""
+
+    @staticmethod
+    def forward(ctx, traj, fn_name, ori, rot, sca):
+        ctx.fn_name = fn_name
+        ctx.save_for_backward(*(v for v in (rot, sca) if v is not None))
+        ctx.have = (rot is not None, sca is not None)
+        return _apply_norm(fn_name, traj, ori, rot, sca)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = list(ctx.saved_tensors)
+        rot = saved.pop(0) if ctx.have[0] else None
+        sca = saved.pop(0) if ctx.have[1] else None
+        inv = (1.0 / sca) if sca is not None else None
+        back = "et_denormalize" if ctx.fn_name == "et_normalize" else "et_normalize"
+        if rot is None and inv is None:
+            return g, None, None, None, None
+        return _apply_norm(back, g.contiguous(), None, rot, inv), None, None, None, None
+
+
 def normalize(traj, ori, rot, sca):
-    """TrajNorm.normalize with explicit state (None = stage disabled)."""
+    """TrajNorm.normalize with explicit state (None = stage disabled); differentiable with respect to ``traj``."""
+    if _wants_grad(traj):
+        return _AffineMap.apply(traj, "et_normalize", ori, rot, sca)
     return _apply_norm("et_normalize", traj, ori, rot, sca)
 
 
 def denormalize(traj, ori, rot, sca):
-    """TrajNorm.denormalize with explicit state (None = stage disabled)."""
+    """TrajNorm.denormalize with explicit state (None = stage disabled); differentiable with respect to ``traj``."""
+    if _wants_grad(traj):
+        return _AffineMap.apply(traj, "et_denormalize", ori, rot, sca)
     return _apply_norm("et_denormalize", traj, ori, rot, sca)
 
 
 # ----------------------------------------------------------------------------------------
 # descriptor (EigenTrajectory/descriptor.py)
 # ----------------------------------------------------------------------------------------
-def to_et_space(traj, evec):
-    """C (k,N) = evec^T M,  M = traj.reshape(-1, 2T)^T."""
+def _to_et_space_raw(traj, evec):
     U = to_dev(evec)
     x = to_dev(traj).to(U.device).reshape(-1, U.size(0))
     n, k = x.size(0), U.size(1)
@@ -102,9 +134,7 @@ def to_et_space(traj, evec):
     return back_to(C, traj)
 
 
-def to_euclidean_space(C, evec, dim=2):
-    """traj (N,T,dim) = (evec C)^T; C (k,N) may be a strided view (e.g. C3[:, :, s])."""
-    assert dim == 2, "only 2-D trajectories are supported"
+def _to_euclidean_space_raw(C, evec):
     U = to_dev(evec)
     Cd = C.detach()
     if not Cd.is_cuda:
@@ -117,6 +147,51 @@ def to_euclidean_space(C, evec, dim=2):
     check(load().et_to_euclidean_space(ptr(Cd), Cd.stride(0), Cd.stride(1), n, U.size(0) // 2, ptr(U), k, ptr(out),
                                        stream_of(Cd.device)), "et_to_euclidean_space")
     return back_to(out, C)
+
+
+class _ToETSpace(torch.autograd.Function):
+    """C = U^T M with autograd with respect to the trajectory (``evec`` is detached in the reference, descriptor.py:71):
+    the vector-Jacobian product is the other direction of the same pair of kernels, grad_traj = (U grad_C)^T."""
+
+    @staticmethod
+    def forward(ctx, traj, evec):
+        ctx.save_for_backward(evec)
+        ctx.shape = traj.shape
+        return _to_et_space_raw(traj, evec)
+
+    @staticmethod
+    def backward(ctx, g):
+        (evec,) = ctx.saved_tensors
+        return _to_euclidean_space_raw(g, evec).reshape(ctx.shape), None
+
+
+class _ToEuclideanSpace(torch.autograd.Function):
+    """traj = (U C)^T with autograd with respect to C (descriptor.py:87): grad_C = U^T grad_traj."""
+
+    @staticmethod
+    def forward(ctx, C, evec):
+        ctx.save_for_backward(evec)
+        return _to_euclidean_space_raw(C, evec)
+
+    @staticmethod
+    def backward(ctx, g):
+        (evec,) = ctx.saved_tensors
+        return _to_et_space_raw(g.contiguous(), evec), None
+
+
+def to_et_space(traj, evec):
+    """C (k,N) = evec^T M,  M = traj.reshape(-1, 2T)^T; differentiable with respect to ``traj``."""
+    if _wants_grad(traj):
+        return _ToETSpace.apply(traj, evec.detach())
+    return _to_et_space_raw(traj, evec)
+
+
+def to_euclidean_space(C, evec, dim=2):
+    """traj (N,T,dim) = (evec C)^T; C (k,N) may be a strided view (e.g. C3[:, :, s]); differentiable with respect to C."""
+    assert dim == 2, "only 2-D trajectories are supported"
+    if _wants_grad(C):
+        return _ToEuclideanSpace.apply(C, evec.detach())
+    return _to_euclidean_space_raw(C, evec)
 
 
 def project(obs, pred, U_obs, U_pred, ori=True, rot=True, sca=True):
@@ -380,13 +455,77 @@ def _streams(device, count=3):
 
 
 def _host_chunks(n):
+    """Cut [0, n) into pipeline chunks: a short first chunk (the D2H direction idles until the first kernel has run)
+    and short last chunks (the H2D direction idles while the last results drain), full-size chunks in between."""
+    first, tail = min(HOST_FIRST_CHUNK, HOST_CHUNK), [HOST_CHUNK // 2, HOST_CHUNK // 4]
     cuts, a = [], 0
-    size = min(HOST_FIRST_CHUNK, HOST_CHUNK)
-    while a < n:
-        b = min(n, a + size)
+    body_end = (n - sum(tail)) // 128 * 128 if n >= 4 * HOST_CHUNK else n      # chunk starts stay on tile boundaries
+    size = first
+    while a < body_end:
+        b = min(body_end, a + size)
         cuts.append((a, b))
         a, size = b, HOST_CHUNK
+    for size in tail[:-1]:
+        if n - a > size + tail[-1]:
+            cuts.append((a, a + size))
+            a += size
+    if a < n:
+        cuts.append((a, n))          # the last chunk takes the remainder
     return cuts
+
+
+_numa = {"bound": False, "why": "bind_host_memory_to_device() not called"}
+
+
+def _read(path):
+    with open(path) as f:
+        return f.read().strip()
+
+
+def _cpulist(text):
+    cpus = set()
+    for part in text.split(","):
+        if "-" in part:
+            lo, hi = part.split("-")
+            cpus.update(range(int(lo), int(hi) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_host_memory_to_device(device):
+    """Best effort, one process per GPU: run this process on the CPUs of the NUMA node the GPU hangs off and make that
+    node the preferred one for its memory (pinned staging buffers included), so that host <-> device copies of several
+    ranks do not all cross the same socket link.  A no-op (with the reason recorded) on single-node hosts, when the
+    topology is hidden (numa_node = -1) or when the calls are not permitted.  Returns the summary dict."""
+    import ctypes
+    import glob
+    import os
+    global _numa
+    try:
+        nodes = sorted(int(os.path.basename(p)[4:]) for p in glob.glob("/sys/devices/system/node/node[0-9]*"))
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(_read(f"/sys/bus/pci/devices/{bus}/numa_node"))
+        info = {"gpu_pci": bus, "gpu_numa_node": node, "host_numa_nodes": len(nodes)}
+        if len(nodes) < 2 or node < 0:
+            _numa = dict(info, bound=False, why="single NUMA node visible" if len(nodes) < 2 else "GPU reports no NUMA node")
+            return _numa
+        cpus = _cpulist(_read(f"/sys/devices/system/node/node{node}/cpulist")) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238          # x86-64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        _numa = dict(info, bound=rc == 0, cpus=len(cpus), why="ok" if rc == 0 else f"set_mempolicy errno {ctypes.get_errno()}")
+    except Exception as exc:      # topology files missing, sandboxed syscalls, ...
+        _numa = {"bound": False, "why": f"{type(exc).__name__}: {exc}"}
+    return _numa
+
+
+def host_numa_summary():
+    return dict(_numa)
 
 
 def _project_reconstruct_host(obs, pred, U_obs, U_pred, ori, rot, sca, want_coeffs, variant):

@@ -176,6 +176,36 @@ def test_round_trip_is_a_projection(et, O):
     assert torch.isfinite(ro).all() and torch.isfinite(rp).all()
 
 
+def test_headline_size_vs_oracle(et, O):
+    """Config 2, the exact bench inputs (synthetic_trajectories(1e6, seed=0), k = 6, ori+rot+sca, basis from the same
+    data): fused round trip and stand-alone projection against the CPU oracle at N = 1e6.
+    Tolerance 1e-5 (north_star) as max|x - ref| / max|ref| and relative Frobenius norm."""
+    n = 1_000_000
+    obs, pred = O.synthetic_trajectories(n, seed=0)
+    d = et.ETDescriptor(et.DotDict(HP)).cuda()
+    d.parameter_initialization(obs.cuda(), pred.cuda())
+    Uo, Up = d.U_obs_trunc.detach().cpu(), d.U_pred_trunc.detach().cpu()
+    want = O.project_reconstruct(obs, pred, Uo, Up)
+    worst = 0.0
+    for variant in (0, 1):
+        got = d.project_reconstruct(obs.cuda(), pred.cuda(), variant=variant)
+        for name, mine, ref in zip(("rec_obs", "rec_pred", "C_obs", "C_pred"), got, want):
+            e_max, e_fro = rel_max(mine.cpu(), ref), rel_fro(mine.cpu(), ref)
+            worst = max(worst, e_max, e_fro)
+            assert e_max < TOL and e_fro < TOL, (name, variant, e_max, e_fro)
+    C_obs, C_pred = d.projection(obs.cuda(), pred.cuda())
+    for name, mine, ref in (("C_obs", C_obs, want[2]), ("C_pred", C_pred, want[3])):
+        e_max, e_fro = rel_max(mine.cpu(), ref), rel_fro(mine.cpu(), ref)
+        worst = max(worst, e_max, e_fro)
+        assert e_max < TOL and e_fro < TOL, (name, "projection", e_max, e_fro)
+    # the host-buffer (pipelined H2D / kernel / D2H) path returns the same numbers as the resident one
+    host = d.project_reconstruct(obs.pin_memory(), pred.pin_memory())
+    resident = d.project_reconstruct(obs.cuda(), pred.cuda())
+    for mine, dev in zip(host, resident):
+        assert not mine.is_cuda and torch.equal(mine, dev.cpu())
+    print(f"headline size vs oracle: worst relative error {worst:.3e} (tolerance {TOL:g})")
+
+
 @pytest.mark.parametrize("tag,sca", [("sca1", True), ("sca0", False)])
 def test_reconstruction_and_gradient_match_reference(et, tag, sca):
     g = load_golden("descriptor_syn")
@@ -262,3 +292,64 @@ def test_host_buffers_round_trip(et, O):
     d.projection(t(g["obs"])[:100], t(g["pred"])[:100])
     rec = d.reconstruction(t(g["C_in"]))
     assert not rec.is_cuda and rel_max(rec, g["recon20_sca1"]) < TOL
+
+
+def test_descriptor_maps_are_differentiable(et, O):
+    """normalize / to_ET_space / to_Euclidean_space / denormalize carry autograd with respect to their data argument,
+    as the reference's tensor algebra does (normalizer.py:42-62, descriptor.py:59-89); the state and ``evec`` are
+    constants.  Gradients against torch autograd through the oracle's restatement."""
+    g = load_golden("descriptor_syn")
+    obs, pred = t(g["obs"])[:777], t(g["pred"])[:777]
+    U = t(g["U_pred_sca1"])
+    st = O.norm_params(obs)
+    w1 = torch.randn(6, 777, generator=torch.Generator().manual_seed(5))
+    w2 = torch.randn(777, 12, 2, generator=torch.Generator().manual_seed(6))
+
+    def chain(x, norm, to_et, to_eu, denorm):
+        C = to_et(norm(x))
+        back = denorm(to_eu(C))
+        return (C * w1.to(C.device)).sum() + (back * w2.to(back.device)).sum(), C, back
+
+    x_ref = pred.clone().requires_grad_(True)
+    loss_ref, C_ref, back_ref = chain(x_ref, lambda x: O.normalize(x, *st), lambda x: O.project(x, U),
+                                      lambda C: O.unproject(C, U), lambda x: O.denormalize(x, *st))
+    loss_ref.backward()
+
+    tn = et.TrajNorm()
+    tn.calculate_params(obs.cuda())
+    d = make_desc(et, g, "sca1", True)
+    x = pred.clone().cuda().requires_grad_(True)
+    loss, C, back = chain(x, tn.normalize, lambda v: d.to_ET_space(v, d.U_pred_trunc),
+                          lambda c: d.to_Euclidean_space(c, d.U_pred_trunc), tn.denormalize)
+    assert C.requires_grad and back.requires_grad
+    loss.backward()
+    assert rel_max(C.detach().cpu(), C_ref.detach()) < TOL and rel_max(back.detach().cpu(), back_ref.detach()) < TOL
+    assert rel_max(x.grad.cpu(), x_ref.grad) < TOL and rel_fro(x.grad.cpu(), x_ref.grad) < TOL
+    assert d.U_pred_trunc.grad is None                      # evec is detached, as in the reference
+    # without requires_grad (or under no_grad) nothing is recorded
+    with torch.no_grad():
+        assert not tn.normalize(x).requires_grad
+    assert not tn.normalize(pred.cuda()).requires_grad
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_tensors_on_a_non_current_device(et, O):
+    """A module / tensors on cuda:1 while cuda:0 is the current device: every op runs on the tensors' device (grids,
+    attributes and cooperative launches included) and the caller's current device is left untouched."""
+    g = load_golden("descriptor_syn")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 1)
+    obs, pred = O.synthetic_trajectories(20_000, seed=9)
+    d = et.ETDescriptor(et.DotDict(HP)).to(dev)
+    d.parameter_initialization(obs.to(dev), pred.to(dev))          # cooperative Gram pass + eigen-solve on cuda:1
+    assert torch.cuda.current_device() == 0
+    got = d.project_reconstruct(obs.to(dev), pred.to(dev))
+    want = O.project_reconstruct(obs, pred, d.U_obs_trunc.detach().cpu(), d.U_pred_trunc.detach().cpu())
+    for mine, ref in zip(got, want):
+        assert mine.device == dev and rel_max(mine.cpu(), ref) < TOL
+    km = et.BatchKMeans(n_clusters=20, max_iter=5)
+    data = got[3].unsqueeze(0).contiguous()
+    labels = km.fit(data, centroids=data[:, :, :20].contiguous())   # persistent cooperative kernel on cuda:1
+    o_lab, _, _, _ = O.kmeans_fit(data.cpu(), 20, centroids=data[:, :, :20].cpu().contiguous(), max_iter=5)
+    assert labels.device == dev and int((labels.cpu() != o_lab).sum()) <= 2
+    assert torch.cuda.current_device() == 0

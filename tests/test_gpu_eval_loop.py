@@ -55,16 +55,22 @@ def test_eth_test_loop_matches_reference(et, tmp_path, resident):
     funcs = {"ADE": et.compute_batch_ade, "FDE": et.compute_batch_fde, "TCC": et.compute_batch_tcc, "COL": et.compute_batch_col}
     vals = {k: [] for k in funcs}
     launches = et.launch_count()
+    scenes = 0
     with torch.no_grad():
         for batch in loader:
             obs, pred = [x.cuda(non_blocking=True) for x in batch[:2]]
             assert batch[0].is_cuda == resident
             out = model(obs)
+            before = et.launch_count()
             for k, fn in funcs.items():
                 v = fn(out["recon_traj"], pred)
                 assert isinstance(v, np.ndarray) and v.shape == (obs.size(0),)
                 vals[k].append(v)
-    assert et.launch_count() > launches                    # the CUDA library did the work
+            # ADE, FDE and TCC called in sequence (utils/trainer.py:186-193) share ONE pass over the samples; COL is the
+            # second launch
+            assert et.launch_count() - before == 2, et.launch_count() - before
+            scenes += 1
+    assert et.launch_count() - launches == 4 * scenes        # forward: project + reconstruct; metrics: one pass + COL
     for k in funcs:
         mine, ref = np.concatenate(vals[k]), gold[f"per_ped_{k}"]
         assert mine.shape == ref.shape == (181,)
