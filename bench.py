@@ -244,14 +244,23 @@ def run_stages(et, dist, dev, rank, world, n_rows, reps):
     first = 12345
     cent0 = P.sharded_farthest_init(C, 20, first, a)
     m = 6
-    lab_n, cent_n, it_n, inertia_n = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m, tol=-1.0)
-    _, cent_before, _, _ = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m - 1, tol=-1.0)
-    _, o_lab = O.kmeans_assign(C.cpu(), cent_before.cpu())                           # the reference's arithmetic on this shard
+    lab_n, cent_n, it_n, inertia_n = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m, tol=-1.0, row_offset=a)
+    _, cent_before, _, _ = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m - 1, tol=-1.0, row_offset=a)
+    if n_rows % 32 == 0 or world == 1:
+        # (with whole 32-column blocks per shard the reference's summation-order rule reads the same for a shard numbered
+        # on its own and for the same columns inside the unsharded tensor)
+        _, o_lab = O.kmeans_assign(C.cpu(), cent_before.cpu())                       # the reference's arithmetic
+    else:
+        C_all = torch.empty((world, 6, n_rows), device=dev)
+        dist.all_gather_into_tensor(C_all, C)
+        _, o_all = O.kmeans_assign(C_all.permute(1, 0, 2).reshape(1, 6, n_total).contiguous().cpu(), cent_before.cpu())
+        o_lab = o_all[:, a:a + n_rows]
+        del C_all
     mism_nccl = int((lab_n.cpu() != o_lab).sum())
     fused_ok = world > 1 and P.peer_exchange_available(dev)
     mism_fused, fused_equal = None, None
     if fused_ok:
-        lab_f, cent_f, it_f, inertia_f = P.sharded_kmeans_fit_fused(C, 20, n_total, cent0, max_iter=m, tol=-1.0)
+        lab_f, cent_f, it_f, inertia_f = P.sharded_kmeans_fit_fused(C, 20, n_total, cent0, max_iter=m, tol=-1.0, row_offset=a)
         mism_fused = int((lab_f.cpu() != o_lab).sum())
         fused_equal = bool(torch.equal(lab_f, lab_n) and torch.equal(cent_f, cent_n) and it_f == it_n)
     elif world == 1:

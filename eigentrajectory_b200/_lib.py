@@ -50,9 +50,10 @@ PROTOTYPES = {
     "et_svd_small": (_i, [_p, _p, _i, _l, _i, _i, _p, _p, _p]),
     "et_kmeans_workspace_bytes": (_sz, [_i, _i, _i]),
     "et_kmeans_assign": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "et_kmeans_assign_shard": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _l, _l, _p]),
     "et_kmeans_lloyd": (_i, [_p, _p, _i, _i, _l, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p]),
     "et_kmeans_exchange_bytes": (_sz, [_i, _i, _i, _i]),
-    "et_kmeans_lloyd_sharded": (_i, [_p, _p, _i, _i, _l, _i, _i, _d, _p, _p, _p, _p, _p, _p, _i, _i, _p, C.c_uint, _p]),
+    "et_kmeans_lloyd_sharded": (_i, [_p, _p, _i, _i, _l, _i, _i, _d, _p, _p, _p, _p, _p, _p, _i, _i, _p, C.c_uint, _l, _l, _p]),
     "et_kmeans_accumulate": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p]),
     "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _p]),
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),

@@ -152,16 +152,22 @@ __device__ __forceinline__ void best_centroid_packed(const float (&a)[PPL][DMAX]
     const ulonglong2 nb4 = *reinterpret_cast<const ulonglong2*>(nbn + j0);
 #pragma unroll
     for (int u = 0; u < PPL; ++u) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float y0, y1;
-        unpack2(add2(add2(mul2(dot[u][h], two), nan2[u]), h ? nb4.y : nb4.x), y0, y1);
-        if (LABELS) {
-          if (y0 > best[u]) { best[u] = y0; label[u] = j0 + 2 * h; }
-          if (y1 > best[u]) { best[u] = y1; label[u] = j0 + 2 * h + 1; }
-        } else {
-          best[u] = fmaxf(best[u], fmaxf(y0, y1));
-        }
+      float y0, y1, y2, y3;
+      unpack2(add2(add2(mul2(dot[u][0], two), nan2[u]), nb4.x), y0, y1);
+      unpack2(add2(add2(mul2(dot[u][1], two), nan2[u]), nb4.y), y2, y3);
+      if (LABELS) {
+        // arg-max of the group as a two-level tournament (a later column wins only if strictly greater, so ties keep
+        // the lowest index exactly like the ascending scan), then ONE dependent compare/select against the running
+        // best: the serial chain through `best` is K/4 steps long instead of K
+        const bool p01 = y1 > y0, p23 = y3 > y2;
+        const float v01 = p01 ? y1 : y0, v23 = p23 ? y3 : y2;
+        const int i01 = p01 ? j0 + 1 : j0, i23 = p23 ? j0 + 3 : j0 + 2;
+        const bool pg = v23 > v01;
+        const float vg = pg ? v23 : v01;
+        const int ig = pg ? i23 : i01;
+        if (vg > best[u]) { best[u] = vg; label[u] = ig; }
+      } else {
+        best[u] = fmaxf(best[u], fmaxf(fmaxf(y0, y1), fmaxf(y2, y3)));
       }
     }
   }
@@ -191,6 +197,10 @@ struct KmLloyd {
   int rank, world;
   unsigned char* const* xchg;   // DEVICE array [world]: base of every rank's exchange buffer as mapped on THIS rank
   unsigned stamp_base;          // flags of this call are stamp_base (ready) and stamp_base + 1 + iteration
+  // Row shards of one data set: the |a|^2 summation order of a column follows its GLOBAL index and the GLOBAL column
+  // count (as one unsharded tensor would be summed), so sharded and unsharded labels are the same bits.
+  int64_t col_offset;           // global index of this shard's column 0
+  int64_t n_global;             // columns over all shards (0: this launch holds all of them)
 };
 
 // Exchange buffer of one rank: uint32 ready[world] at byte 0, uint32 flag[2][world] at byte 128, then at byte 256
@@ -316,7 +326,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   // instruction per element instead of a conversion and an fp64 addition each -- starting at a lane-dependent column
   // (conflict-free, and a fixed order per row), and only the row sums go to the fp64 registers.  fp32 therefore
   // carries at most 32 * KM_FLUSH_EVERY points; everything above that (warps, blocks, grid, iterations) is fp64.
+  float sim32 = 0.f;            // best similarities of the points since the last flush (<= KM_FLUSH_EVERY per lane)
   auto flush = [&]() {
+    sim_acc += (double)sim32;
+    sim32 = 0.f;
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < NJP; ++j) {
@@ -397,7 +410,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     // is 32-bit arithmetic too and a load costs one IMAD + one IMAD.WIDE (no 64-bit address chains)
     const uint32_t n32 = (uint32_t)n;
     const uint32_t stride = gridDim.x * (uint32_t)(WARPS * 32 * PPL);
-    const uint32_t seq_limit = (n >= 4 && n < 8) ? 4u : 32u * (n32 / 32u);    // col_is_sequential(i, n) == i < seq_limit
+    const int64_t n_all = fit.n_global > 0 ? fit.n_global : n;
+    const uint32_t goff = (uint32_t)fit.col_offset;                           // km_check keeps global indices below 2^32
+    const uint32_t seq_limit = (n_all >= 4 && n_all < 8) ? 4u : 32u * (uint32_t)(n_all / 32);   // col_is_sequential(g, n_all) == g < seq_limit
     const float* dl_pin = dl;
     asm volatile("" : "+l"(dl_pin));     // opaque: keeps the batch entry's base in a register pair instead of re-deriving
                                          // data + l * d * n (64-bit multiplies) in front of every load
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
         bool finite = !nan_possible;
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
-          anorm[u] = sumsq_torch_order<DMAX>(a[u], d, idx[u] < seq_limit);
+          anorm[u] = sumsq_torch_order<DMAX>(a[u], d, goff + idx[u] < seq_limit);
           finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
         }
         if (finite) {
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
             } else {
               sslot[0] += 1.0f;
             }
-            sim_acc += (double)best[u];
+            sim32 += best[u];
           }
         }
       }
@@ -520,52 +535,66 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     // partial records are stored entry-major ([l][entry][block]) so that the fold below reads contiguous doubles
     double* lpart = partials + (size_t)l * gridDim.x * out_rec;
     for (int e = tid; e < out_rec; e += THREADS) lpart[(size_t)e * gridDim.x + blockIdx.x] = blk[e];
-    // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
-    if (!whole_fit) grid_barrier(barrier_ctr, nblocks);
-    else km_barrier(barrier_ctr + 2, nblocks, ++phase);
-    for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
-      const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
-      if (lane == 0) {
-        if (whole_fit && fit.world > 1) {
-          // sharded fit: this rank's folded entry goes straight into every rank's slot (its own included)
-          if (it == 0) xchg_wait_all(xchg_ready(fit.xchg[fit.rank]), fit.world, fit.stamp_base);   // peers are in this call
-          const size_t slot = (size_t)gridDim.y * out_rec;
-          for (int p = 0; p < fit.world; ++p)
-            xchg_slot(fit.xchg[p], it & 1, fit.world, fit.rank, slot)[(size_t)l * out_rec + e] = tot;
-          __threadfence_system();
-        } else if (whole_fit) {
-          fit.totals[(size_t)l * out_rec + e] = tot;
-        } else if (e < rec) {
-          const int c = e / (d + 1), r = e % (d + 1);
-          if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
-          else counts[(int64_t)l * k + c] += tot;
-        } else if (simsum) {
-          simsum[l] += tot;
+    if (!whole_fit) {
+      // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
+      grid_barrier(barrier_ctr, nblocks);
+      for (int e = blockIdx.x * WARPS + warp; e < out_rec; e += gridDim.x * WARPS) {
+        const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
+        if (lane == 0) {
+          if (e < rec) {
+            const int c = e / (d + 1), r = e % (d + 1);
+            if (r < d) sums[((int64_t)l * d + r) * k + c] += tot;
+            else counts[(int64_t)l * k + c] += tot;
+          } else if (simsum) {
+            simsum[l] += tot;
+          }
         }
       }
+      break;
     }
-    if (!whole_fit) break;
 
-    // ---- whole-fit mode: division, error and convergence test, identically in every block (compute_centroids'
-    // division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` kmeans.py:239) ----
+    // ---- whole-fit mode: ONE grid barrier per iteration.  Behind it every block folds ALL record entries of its batch
+    // entry itself (same warp_fold_contig over the same entry-major partials as the launch-per-iteration path, hence the
+    // same bits) into its own shared memory -- no folded totals travel through global memory and no second barrier
+    // separates "fold" from "use".  Then division, error and convergence test, identically in every block
+    // (compute_centroids' division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` :239).
     km_barrier(barrier_ctr + 2, nblocks, ++phase);
+    for (int e = warp; e < out_rec; e += WARPS) {
+      const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
+      if (lane == 0) blk[e] = tot;
+    }
+    __syncthreads();
     const bool sharded = fit.world > 1;
     const size_t slot = (size_t)gridDim.y * out_rec;
     if (sharded) {
-      // all of this rank's entries are in every peer's slot (system-scope fences above, grid barrier here): raise our
-      // flag on every rank, then wait until every rank's flag for this iteration is up in OUR buffer
+      // Row-sharded fit: block 0 of every batch entry stores this rank's folded record straight into every rank's
+      // exchange slot (its own included); one thread then fences at system scope and raises this rank's flag for the
+      // iteration on every peer; every block waits until all `world` flags are up in its OWN buffer.
       const unsigned stamp = fit.stamp_base + 1u + (unsigned)it;
+      if (blockIdx.x == 0) {
+        if (it == 0) {           // peers must have entered this call (they are done reading the previous call's slots)
+          if (tid == 0) xchg_wait_all(xchg_ready(fit.xchg[fit.rank]), fit.world, fit.stamp_base);
+          __syncthreads();
+        }
+        for (int e = tid; e < out_rec; e += THREADS) {
+          const double v = blk[e];
+          for (int p = 0; p < fit.world; ++p)
+            xchg_slot(fit.xchg[p], it & 1, fit.world, fit.rank, slot)[(size_t)l * out_rec + e] = v;
+        }
+        if (gridDim.y > 1) __threadfence_system();      // the flag is raised by another block: every writer fences
+      }
+      if (gridDim.y > 1) km_barrier(barrier_ctr + 2, nblocks, ++phase);     // all batch entries are stored
+      else __syncthreads();
       if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-        __threadfence_system();
+        __threadfence_system();                         // cumulative over the block's stores ordered by the barrier above
         for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_flag(fit.xchg[p], it & 1, fit.world) + fit.rank, stamp);
       }
       if (tid == 0) xchg_wait_all(xchg_flag(fit.xchg[fit.rank], it & 1, fit.world), fit.world, stamp);
       __syncthreads();
     }
-    const double* tl = fit.totals + (size_t)l * out_rec;
-    // folded total of record entry idx of this batch entry: local scratch, or the ranks' records added in rank order
+    // folded total of record entry idx of this batch entry: this block's fold, or the ranks' records added in rank order
     auto total_at = [&](int idx) -> double {
-      if (!sharded) return __ldcg(tl + idx);
+      if (!sharded) return blk[idx];
       double t = 0.0;
       for (int r = 0; r < fit.world; ++r)
         t += __ldcg(xchg_slot(fit.xchg[fit.rank], it & 1, fit.world, r, slot) + (size_t)l * out_rec + idx);
@@ -950,6 +979,24 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
                      KmLloyd{}, st);
 }
 
+int et_kmeans_assign_shard(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
+                           int64_t* labels, float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
+                           const int32_t* status, int64_t row_offset, int64_t n_global, et_stream_t stream) {
+  int rc = km_check(l, d, n, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(row_offset >= 0 && n_global >= row_offset + n && km_check(l, d, n_global, k_clusters) == ET_OK, ET_ERR_BADARG,
+             "et_kmeans_assign_shard: columns [%lld, %lld) outside a data set of %lld", (long long)row_offset,
+             (long long)(row_offset + n), (long long)n_global);
+  if (n == 0) return ET_OK;
+  ET_REQUIRE(data && centroids, ET_ERR_BADARG, "et_kmeans_assign_shard: data / centroids null");
+  ET_REQUIRE(!sums || (counts && workspace), ET_ERR_BADARG, "et_kmeans_assign_shard: sums given without counts / workspace");
+  KmLloyd shard{};
+  shard.col_offset = row_offset;
+  shard.n_global = n_global;
+  return km_dispatch(data, centroids, l, d, n, k_clusters, labels, maxsims, sums, counts, simsum, workspace, status, nullptr,
+                     shard, as_stream(stream));
+}
+
 int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int max_iter,
                     double tol, float* centroids_out, int64_t* labels, double* err, int32_t* status, double* simsum_last,
                     void* workspace, et_stream_t stream) {
@@ -978,7 +1025,7 @@ size_t et_kmeans_exchange_bytes(int l, int d, int k_clusters, int world) {
 int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, int d, int64_t n_local, int k_clusters,
                             int max_iter, double tol, float* centroids_out, int64_t* labels, double* err, int32_t* status,
                             double* simsum_last, void* workspace, int rank, int world, void* const* exchange_peers,
-                            unsigned stamp_base, et_stream_t stream) {
+                            unsigned stamp_base, int64_t row_offset, int64_t n_global, et_stream_t stream) {
   int rc = km_check(l, d, n_local, k_clusters);
   if (rc) return rc;
   ET_REQUIRE(centroids && centroids_out && workspace && exchange_peers && (n_local == 0 || data), ET_ERR_BADARG,
@@ -999,6 +1046,13 @@ int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, in
   fit.world = world;
   fit.xchg = reinterpret_cast<unsigned char* const*>(exchange_peers);
   fit.stamp_base = stamp_base;
+  if (n_global > 0) {
+    ET_REQUIRE(row_offset >= 0 && n_global >= row_offset + n_local && km_check(l, d, n_global, k_clusters) == ET_OK, ET_ERR_BADARG,
+               "et_kmeans_lloyd_sharded: columns [%lld, %lld) outside a data set of %lld", (long long)row_offset,
+               (long long)(row_offset + n_local), (long long)n_global);
+    fit.col_offset = row_offset;
+    fit.n_global = n_global;
+  }
   // an empty shard still takes part in every exchange: give the kernel a valid (never dereferenced) data pointer
   return km_dispatch(data ? data : centroids, centroids, l, d, n_local, k_clusters, nullptr, nullptr, nullptr, nullptr, nullptr,
                      workspace, nullptr, nullptr, fit, as_stream(stream));

@@ -720,8 +720,12 @@ class KMeansWorkspace:
         self.status.zero_()
 
 
-def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None, simsum=None, status=None):
-    """get_labels (+ optional accumulation for compute_centroids).  data (l,d,N), centroids (l,d,K) on the GPU."""
+def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None, simsum=None, status=None, row_offset=0,
+                  n_global=0):
+    """get_labels (+ optional accumulation for compute_centroids).  data (l,d,N), centroids (l,d,K) on the GPU.
+
+    ``n_global`` > 0: ``data`` is the row shard [row_offset, row_offset + N) of a data set with ``n_global`` columns
+    (same bits as the unsharded call would give for these columns)."""
     l, d, n = data.shape
     k = centroids.size(-1)
     labels = torch.empty((l, n), dtype=torch.int64, device=data.device) if want_labels else None
@@ -729,8 +733,13 @@ def kmeans_assign(data, centroids, want_labels=True, want_maxsims=True, acc=None
     sums = counts = ws = None
     if acc is not None:
         sums, counts, ws = acc.sums, acc.counts, acc.ws
-    check(load().et_kmeans_assign(ptr(data), ptr(centroids), l, d, n, k, ptr(labels), ptr(maxsims), ptr(sums), ptr(counts),
-                                  ptr(simsum), ptr(ws), ptr(status), stream_of(data.device)), "et_kmeans_assign")
+    if n_global:
+        check(load().et_kmeans_assign_shard(ptr(data), ptr(centroids), l, d, n, k, ptr(labels), ptr(maxsims), ptr(sums),
+                                            ptr(counts), ptr(simsum), ptr(ws), ptr(status), int(row_offset), int(n_global),
+                                            stream_of(data.device)), "et_kmeans_assign_shard")
+    else:
+        check(load().et_kmeans_assign(ptr(data), ptr(centroids), l, d, n, k, ptr(labels), ptr(maxsims), ptr(sums), ptr(counts),
+                                      ptr(simsum), ptr(ws), ptr(status), stream_of(data.device)), "et_kmeans_assign")
     return maxsims, labels
 
 
@@ -753,7 +762,8 @@ def kmeans_lloyd(data, centroids, acc, max_iter, tol, want_labels=True):
     return labels, out
 
 
-def kmeans_lloyd_sharded(data, centroids, acc, max_iter, tol, rank, world, peers, stamp_base, want_labels=True):
+def kmeans_lloyd_sharded(data, centroids, acc, max_iter, tol, rank, world, peers, stamp_base, want_labels=True, row_offset=0,
+                         n_global=0):
     """Row-sharded whole-fit kernel with the per-iteration exchange over peer memory (see et_kmeans_lloyd_sharded).
 
     ``peers``: int64 device tensor (world,) of exchange-buffer addresses as mapped in this process."""
@@ -764,7 +774,8 @@ def kmeans_lloyd_sharded(data, centroids, acc, max_iter, tol, rank, world, peers
     check(load().et_kmeans_lloyd_sharded(ptr(data) if n > 0 else None, ptr(centroids), l, d, n, k, int(max_iter), float(tol),
                                          ptr(out), ptr(labels) if n > 0 else None, ptr(acc.err), ptr(acc.status),
                                          ptr(acc.simsum_last), ptr(acc.ws), int(rank), int(world), ptr(peers),
-                                         int(stamp_base) & 0xFFFFFFFF, stream_of(centroids.device)), "et_kmeans_lloyd_sharded")
+                                         int(stamp_base) & 0xFFFFFFFF, int(row_offset), int(n_global),
+                                         stream_of(centroids.device)), "et_kmeans_lloyd_sharded")
     return labels, out
 
 

@@ -41,14 +41,15 @@ class CudaBackend:
     def new_workspace(self, l, d, k, device):
         return ops.KMeansWorkspace(l, d, k, device)
 
-    def assign_accumulate(self, data, cent, acc):
-        ops.kmeans_assign(data, cent, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum, status=acc.status)
+    def assign_accumulate(self, data, cent, acc, row_offset=0, n_global=0):
+        ops.kmeans_assign(data, cent, want_labels=False, want_maxsims=False, acc=acc, simsum=acc.simsum, status=acc.status,
+                          row_offset=row_offset, n_global=n_global)
 
     def finalize(self, acc, old, new, tol):
         ops.kmeans_finalize(acc, old, new, tol=tol, use_status=True)
 
-    def labels(self, data, cent):
-        return ops.kmeans_assign(data, cent, want_labels=True, want_maxsims=False)[1]
+    def labels(self, data, cent, row_offset=0, n_global=0):
+        return ops.kmeans_assign(data, cent, want_labels=True, want_maxsims=False, row_offset=row_offset, n_global=n_global)[1]
 
     def seed_candidate(self, data, cent, ncols, row_offset, out=None):
         return ops.kmeans_seed_candidate(data, cent, ncols, row_offset, out=out)
@@ -196,17 +197,19 @@ def peer_exchange_available(device, group=None):
     return True
 
 
-def sharded_kmeans_fit_fused(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, group=None):
+def sharded_kmeans_fit_fused(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, group=None, row_offset=None):
     """``sharded_kmeans_fit`` with the whole Lloyd loop AND its per-iteration all-reduce inside one persistent kernel per
     rank (``et_kmeans_lloyd_sharded``): the ranks exchange their folded records through peer memory, no NCCL call and
     no host round trip per iteration.  Same return values; centroids and iteration count are identical on all ranks by
-    construction (every rank adds the same records in rank order)."""
+    construction (every rank adds the same records in rank order).  ``row_offset`` (global index of this shard's first
+    column): when given, labels are the same bits as a fit of the unsharded (l, d, n_total) tensor would assign."""
     l, d, n_local = data_shard.shape
     dev = centroids.device
     ex = PeerExchange.get(l, d, n_clusters, dev, group)
     acc = ops.KMeansWorkspace(l, d, n_clusters, dev)
     labels, final = ops.kmeans_lloyd_sharded(data_shard, centroids.contiguous(), acc, max_iter, tol, ex.rank, ex.world,
-                                             ex.peers, ex.next_stamp(max_iter))
+                                             ex.peers, ex.next_stamp(max_iter), row_offset=row_offset or 0,
+                                             n_global=n_total if row_offset is not None else 0)
     _, n_iter = (int(v) for v in acc.status.tolist())
     if labels is None:
         labels = torch.zeros((l, 0), dtype=torch.int64, device=dev)
@@ -215,13 +218,16 @@ def sharded_kmeans_fit_fused(data_shard, n_clusters, n_total, centroids, max_ite
 
 
 def sharded_kmeans_fit(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, sync_every=8, group=None,
-                       backend=None):
+                       backend=None, row_offset=None):
     """Lloyd iterations (kmeans.py:200-259, n_redo = 1) over row shards: per iteration one fused
     assign+accumulate pass on local rows and ONE all-reduce of the packed (sums, counts, sum of similarities).
 
     Returns (labels of the local rows (l,n_local) int64, centroids (l,d,K) -- identical on all ranks --,
-    iterations executed, inertia)."""
+    iterations executed, inertia).  ``row_offset`` (global index of this shard's first column): when given, the
+    assignment arithmetic follows the global column numbering, i.e. the labels are the same bits as a fit of the
+    unsharded (l, d, n_total) tensor would assign."""
     backend = backend or CudaBackend()
+    where = {} if row_offset is None else {"row_offset": int(row_offset), "n_global": int(n_total)}
     l, d, n_local = data_shard.shape
     dev = data_shard.device
     acc = backend.new_workspace(l, d, n_clusters, dev)
@@ -232,7 +238,7 @@ def sharded_kmeans_fit(data_shard, n_clusters, n_total, centroids, max_iter=100,
         chunk = min(sync_every, max_iter - done)
         for j in range(done, done + chunk):
             cur, nxt = bufs[j % 2], bufs[(j + 1) % 2]
-            backend.assign_accumulate(data_shard, cur, acc)
+            backend.assign_accumulate(data_shard, cur, acc, **where)
             _all_reduce(acc.flat, group)            # sums | counts | sum of similarities: one in-place collective
             backend.finalize(acc, cur, nxt, tol)
         done += chunk
@@ -240,7 +246,7 @@ def sharded_kmeans_fit(data_shard, n_clusters, n_total, centroids, max_iter=100,
         if converged:
             break
     final, before = bufs[n_iter % 2], bufs[(n_iter - 1) % 2]
-    labels = backend.labels(data_shard, before) if n_local > 0 else torch.zeros((l, 0), dtype=torch.int64, device=dev)
+    labels = backend.labels(data_shard, before, **where) if n_local > 0 else torch.zeros((l, 0), dtype=torch.int64, device=dev)
     inertia = float(-(acc.simsum_last / n_total).mean())
     return labels, final.clone(), n_iter, inertia
 

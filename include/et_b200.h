@@ -218,6 +218,14 @@ int et_kmeans_assign(const float* data, const float* centroids, int l, int d, in
                      int k_clusters, int64_t* labels, float* maxsims, double* sums,
                      double* counts, double* simsum, void* workspace, const int32_t* status,
                      et_stream_t stream);
+/* et_kmeans_assign on a ROW SHARD: data (l,d,n) holds the global columns [row_offset, row_offset + n) of a data set
+ * with n_global columns.  The |a|^2 summation order of a column follows its GLOBAL index and the GLOBAL column count,
+ * so labels and similarities are the same bits as et_kmeans_assign on the unsharded tensor would give for these
+ * columns.  n_global < 2^32 - 2^21. */
+int et_kmeans_assign_shard(const float* data, const float* centroids, int l, int d, int64_t n,
+                           int k_clusters, int64_t* labels, float* maxsims, double* sums,
+                           double* counts, double* simsum, void* workspace, const int32_t* status,
+                           int64_t row_offset, int64_t n_global, et_stream_t stream);
 /* The whole Lloyd loop of BatchKMeans.fit (kmeans.py:226-239) in ONE persistent cooperative launch: up to max_iter
  * iterations of {get_labels, compute_centroids, calculate_error, `if error <= tol: break`} with the grid-wide sums
  * folded behind in-kernel grid barriers, no host round trip and no relaunch (the data stay L2 resident), then one
@@ -239,13 +247,15 @@ int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int
  * (et_kmeans_exchange_bytes() bytes each, zero-filled once before the first call, e.g. a torch symmetric-memory
  * allocation).  stamp_base: a number that grows by at least max_iter + 2 from one call to the next on the same
  * buffers (the same on every rank).  labels / simsum_last cover the local rows / the global sum.  world <= 16, l <= 32;
- * n_local may be 0.  A rank that never arrives traps the kernel after ~10 s instead of hanging it. */
+ * n_local may be 0.  row_offset / n_global: global index of this shard's first column and the global column count
+ * (as et_kmeans_assign_shard; n_global = 0: the shard is numbered on its own).  A rank that never arrives traps the
+ * kernel after ~10 s instead of hanging it. */
 size_t et_kmeans_exchange_bytes(int l, int d, int k_clusters, int world);
 int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, int d, int64_t n_local,
                             int k_clusters, int max_iter, double tol, float* centroids_out,
                             int64_t* labels, double* err, int32_t* status, double* simsum_last,
                             void* workspace, int rank, int world, void* const* exchange_peers,
-                            unsigned stamp_base, et_stream_t stream);
+                            unsigned stamp_base, int64_t row_offset, int64_t n_global, et_stream_t stream);
 /* Accumulation half of compute_centroids (kmeans.py:160-184) for caller-supplied labels
  * (l,N) int64; labels outside [0,K) are ignored.  sums / counts / workspace as above. */
 int et_kmeans_accumulate(const float* data, const int64_t* labels, int l, int d, int64_t n,

@@ -1,4 +1,4 @@
-"""GPU: the row-sharded paths with the CUDA backend, world_size = 2.  With two or more GPUs the ranks use NCCL on
+"""GPU: the row-sharded paths with the CUDA backend, world_size = 2 (and 4, 8 when the box has that many GPUs).  With two or more GPUs the ranks use NCCL on
 separate devices; on a single-GPU box both ranks share cuda:0 and the collectives go through gloo (CUDA tensors),
 which still exercises every kernel and the whole sharded control flow."""
 import os
@@ -41,21 +41,32 @@ def _worker(rank, world, port, use_nccl, out):
         cent0 = P.sharded_farthest_init(C[:, :, a:b].contiguous(), 20, first, a)
         ref0 = ops.kmeans_farthest_init(C, 20, first)
         res["init_equal"] = bool(torch.equal(cent0, ref0))
-        labels, cent, n_iter, inertia = P.sharded_kmeans_fit(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25)
+        labels, cent, n_iter, inertia = P.sharded_kmeans_fit(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25, row_offset=a)
         km = et.BatchKMeans(n_clusters=20, max_iter=25)
         ref_labels = km.fit(C, centroids=ref0)
         res["label_mismatch"] = int((labels != ref_labels[:, a:b]).sum())
         res["cent_err"] = float((cent - km.centroids).abs().max() / km.centroids.abs().max())
         res["iters"] = (n_iter, km.n_iter_)
         res["cent"] = cent.cpu()
-        # the same fit with the all-reduce fused into the persistent kernel (peer memory; needs NCCL + one GPU per rank)
+        # the reference loop (oracle) on the FULL data from the same seeds: the sharded fits must reproduce it
+        o_lab, o_cent, o_it, _ = O.kmeans_fit(C.cpu(), 20, centroids=ref0.cpu().clone(), max_iter=25)
+        res["nccl_vs_oracle"] = (int((labels.cpu() != o_lab[:, a:b]).sum()), float((cent.cpu() - o_cent).abs().max() / o_cent.abs().max()))
+        # the same fit with the all-reduce fused into the persistent kernel (peer memory; needs NCCL + one GPU per rank),
+        # compared with the ORACLE and, bit for bit, with the NCCL path
         if use_nccl and P.peer_exchange_available(dev):
             for rep in range(2):                                 # twice: the exchange buffers and stamps are reused
-                fl, fc, fi, fin = P.sharded_kmeans_fit_fused(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25)
+                fl, fc, fi, fin = P.sharded_kmeans_fit_fused(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=25, row_offset=a)
             res["fused_equal"] = bool(torch.equal(fl, labels) and torch.equal(fc, cent) and fi == n_iter
                                       and abs(fin - inertia) <= 1e-12 * abs(inertia))
+            res["fused_vs_oracle"] = (int((fl.cpu() != o_lab[:, a:b]).sum()), float((fc.cpu() - o_cent).abs().max() / o_cent.abs().max()),
+                                      fi, o_it)
+            # lock-step: the labels of the fused fit ARE the oracle's assignment against the centroids one update earlier
+            _, before, _, _ = P.sharded_kmeans_fit_fused(C[:, :, a:b].contiguous(), 20, n, cent0, max_iter=fi - 1, tol=-1.0,
+                                                         row_offset=a) if fi > 1 else (None, cent0, None, None)
+            _, lock = O.kmeans_assign(C.cpu(), before.cpu())          # the reference's assignment of the UNSHARDED tensor
+            res["fused_lockstep_mismatch"] = int((fl.cpu() != lock[:, a:b]).sum())
         else:
-            res["fused_equal"] = None
+            res["fused_equal"] = res["fused_vs_oracle"] = res["fused_lockstep_mismatch"] = None
         # sharded metric mean
         rec = ops.reconstruct(torch.zeros(6, b - a, 20, device=dev), Up, ops.norm_params(obs[a:b].to(dev)))
         ade, fde = ops.ade_fde(rec, pred[a:b].to(dev))
@@ -68,21 +79,34 @@ def _worker(rank, world, port, use_nccl, out):
         dist.destroy_process_group()
 
 
-def test_sharded_basis_kmeans_metrics_world2():
+WORLDS = [w for w in (2, 4, 8) if w == 2 or torch.cuda.device_count() >= w]
+
+
+@pytest.mark.parametrize("world", WORLDS)
+def test_sharded_basis_kmeans_metrics(world):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    use_nccl = torch.cuda.device_count() >= 2
+    use_nccl = torch.cuda.device_count() >= world
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, use_nccl, out), nprocs=2, join=True)
-    r0, r1 = out[0], out[1]
-    for r in (r0, r1):
+    mp.spawn(_worker, args=(world, port, use_nccl, out), nprocs=world, join=True)
+    rs = [out[r] for r in range(world)]
+    for r in rs:
         assert r["S_err"] < 1e-6 and r["P_err"] < 1e-6
         assert r["init_equal"]
         assert r["label_mismatch"] <= 4 and r["cent_err"] < 1e-4
         assert r["iters"][0] == r["iters"][1]
+        # against the reference loop: the reference's fp32 centroid sums let a near tie resolve differently now and then
+        assert r["nccl_vs_oracle"][0] <= 8 and r["nccl_vs_oracle"][1] < 1e-4, r["nccl_vs_oracle"]
         assert r["fused_equal"] in (None, True)
-    assert torch.equal(r0["U_pred"], r1["U_pred"]) and torch.equal(r0["cent"], r1["cent"])
-    assert abs(r0["ade_mean"] - r1["ade_mean"]) < 1e-12
-    assert abs(r0["ade_mean"] - r0["ade_mean_ref"]) < 1e-6 * abs(r0["ade_mean_ref"])
+        if r["fused_vs_oracle"] is not None:
+            mism, cerr, it_f, it_o = r["fused_vs_oracle"]
+            assert mism <= 8 and cerr < 1e-4 and it_f == it_o, r["fused_vs_oracle"]
+            assert r["fused_lockstep_mismatch"] == 0
+    if use_nccl:
+        assert all(r["fused_equal"] is True for r in rs), "the fused peer-memory fit did not run on a multi-GPU box"
+    for r in rs[1:]:
+        assert torch.equal(rs[0]["U_pred"], r["U_pred"]) and torch.equal(rs[0]["cent"], r["cent"])
+        assert abs(rs[0]["ade_mean"] - r["ade_mean"]) < 1e-12
+    assert abs(rs[0]["ade_mean"] - rs[0]["ade_mean_ref"]) < 1e-6 * abs(rs[0]["ade_mean_ref"])
