@@ -28,7 +28,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/et_b200.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -cudart static -o $@ $(OBJS)
+	$(NVCC) -shared -cudart static -o $@ $(OBJS) -ldl
 
 clean:
 	rm -rf $(OBJDIR) $(LIB) oracle/_build oracle/_ref

@@ -280,7 +280,14 @@ def run_stages(et, dist, dev, rank, world, n_rows, reps):
     st = {"rows_per_gpu": n_rows, "rows_total": n_total, "kmeans": "d=6, K=20 on the C_pred coefficients of the rows"}
     st["basis_ms"] = timed(lambda: P.sharded_basis(obs, pred, K_RANK), reps)
     st["gram_pass_ms"] = timed(lambda: ops.gram(obs, pred, True, True, True), reps)
-    st["seed_ms"] = timed(lambda: P.sharded_farthest_init(C, 20, first, a), 3)
+    st["seed_ms"] = timed(lambda: P.sharded_farthest_init(C, 20, first, a), 3)                 # two small all-reduces per step
+    if fused_ok:
+        seeded = P.sharded_farthest_init_fused(C, 20, first, a, n_total)
+        assert torch.equal(seeded, cent0), "fused sharded seeding differs from the all-reduce form"
+        st["seed_fused_ms"] = timed(lambda: P.sharded_farthest_init_fused(C, 20, first, a, n_total), 5)
+    elif world == 1:
+        assert torch.equal(ops.kmeans_farthest_init(C, 20, first), cent0), "persistent seeding differs from the per-step form"
+        st["seed_fused_ms"] = timed(lambda: ops.kmeans_farthest_init(C, 20, first), 5)
     acc = ops.KMeansWorkspace(1, 6, 20, dev)
     nxt = torch.empty_like(cent0)
 

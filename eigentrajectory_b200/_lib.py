@@ -57,9 +57,16 @@ PROTOTYPES = {
     "et_kmeans_accumulate": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p]),
     "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _p]),
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),
+    "et_kmeans_farthest_init_sharded": (_i, [_p, _i, _i, _l, _i, _l, _l, _l, _p, _p, _i, _i, _p, C.c_uint, _p]),
     "et_kmeans_seed_step": (_i, [_p, _p, _i, _i, _l, _i, _i, _p, _p]),
     "et_kmeans_seed_candidate": (_i, [_p, _p, _i, _i, _l, _i, _i, _l, _p, _p]),
     "et_kmeans_seed_fetch": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
+    "et_comm_unique_id": (_i, [_p]),
+    "et_comm_init": (_i, [_i, _i, _p, _p]),
+    "et_comm_rank": (_i, [_p, _p, _p]),
+    "et_allreduce_f64": (_i, [_p, _sz, _p, _p]),
+    "et_allreduce_min_i64": (_i, [_p, _sz, _p, _p]),
+    "et_comm_destroy": (_i, [_p]),
     "et_ade_fde": (_i, [_p, _p, _i, _l, _i, _p, _p, _p, _p, _p]),
     "et_col": (_i, [_p, _i, _l, _i, C.c_float, _p, _p]),
     "et_dataset_parse_host": (_i, [C.c_char_p, _sz, C.c_char, _p, _l, _p]),

@@ -238,6 +238,49 @@ __device__ __forceinline__ double warp_fold_contig(const double* v, int n_part, 
   return s;
 }
 
+// NE entries at once (entry e of the group starts at v + e * stride): all NE * ceil(n_part / 32) loads of a lane are in
+// flight together and the NE shuffle trees interleave, so a warp that has to fold many entries pays about one L2 round
+// trip per group instead of one per entry.  Per entry the additions are exactly those of warp_fold_contig (same bits).
+template <int NE>
+__device__ __forceinline__ void warp_fold_contig_multi(const double* v, size_t stride, int n_valid, int n_part, int lane,
+                                                       double (&out)[NE]) {
+  double s0[NE], s1[NE], s2[NE], s3[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) s0[e] = s1[e] = s2[e] = s3[e] = 0.0;
+  int p = lane;
+  for (; p + 96 < n_part; p += 128) {
+    double v0[NE], v1[NE], v2[NE], v3[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      const double* ve = v + (size_t)(e < n_valid ? e : 0) * stride;
+      v0[e] = __ldcg(ve + p);
+      v1[e] = __ldcg(ve + p + 32);
+      v2[e] = __ldcg(ve + p + 64);
+      v3[e] = __ldcg(ve + p + 96);
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { s0[e] += v0[e]; s1[e] += v1[e]; s2[e] += v2[e]; s3[e] += v3[e]; }
+  }
+  double t0[NE], t1[NE], t2[NE];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    const double* ve = v + (size_t)(e < n_valid ? e : 0) * stride;
+    t0[e] = p < n_part ? __ldcg(ve + p) : 0.0;
+    t1[e] = p + 32 < n_part ? __ldcg(ve + p + 32) : 0.0;
+    t2[e] = p + 64 < n_part ? __ldcg(ve + p + 64) : 0.0;
+  }
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    s0[e] += t0[e]; s1[e] += t1[e]; s2[e] += t2[e];
+    out[e] = (s0[e] + s1[e]) + (s2[e] + s3[e]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int e = 0; e < NE; ++e) out[e] += __shfl_xor_sync(0xffffffffu, out[e], o);
+  }
+}
+
 // Cooperative launch wrapper (guarantees co-residency or fails loudly).
 template <typename... Args>
 inline cudaError_t launch_cooperative(void (*kernel)(Args...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

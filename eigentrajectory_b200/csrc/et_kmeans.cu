@@ -118,7 +118,7 @@ __device__ __forceinline__ void best_centroid_neg(const float (&a)[DMAX], int d,
 // rounding sequence (x - y == x + (-y) bit for bit; the centroid norms are staged negated in nbn).
 // KPAD > 0: the padded cluster count is known at compile time and the scan is fully unrolled (shared-memory operands
 // become immediate offsets); KPAD == 0: run-time kpad.  LABELS = false keeps only the best similarity (seeding).
-template <int DMAX, bool EXACT, int PPL, int KPAD, bool LABELS>
+template <int DMAX, bool EXACT, int PPL, int KPAD, bool LABELS, bool TOURN = false>
 __device__ __forceinline__ void best_centroid_packed(const float (&a)[PPL][DMAX], int d, const float (&anorm)[PPL],
                                                      const float* cs, int kpitch, const float* nbn, int kpad_rt,
                                                      float (&best)[PPL], int (&label)[PPL]) {
@@ -155,7 +155,14 @@ __device__ __forceinline__ void best_centroid_packed(const float (&a)[PPL][DMAX]
       float y0, y1, y2, y3;
       unpack2(add2(add2(mul2(dot[u][0], two), nan2[u]), nb4.x), y0, y1);
       unpack2(add2(add2(mul2(dot[u][1], two), nan2[u]), nb4.y), y2, y3);
-      if (LABELS) {
+      if (LABELS && !TOURN) {             // plain ascending scan
+        if (y0 > best[u]) { best[u] = y0; label[u] = j0; }
+        if (y1 > best[u]) { best[u] = y1; label[u] = j0 + 1; }
+        if (y2 > best[u]) { best[u] = y2; label[u] = j0 + 2; }
+        if (y3 > best[u]) { best[u] = y3; label[u] = j0 + 3; }
+      } else if (LABELS) {
+        // (measured on B200: 21.75 us per iteration against 21.5 us for the plain scan above -- the kernel is bound by
+        // issue slots and the FMA pipe, not by this dependency chain; kept as an A/B switch, ET_TUNE_KM_TOURNAMENT)
         // arg-max of the group as a two-level tournament (a later column wins only if strictly greater, so ties keep
         // the lowest index exactly like the ascending scan), then ONE dependent compare/select against the running
         // best: the serial chain through `best` is K/4 steps long instead of K
@@ -274,7 +281,10 @@ __device__ __forceinline__ void km_barrier_exit(unsigned* ctr, unsigned nblocks)
 // folds its 32 lane records (fp32 row sums, then fp64: see flush below) in a fixed order, so totals are reproducible
 // and fp32 never carries more than 32 * KM_FLUSH_EVERY points.  KPAD: compile-time padded cluster count of the packed
 // scan (0 = run time).
-template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
+// SHARE: lanes per record slot.  1: every lane owns a private record (LANES = 32 columns per row).  2: lanes i and i + 16
+// share a column and update it in two half-warp phases -- half the shared memory per warp, which is what lets 16 warps
+// (instead of 12) live on an SM with the reference shape's 140-float records.
+template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD, bool TOURN = false, int SHARE = 1>
 __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_kernel(
     const float* __restrict__ data, const float* __restrict__ centroids, int d, int64_t n, int k,
     int64_t* __restrict__ labels, float* __restrict__ maxsims, double* __restrict__ sums, double* __restrict__ counts,
@@ -285,6 +295,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   constexpr int NJP = (KMAX * (DMAX / 2) + 31) / 32;        // record rows per lane: coordinate pairs ...
   constexpr int NJS = (KMAX * 2 + 31) / 32;                 // ... and singles (odd coordinate, count)
   constexpr int THREADS = WARPS * 32;
+  constexpr int LANES = 32 / SHARE;                         // record columns per row
   extern __shared__ __align__(16) unsigned char km_smem[];
   float* cs = reinterpret_cast<float*>(km_smem);            // [DMAX][KMAX]
   float* bn = cs + DMAX * KMAX;                             // [KMAX]   |b_j|^2
@@ -295,7 +306,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   if (EXACT) d = DMAX;                                      // lets the record layout below fold to constants
   const int rec = k * (d + 1);
   // (blk is padded to an even number of doubles: the records below are read with 128-bit accesses)
-  float* lanerec = reinterpret_cast<float*>(blk + ((RECMAX + 2) & ~1)) + (size_t)warp * rec * 32;   // rec * 32 floats
+  float* lanerec = reinterpret_cast<float*>(blk + ((RECMAX + 2) & ~1)) + (size_t)warp * rec * LANES;   // rec * LANES floats
   const bool whole_fit = fit.cent_out != nullptr;
   const bool accumulate = sums != nullptr || whole_fit;
   if (whole_fit && fit.world > 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_ready(fit.xchg[p]) + fit.rank, fit.stamp_base);
   }
   const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
-  float* lanesingle = lanerec + (size_t)k * npair * 64;
+  float* lanesingle = lanerec + (size_t)k * npair * 2 * LANES;
   __shared__ int nan_centroid;
   __shared__ double red_s[WARPS];
 
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   if (centroids)
     for (int e = tid; e < d * k; e += THREADS) cs[(e / k) * KMAX + (e % k)] = __ldg(centroids + (int64_t)l * d * k + e);
   if (accumulate)
-    for (int e = lane; e < rec * 32; e += 32) lanerec[e] = 0.f;
+    for (int e = lane; e < rec * LANES; e += 32) lanerec[e] = 0.f;
   const int kpad = (k + 3) & ~3;
   const float* dl = data + (int64_t)l * d * n;
   const int out_rec = rec + 1;
@@ -335,12 +346,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     for (int j = 0; j < NJP; ++j) {
       const int rho = lane + 32 * j;
       if (rho < k * npair) {
-        ulonglong2* row = reinterpret_cast<ulonglong2*>(lanerec + rho * 64);
+        ulonglong2* row = reinterpret_cast<ulonglong2*>(lanerec + rho * 2 * LANES);
         f32x2_t sa = pack2(0.f, 0.f), sb = sa;
         const ulonglong2 z = make_ulonglong2(0ull, 0ull);
 #pragma unroll
-        for (int st = 0; st < 16; ++st) {
-          const int cp = (st + lane) & 15;
+        for (int st = 0; st < LANES / 2; ++st) {
+          const int cp = (st + lane) & (LANES / 2 - 1);
           const ulonglong2 v = row[cp];
           row[cp] = z;
           sa = add2(sa, v.x);
@@ -356,11 +367,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     for (int j = 0; j < NJS; ++j) {
       const int sg = lane + 32 * j;
       if (sg < k * nsingle) {
-        float4* row = reinterpret_cast<float4*>(lanesingle + sg * 32);
+        float4* row = reinterpret_cast<float4*>(lanesingle + sg * LANES);
         float sa = 0.f, sb = 0.f;
 #pragma unroll
-        for (int st = 0; st < 8; ++st) {
-          const int cp = (st + lane) & 7;
+        for (int st = 0; st < LANES / 4; ++st) {
+          const int cp = (st + lane) & (LANES / 4 - 1);
           const float4 v = row[cp];
           row[cp] = make_float4(0.f, 0.f, 0.f, 0.f);
           sa += v.x + v.y;
@@ -464,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
           finite = finite && (fabsf(anorm[u]) <= KM_FAST_NORM_MAX);   // finite (and not huge) iff every coordinate is
         }
         if (finite) {
-          best_centroid_packed<DMAX, EXACT, PPL, KPAD, true>(a, d, anorm, cs, KMAX, nbn, kpad, best, label);
+          best_centroid_packed<DMAX, EXACT, PPL, KPAD, true, TOURN>(a, d, anorm, cs, KMAX, nbn, kpad, best, label);
         } else {
 #pragma unroll
           for (int u = 0; u < PPL; ++u)
@@ -473,27 +484,36 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
       }
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
-        if (idx[u] < n32) {
+        const bool live = idx[u] < n32;
+        if (live) {
           if (lab_out) lab_out[idx[u]] = label[u];
           if (sim_out) sim_out[idx[u]] = best[u];
-          if (acc_pass && label[u] >= 0) {
-            f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * 32 + lane;
+        }
+        if (acc_pass) {                                   // (warp-uniform)
+          const bool upd = live && label[u] >= 0;
 #pragma unroll
-            for (int p2 = 0; p2 < DMAX / 2; ++p2)
-              if (EXACT || p2 < npair) pslot[p2 * 32] = add2(pslot[p2 * 32], pack2(a[u][2 * p2], a[u][2 * p2 + 1]));
-            float* sslot = lanesingle + (label[u] * nsingle) * 32 + lane;
-            if (d & 1) {
-              float last = 0.f;
+          for (int h = 0; h < SHARE; ++h) {               // SHARE == 2: the half-warps take turns on the shared columns
+            if (upd && (SHARE == 1 || (lane >> 4) == h)) {
+              const int col = lane & (LANES - 1);
+              f32x2_t* pslot = reinterpret_cast<f32x2_t*>(lanerec) + (label[u] * npair) * LANES + col;
 #pragma unroll
-              for (int r = 0; r < DMAX; ++r)
-                if (r == d - 1) last = a[u][r];
-              sslot[0] += last;
-              sslot[32] += 1.0f;
-            } else {
-              sslot[0] += 1.0f;
+              for (int p2 = 0; p2 < DMAX / 2; ++p2)
+                if (EXACT || p2 < npair) pslot[p2 * LANES] = add2(pslot[p2 * LANES], pack2(a[u][2 * p2], a[u][2 * p2 + 1]));
+              float* sslot = lanesingle + (label[u] * nsingle) * LANES + col;
+              if (d & 1) {
+                float last = 0.f;
+#pragma unroll
+                for (int r = 0; r < DMAX; ++r)
+                  if (r == d - 1) last = a[u][r];
+                sslot[0] += last;
+                sslot[LANES] += 1.0f;
+              } else {
+                sslot[0] += 1.0f;
+              }
             }
-            sim32 += best[u];
+            if (SHARE > 1) __syncwarp();
           }
+          if (upd) sim32 += best[u];
         }
       }
       if (acc_pass && (since_flush += PPL) >= KM_FLUSH_EVERY) {
@@ -504,34 +524,44 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     if (!acc_pass) break;
     flush();
 
-    // ---- block reduction in fixed warp order ----
-    for (int e = tid; e <= rec; e += THREADS) blk[e] = 0.0;
+    // ---- block reduction in fixed warp order: every warp parks its folded record in its own (now all-zero) lane-record
+    // area, one barrier, then thread e adds entry e over the warps in ascending order (the same sums, bit for bit, as
+    // letting the warps add into blk[] one after the other -- without the WARPS serial rounds) ----
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sim_acc += __shfl_xor_sync(0xffffffffu, sim_acc, o);
-    __syncthreads();
-    for (int w = 0; w < WARPS; ++w) {
-      if (warp == w) {
+    {
+      double* wst = reinterpret_cast<double*>(lanerec);
 #pragma unroll
-        for (int j = 0; j < NJP; ++j) {
-          const int rho = lane + 32 * j;
-          if (rho < k * npair) {
-            const int c = rho / npair, e = c * (d + 1) + 2 * (rho - c * npair);
-            blk[e] += accp[j][0];
-            blk[e + 1] += accp[j][1];
-          }
+      for (int j = 0; j < NJP; ++j) {
+        const int rho = lane + 32 * j;
+        if (rho < k * npair) {
+          const int c = rho / npair, e = c * (d + 1) + 2 * (rho - c * npair);
+          wst[e] = accp[j][0];
+          wst[e + 1] = accp[j][1];
         }
-#pragma unroll
-        for (int j = 0; j < NJS; ++j) {
-          const int sg = lane + 32 * j;
-          if (sg < k * nsingle) {
-            const int c = sg / nsingle;
-            blk[c * (d + 1) + 2 * npair + (sg - c * nsingle)] += accs[j];
-          }
-        }
-        if (lane == 0) blk[rec] += sim_acc;
       }
-      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < NJS; ++j) {
+        const int sg = lane + 32 * j;
+        if (sg < k * nsingle) {
+          const int c = sg / nsingle;
+          wst[c * (d + 1) + 2 * npair + (sg - c * nsingle)] = accs[j];
+        }
+      }
+      if (lane == 0) wst[rec] = sim_acc;
     }
+    __syncthreads();
+    {
+      const double* st0 = reinterpret_cast<const double*>(lanerec - (size_t)warp * rec * LANES);   // warp 0's area
+      for (int e = tid; e <= rec; e += THREADS) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) sum += st0[(size_t)w * rec * (LANES / 2) + e];
+        blk[e] = sum;
+      }
+    }
+    __syncthreads();
+    for (int e = lane; e < 2 * (rec + 1); e += 32) lanerec[e] = 0.f;        // the staging words are lane records again
     // partial records are stored entry-major ([l][entry][block]) so that the fold below reads contiguous doubles
     double* lpart = partials + (size_t)l * gridDim.x * out_rec;
     for (int e = tid; e < out_rec; e += THREADS) lpart[(size_t)e * gridDim.x + blockIdx.x] = blk[e];
@@ -559,9 +589,20 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     // separates "fold" from "use".  Then division, error and convergence test, identically in every block
     // (compute_centroids' division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` :239).
     km_barrier(barrier_ctr + 2, nblocks, ++phase);
-    for (int e = warp; e < out_rec; e += WARPS) {
-      const double tot = warp_fold_contig(lpart + (size_t)e * gridDim.x, (int)gridDim.x, lane);
-      if (lane == 0) blk[e] = tot;
+    {
+      constexpr int NE = 8;                       // entries folded together (their loads overlap)
+      const int per_warp = (out_rec + WARPS - 1) / WARPS;
+      const int e_lo = warp * per_warp, e_hi = e_lo + per_warp < out_rec ? e_lo + per_warp : out_rec;
+      for (int e = e_lo; e < e_hi; e += NE) {
+        double tot[NE];
+        const int valid = e_hi - e < NE ? e_hi - e : NE;
+        warp_fold_contig_multi<NE>(lpart + (size_t)e * gridDim.x, gridDim.x, valid, (int)gridDim.x, lane, tot);
+        if (lane == 0) {
+#pragma unroll
+          for (int u = 0; u < NE; ++u)
+            if (u < valid) blk[e + u] = tot[u];
+        }
+      }
     }
     __syncthreads();
     const bool sharded = fit.world > 1;
@@ -645,9 +686,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
 }
 
 template <int DMAX, int KMAX>
-static size_t km_smem_bytes(int d, int k, int warps, bool accumulate) {
+static size_t km_smem_bytes(int d, int k, int warps, bool accumulate, int share = 1) {
   return (size_t)(2 * DMAX * KMAX + 2 * KMAX) * sizeof(float) + (size_t)((KMAX * (DMAX + 1) + 2) & ~1) * sizeof(double) +
-         (accumulate ? (size_t)warps * k * (d + 1) * 32 * sizeof(float) : 0);
+         (accumulate ? (size_t)warps * k * (d + 1) * (32 / share) * sizeof(float) : 0);
 }
 
 // new = float(sums / counts); err = sum (old - new)^2; clears the accumulators for the next iteration.
@@ -699,9 +740,13 @@ __device__ __forceinline__ unsigned long long pack_min_key(float v, int64_t idx)
   return ((unsigned long long)u << 32) | (unsigned long long)(uint32_t)idx;
 }
 
+// scratch = l*K candidate keys (column 0 = the caller's first index, the others "none yet") followed by 16 words for the
+// barrier counters of the persistent kernel, zeroed here on every call (a kernel that died half way cannot poison the next)
+constexpr int SEED_SCRATCH_EXTRA = 16;
 __global__ void kmeans_seed_init_kernel(unsigned long long* scratch, int l, int k, int64_t first_index) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < l * k) scratch[e] = (e % k == 0) ? (unsigned long long)first_index : ~0ull;
+  else if (e < l * k + SEED_SCRATCH_EXTRA) scratch[e] = 0ull;
 }
 
 // Step `ncols` (1 <= ncols < K): the chosen points scratch[l*K + 0 .. ncols) are the current centroids; every
@@ -829,15 +874,206 @@ __global__ void kmeans_seed_gather_kernel(const float* __restrict__ data, int l,
   centroids[e] = __ldg(data + ((int64_t)li * d + r) * n + idx);
 }
 
+// ---- farthest-point seeding, all K - 1 steps in ONE persistent cooperative launch ------------------------------------
+// Every block keeps its chunk of points in shared memory (coordinate-major, loaded once) and every thread keeps the
+// running best similarity and |a|^2 of its <= SEEDP_MMAX points in registers, so a step costs one scan of the resident
+// points against the NEWEST centroid only.  That is exact, not an approximation: the similarity of a point to an
+// already chosen centroid changes from one step to the next only when the summation order of the centroid norms
+// changes (col_is_sequential depends on the number of columns: at 4, 8 and 32 columns), and at exactly those steps the
+// running best is recomputed against all columns -- the reference recomputes everything every step (kmeans.py:95-98)
+// and obtains the same bits.  Every similarity is the separately rounded scalar sequence fl(fl(fl(2 dot) - |a|^2) -
+// |b|^2), which is what all three paths of kmeans_seed_step_kernel produce.  Per step: block arg-min -> 64-bit
+// atomicMin -> ONE grid barrier -> every block reads the winner.  Row shards (world > 1): after the barrier block (0,0)
+// stores this rank's candidate (key with GLOBAL index, coordinates) into every rank's exchange slot and raises its flag;
+// all ranks then take the smallest key in rank order -- the (value, index) arg-min exchange and the broadcast of the
+// winner of SURVEY section 8e, inside the kernel.
+constexpr int SEEDP_THREADS = 1024;
+constexpr int SEEDP_MMAX = 10;              // resident points per thread
+constexpr int SEEDP_SMEM_MAX = 208 * 1024;  // bytes of resident coordinates per block
+
+struct SeedShard {
+  int rank, world;
+  unsigned char* const* xchg;   // as KmLloyd::xchg
+  unsigned stamp_base;          // flags of this call: stamp_base (ready), stamp_base + 1 + step
+  int64_t col_offset, n_global; // global numbering of this shard's columns (n_global = 0: numbered on its own)
+};
+
+template <int DMAX, int KMAX, bool EXACT>
+__global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kernel(
+    const float* __restrict__ data, int d, int64_t n, int k, int64_t first_index, unsigned long long* __restrict__ scratch,
+    float* __restrict__ centroids, unsigned* __restrict__ barrier_ctr, int pts_per_block, const SeedShard sh) {
+  extern __shared__ __align__(16) float seed_xs[];               // [d][pts_per_block]
+  __shared__ float cs[DMAX * KMAX];                               // chosen centroids, [coordinate][column]
+  __shared__ float bn[KMAX];                                      // their squared norms under the current column count
+  __shared__ unsigned long long wmin[SEEDP_THREADS / 32];
+  __shared__ unsigned long long win_s;
+  __shared__ float win_xyz[DMAX];
+  if (EXACT) d = DMAX;
+  const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = pts_per_block;
+  const int64_t p0 = (int64_t)blockIdx.x * P;
+  const int np = (int)(n - p0 < P ? (n - p0 > 0 ? n - p0 : 0) : P);
+  const float* dl = data + (int64_t)l * d * n;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  const bool sharded = sh.world > 1;
+  const int64_t n_all = sh.n_global > 0 ? sh.n_global : n;
+  const int64_t goff = sh.col_offset + p0;                        // global index of this block's first point
+  unsigned phase = 0;
+  if (sharded && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
+    for (int p = 0; p < sh.world; ++p) st_release_sys(xchg_ready(sh.xchg[p]) + sh.rank, sh.stamp_base);
+
+  for (int r = 0; r < d; ++r)
+    for (int t = tid; t < np; t += SEEDP_THREADS) seed_xs[r * P + t] = __ldg(dl + (int64_t)r * n + p0 + t);
+  __syncthreads();
+  float best[SEEDP_MMAX], an[SEEDP_MMAX];
+#pragma unroll
+  for (int m = 0; m < SEEDP_MMAX; ++m) {
+    const int t = m * SEEDP_THREADS + tid;
+    best[m] = -INFINITY;
+    an[m] = 0.f;
+    if (t < np) {
+      float a[DMAX];
+#pragma unroll
+      for (int r = 0; r < DMAX; ++r) a[r] = (EXACT || r < d) ? seed_xs[r * P + t] : 0.f;
+      an[m] = sumsq_torch_order<DMAX>(a, d, col_is_sequential(goff + t, n_all));
+    }
+  }
+
+  for (int i = 0; i < k; ++i) {                                    // elect column i
+    if (i > 0) {
+      // columns whose similarities must be (re)computed this step: all of them when a norm changes its summation order
+      bool full = (i == 1);
+      for (int j = 0; j + 1 < i; ++j) full = full || (col_is_sequential(j, i - 1) != col_is_sequential(j, i));
+      const int jlo = full ? 0 : i - 1;
+      if (tid >= jlo && tid < i) {
+        float v[DMAX];
+#pragma unroll
+        for (int r = 0; r < DMAX; ++r) v[r] = (r < d) ? cs[r * KMAX + tid] : 0.f;
+        bn[tid] = sumsq_torch_order<DMAX>(v, d, col_is_sequential(tid, i));
+      }
+      __syncthreads();
+      unsigned long long key = ~0ull;
+#pragma unroll
+      for (int m = 0; m < SEEDP_MMAX; ++m) {
+        const int t = m * SEEDP_THREADS + tid;
+        if (t < np) {
+          float a[DMAX];
+#pragma unroll
+          for (int r = 0; r < DMAX; ++r) a[r] = (EXACT || r < d) ? seed_xs[r * P + t] : 0.f;
+          float b = full ? -INFINITY : best[m];
+          for (int j = jlo; j < i; ++j) {
+            float dot = 0.f;
+#pragma unroll
+            for (int r = 0; r < DMAX; ++r)
+              if (EXACT || r < d) dot = fmaf(a[r], cs[r * KMAX + j], dot);
+            const float y = __fsub_rn(__fsub_rn(__fmul_rn(dot, 2.0f), an[m]), bn[j]);
+            if (y > b) b = y;
+          }
+          best[m] = b;
+          const unsigned long long kk = pack_min_key(b, goff + t);
+          key = kk < key ? kk : key;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+      }
+      if (lane == 0) wmin[warp] = key;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < SEEDP_THREADS / 32; ++w) key = wmin[w] < key ? wmin[w] : key;
+        if (key != ~0ull) atomicMin(&scratch[(int64_t)l * k + i], key);
+      }
+      km_barrier(barrier_ctr, nblocks, ++phase);
+    }
+    // ---- the winner of this step (column 0: the caller's first index, stored by the init kernel) ----
+    if (sharded) {
+      const unsigned stamp = sh.stamp_base + 1u + (unsigned)i;
+      const int recd = 1 + (DMAX + 1) / 2;                         // doubles per candidate record: key, coordinates
+      const size_t slot = (size_t)gridDim.y * ((size_t)k * (d + 1) + 1);     // slot stride of the exchange buffer
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (i == 0) {
+          if (tid == 0) xchg_wait_all(xchg_ready(sh.xchg[sh.rank]), sh.world, sh.stamp_base);
+          __syncthreads();
+        }
+        if (tid < (int)gridDim.y) {                                // one thread per batch entry
+          const int ll = tid;
+          unsigned long long lw = __ldcg(&scratch[(int64_t)ll * k + i]);
+          const int64_t local = (int64_t)(lw & 0xffffffffull) - sh.col_offset;
+          const bool mine = lw != ~0ull && local >= 0 && local < n;
+          if (!mine) lw = ~0ull;                                    // (column 0: only the owner proposes it)
+          float xyz[DMAX];
+#pragma unroll
+          for (int r = 0; r < DMAX; ++r) xyz[r] = (mine && r < d) ? __ldg(data + ((int64_t)ll * d + r) * n + local) : 0.f;
+          for (int p = 0; p < sh.world; ++p) {
+            unsigned long long* rec =
+                reinterpret_cast<unsigned long long*>(xchg_slot(sh.xchg[p], i & 1, sh.world, sh.rank, slot)) + (size_t)ll * recd;
+            rec[0] = lw;
+#pragma unroll
+            for (int r = 0; r < (DMAX + 1) / 2; ++r) rec[1 + r] = pack2(xyz[2 * r], 2 * r + 1 < DMAX ? xyz[2 * r + 1] : 0.f);
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence_system();
+          for (int p = 0; p < sh.world; ++p) st_release_sys(xchg_flag(sh.xchg[p], i & 1, sh.world) + sh.rank, stamp);
+        }
+      }
+      if (tid == 0) {
+        xchg_wait_all(xchg_flag(sh.xchg[sh.rank], i & 1, sh.world), sh.world, stamp);
+        unsigned long long bestk = ~0ull;
+        int who = 0;
+        for (int r = 0; r < sh.world; ++r) {
+          const unsigned long long* rec =
+              reinterpret_cast<const unsigned long long*>(xchg_slot(sh.xchg[sh.rank], i & 1, sh.world, r, slot)) + (size_t)l * recd;
+          const unsigned long long kr = __ldcg(rec);
+          if (kr < bestk) { bestk = kr; who = r; }
+        }
+        const unsigned long long* rec =
+            reinterpret_cast<const unsigned long long*>(xchg_slot(sh.xchg[sh.rank], i & 1, sh.world, who, slot)) + (size_t)l * recd;
+#pragma unroll
+        for (int r = 0; r < (DMAX + 1) / 2; ++r) {
+          float lo, hi;
+          unpack2(__ldcg(rec + 1 + r), lo, hi);
+          win_xyz[2 * r] = lo;
+          if (2 * r + 1 < DMAX) win_xyz[2 * r + 1] = hi;
+        }
+        win_s = bestk;
+      }
+      __syncthreads();
+    } else {
+      if (tid == 0) win_s = __ldcg(&scratch[(int64_t)l * k + i]);
+      __syncthreads();
+      const int64_t idx = (int64_t)(win_s & 0xffffffffull);
+      if (tid < d) win_xyz[tid] = __ldg(dl + (int64_t)tid * n + idx);
+      __syncthreads();
+    }
+    if (tid < d) {
+      const float v = win_xyz[tid];
+      cs[tid * KMAX + i] = v;
+      if (blockIdx.x == 0) centroids[((int64_t)l * d + tid) * k + i] = v;
+    }
+    __syncthreads();
+  }
+  km_barrier_exit(barrier_ctr, nblocks);
+}
+
 // Launch the assign kernel (cooperatively when it accumulates: the fold needs a grid barrier).
-template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD>
+template <int DMAX, int KMAX, int WARPS, bool EXACT, int KPAD, bool TOURN = false, int SHARE = 1>
 static int km_launch_k(const float* data, const float* centroids, int l, int d, int64_t n, int k, int64_t* labels,
                      float* maxsims, double* sums, double* counts, double* simsum, void* workspace,
                      const int32_t* status, const int64_t* labels_in, KmLloyd fit, cudaStream_t st) {
-  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT, KPAD>;
+  if constexpr (!TOURN && EXACT && KPAD == 20 && WARPS == 12) {     // A/B switch, reference shape only
+    if (tune_get(ET_TUNE_KM_TOURNAMENT))
+      return km_launch_k<DMAX, KMAX, WARPS, EXACT, KPAD, true>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
+                                                               workspace, status, labels_in, fit, st);
+  }
+  auto kern = kmeans_assign_kernel<DMAX, KMAX, WARPS, EXACT, KPAD, TOURN, SHARE>;
   constexpr int KM_THREADS_L = WARPS * 32;
   const bool coop = sums != nullptr || fit.cent_out != nullptr;    // accumulating launches fold over the grid
-  const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, coop);
+  const size_t smem = km_smem_bytes<DMAX, KMAX>(d, k, WARPS, coop, SHARE);
   if (smem > 226 * 1024) return fail(ET_ERR_UNSUPPORTED, "k-means: K (d+1) = %d too large for the accumulation records", k * (d + 1));
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -855,7 +1091,7 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
     for (int l0 = 0; l0 < l; l0 += lc) {
       const int ll = l - l0 < lc ? l - l0 : lc;
       auto off = [&](auto* p, int64_t stride) { return p ? p + (int64_t)l0 * stride : p; };
-      int rc = km_launch_k<DMAX, KMAX, WARPS, EXACT, KPAD>(off(data, (int64_t)d * n), off(centroids, (int64_t)d * k), ll, d, n, k,
+      int rc = km_launch_k<DMAX, KMAX, WARPS, EXACT, KPAD, TOURN, SHARE>(off(data, (int64_t)d * n), off(centroids, (int64_t)d * k), ll, d, n, k,
                                                           off(labels, n), off(maxsims, n), off(sums, (int64_t)d * k),
                                                           off(counts, k), off(simsum, 1), workspace, status, off(labels_in, n),
                                                           fit, st);
@@ -900,6 +1136,13 @@ static int km_launch(const float* data, const float* centroids, int l, int d, in
   // accumulating launches of the reference shape: ONE 12-warp block per SM while its lane-private records fit shared
   // memory -- a third of the partial records and grid-barrier arrivals of the 3 x 4-warp configuration
   if constexpr (EXACT) {
+    // A/B: more warps per SM on half-size records (two lanes per record column, see SHARE)
+    const int wide = tune_get(ET_TUNE_KM_WARPS);
+    if (wide && (sums != nullptr || fit.cent_out != nullptr) && l <= sm_count() && ((k + 3) & ~3) == 20) {
+      if (wide == 16)
+        return km_launch_k<DMAX, KMAX, 16, EXACT, 20, false, 2>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum,
+                                                                workspace, status, labels_in, fit, st);
+    }
     if ((sums != nullptr || fit.cent_out != nullptr) && l <= sm_count() && km_smem_bytes<DMAX, KMAX>(d, k, 12, true) <= 224 * 1024)
       return km_launch_w<DMAX, KMAX, 12, EXACT>(data, centroids, l, d, n, k, labels, maxsims, sums, counts, simsum, workspace,
                                                 status, labels_in, fit, st);
@@ -941,6 +1184,40 @@ static void launch_seed_step(dim3 grid, cudaStream_t st, const float* data, int 
   else
     kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch,
                                                                                                cent_in, key_out);
+}
+
+// Launch the persistent seeding kernel if the points fit the blocks' shared memory and registers; returns 1 when the
+// caller has to take the launch-per-step path instead.
+template <int DMAX, int KMAX, bool EXACT>
+static int seed_persistent_try(const float* data, int l, int d, int64_t n, int k, int64_t first_index,
+                               unsigned long long* scratch, float* centroids, const SeedShard& sh, cudaStream_t st) {
+  if (l > sm_count() || tune_get(ET_TUNE_SEED_STEPWISE)) return 1;
+  const int gx = sm_count() / l;
+  int64_t P = (n + gx - 1) / gx;
+  P = (P + 31) & ~(int64_t)31;
+  if (P < 32) P = 32;
+  const size_t smem = (size_t)P * d * sizeof(float);
+  if (P > (int64_t)SEEDP_THREADS * SEEDP_MMAX || smem > (size_t)SEEDP_SMEM_MAX) return 1;
+  if (sh.world > 1 && (int64_t)k * (d + 1) + 1 < 1 + (DMAX + 1) / 2) return 1;     // candidate record must fit a slot
+  auto kern = kmeans_seed_persistent_kernel<DMAX, KMAX, EXACT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_seed_persistent_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int blocks_x = (int)((n + P - 1) / P) > 0 ? (int)((n + P - 1) / P) : 1;
+  kmeans_seed_init_kernel<<<(l * k + SEED_SCRATCH_EXTRA + 255) / 256, 256, 0, st>>>(scratch, l, k, first_index);
+  int rc = check_launch("kmeans_seed_init_kernel");
+  if (rc) return rc;
+  unsigned* ctr = reinterpret_cast<unsigned*>(scratch + (size_t)l * k);
+  e = launch_cooperative(kern, dim3(blocks_x, l), dim3(SEEDP_THREADS), smem, st, data, d, n, k, first_index, scratch, centroids, ctr,
+                         (int)P, sh);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_seed_persistent_kernel: cooperative launch: %s", cudaGetErrorString(e));
+  return check_launch("kmeans_seed_persistent_kernel");
+}
+
+static int seed_persistent(const float* data, int l, int d, int64_t n, int k, int64_t first_index, unsigned long long* scratch,
+                           float* centroids, const SeedShard& sh, cudaStream_t st) {
+  if (d == 6 && k <= 32) return seed_persistent_try<6, 32, true>(data, l, d, n, k, first_index, scratch, centroids, sh, st);
+  if (d <= 8 && k <= 32) return seed_persistent_try<8, 32, false>(data, l, d, n, k, first_index, scratch, centroids, sh, st);
+  return seed_persistent_try<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false>(data, l, d, n, k, first_index, scratch, centroids, sh, st);
 }
 
 static int km_check(int l, int d, int64_t n, int k) {
@@ -1089,7 +1366,11 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   ET_REQUIRE(n >= 1 && first_index >= 0 && first_index < n, ET_ERR_BADARG,
              "et_kmeans_farthest_init: first_index %lld outside [0, N = %lld)", (long long)first_index, (long long)n);
   cudaStream_t st = as_stream(stream);
-  kmeans_seed_init_kernel<<<(l * k_clusters + 255) / 256, 256, 0, st>>>(scratch, l, k_clusters, first_index);
+  // all K - 1 steps in one persistent launch while the points fit the SMs' shared memory (<= ~1.3e6 six-dimensional
+  // points on 148 SMs); otherwise one launch per step
+  rc = seed_persistent(data, l, d, n, k_clusters, first_index, scratch, centroids, SeedShard{}, st);
+  if (rc <= 0) return rc;
+  kmeans_seed_init_kernel<<<(l * k_clusters + SEED_SCRATCH_EXTRA + 255) / 256, 256, 0, st>>>(scratch, l, k_clusters, first_index);
   if ((rc = check_launch("kmeans_seed_init_kernel"))) return rc;
   dim3 grid(km_grid(n), l);
   for (int i = 1; i < k_clusters; ++i) {
@@ -1098,6 +1379,34 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   }
   kmeans_seed_gather_kernel<<<(l * d * k_clusters + 255) / 256, 256, 0, st>>>(data, l, d, n, k_clusters, scratch, centroids);
   return check_launch("kmeans_seed_gather_kernel");
+}
+
+int et_kmeans_farthest_init_sharded(const float* data, int l, int d, int64_t n_local, int k_clusters, int64_t first_global_index,
+                                    int64_t row_offset, int64_t n_global, float* centroids, unsigned long long* scratch, int rank,
+                                    int world, void* const* exchange_peers, unsigned stamp_base, et_stream_t stream) {
+  int rc = km_check(l, d, n_local, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(centroids && scratch && exchange_peers && (n_local == 0 || data), ET_ERR_BADARG,
+             "et_kmeans_farthest_init_sharded: null pointer");
+  ET_REQUIRE(world >= 2 && world <= KM_XCHG_MAX_WORLD && rank >= 0 && rank < world, ET_ERR_BADARG,
+             "et_kmeans_farthest_init_sharded: rank %d / world %d outside [2, %d]", rank, world, KM_XCHG_MAX_WORLD);
+  ET_REQUIRE(l <= 32, ET_ERR_UNSUPPORTED, "et_kmeans_farthest_init_sharded: batch l = %d > 32", l);
+  ET_REQUIRE(row_offset >= 0 && n_global >= row_offset + n_local && km_check(l, d, n_global, k_clusters) == ET_OK &&
+                 first_global_index >= 0 && first_global_index < n_global,
+             ET_ERR_BADARG, "et_kmeans_farthest_init_sharded: columns [%lld, %lld), first index %lld outside a data set of %lld",
+             (long long)row_offset, (long long)(row_offset + n_local), (long long)first_global_index, (long long)n_global);
+  SeedShard sh{};
+  sh.rank = rank;
+  sh.world = world;
+  sh.xchg = reinterpret_cast<unsigned char* const*>(exchange_peers);
+  sh.stamp_base = stamp_base;
+  sh.col_offset = row_offset;
+  sh.n_global = n_global;
+  rc = seed_persistent(data ? data : centroids, l, d, n_local, k_clusters, first_global_index, scratch, centroids, sh,
+                       as_stream(stream));
+  if (rc > 0) return fail(ET_ERR_UNSUPPORTED, "et_kmeans_farthest_init_sharded: %lld local points do not fit the resident kernel",
+                          (long long)n_local);
+  return rc;
 }
 
 int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,

@@ -795,13 +795,32 @@ def kmeans_finalize(acc, old_centroids, new_centroids, tol=0.0, use_status=False
           "et_kmeans_finalize")
 
 
+SEED_SCRATCH_EXTRA = 16      # uint64 words behind the l*K candidate keys (barrier counters of the persistent kernel)
+
+
 def kmeans_farthest_init(data, k, first_index, scratch=None):
+    """BatchKMeans.kmeanspp (farthest-point seeding from ``first_index``): all K - 1 steps in one persistent launch."""
     l, d, n = data.shape
     cent = torch.empty((l, d, k), device=data.device)
     if scratch is None:
-        scratch = torch.empty((l * k,), dtype=torch.int64, device=data.device)
+        scratch = torch.empty((l * k + SEED_SCRATCH_EXTRA,), dtype=torch.int64, device=data.device)
+    assert scratch.numel() >= l * k + SEED_SCRATCH_EXTRA
     check(load().et_kmeans_farthest_init(ptr(data), l, d, n, k, int(first_index), ptr(cent), ptr(scratch),
                                          stream_of(data.device)), "et_kmeans_farthest_init")
+    return cent
+
+
+def kmeans_farthest_init_sharded(data, k, first_global_index, row_offset, n_global, rank, world, peers, stamp_base):
+    """Farthest-point seeding over row shards with the per-step candidate exchange inside the persistent kernel (peer
+    memory, see et_kmeans_farthest_init_sharded).  Returns the (l,d,K) centroids, identical on every rank."""
+    l, d, n = data.shape
+    dev = peers.device
+    cent = torch.empty((l, d, k), device=dev)
+    scratch = torch.empty((l * k + SEED_SCRATCH_EXTRA,), dtype=torch.int64, device=dev)
+    check(load().et_kmeans_farthest_init_sharded(ptr(data) if n > 0 else None, l, d, n, k, int(first_global_index),
+                                                 int(row_offset), int(n_global), ptr(cent), ptr(scratch), int(rank), int(world),
+                                                 ptr(peers), int(stamp_base) & 0xFFFFFFFF, stream_of(dev)),
+          "et_kmeans_farthest_init_sharded")
     return cent
 
 

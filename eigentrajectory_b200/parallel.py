@@ -197,6 +197,17 @@ def peer_exchange_available(device, group=None):
     return True
 
 
+def sharded_farthest_init_fused(data_shard, n_clusters, first_global_index, row_offset, n_total, group=None):
+    """``sharded_farthest_init`` with all K - 1 steps AND their per-step candidate exchange inside one persistent kernel
+    per rank (``et_kmeans_farthest_init_sharded``, peer memory): no NCCL call and no host round trip per step.  The
+    centroids are identical on every rank and equal to what the unsharded ``et_kmeans_farthest_init`` picks."""
+    l, d, n_local = data_shard.shape
+    dev = data_shard.device
+    ex = PeerExchange.get(l, d, n_clusters, dev, group)
+    return ops.kmeans_farthest_init_sharded(data_shard, n_clusters, first_global_index, row_offset, n_total, ex.rank, ex.world,
+                                            ex.peers, ex.next_stamp(n_clusters))
+
+
 def sharded_kmeans_fit_fused(data_shard, n_clusters, n_total, centroids, max_iter=100, tol=1e-4, group=None, row_offset=None):
     """``sharded_kmeans_fit`` with the whole Lloyd loop AND its per-iteration all-reduce inside one persistent kernel per
     rank (``et_kmeans_lloyd_sharded``): the ranks exchange their folded records through peer memory, no NCCL call and

@@ -39,7 +39,8 @@ enum {
   ET_ERR_BADARG = -1,      /* null pointer, negative size, unsupported shape       */
   ET_ERR_ALIGN = -2,       /* pointer not 16-byte aligned                           */
   ET_ERR_CUDA = -3,        /* a CUDA runtime / driver call or a launch failed       */
-  ET_ERR_UNSUPPORTED = -4  /* shape outside what the kernels were built for         */
+  ET_ERR_UNSUPPORTED = -4, /* shape outside what the kernels were built for         */
+  ET_ERR_NCCL = -5         /* libnccl could not be loaded or a collective call failed */
 };
 
 enum { ET_NORM_ORI = 1, ET_NORM_ROT = 2, ET_NORM_SCA = 4 };
@@ -68,7 +69,10 @@ int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_
 /* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
  * Results never depend on them. */
 enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_GRAM_UNROLL = 2, ET_TUNE_EIG_THREADS = 3,
-       ET_TUNE_PDL = 4, ET_TUNE_COUNT = 8 };
+       ET_TUNE_PDL = 4, ET_TUNE_SEED_STEPWISE = 5 /* 1: farthest-point seeding as one launch per step */,
+       ET_TUNE_KM_TOURNAMENT = 6 /* 1: per-group tournament arg-max instead of the ascending compare/select scan (A/B) */,
+       ET_TUNE_KM_WARPS = 7 /* 16: sixteen warps per SM on shared record columns instead of twelve on private ones (A/B) */,
+       ET_TUNE_COUNT = 8 };
 int et_tune(int knob, int value);
 
 /* ---- normaliser: EigenTrajectory/normalizer.py ------------------------------------- */
@@ -275,10 +279,25 @@ int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_cluster
 /* BatchKMeans.kmeanspp (kmeans.py:78-112): deterministic farthest-point seeding.
  * centroids (l,d,K) out; column 0 = data[..., first_index]; every later column is the point
  * whose best similarity to the columns chosen so far is lowest (lowest index on ties),
- * recomputed from scratch each step as the reference does.  scratch: l*K uint64. */
+ * with the reference's arithmetic (the reference recomputes every similarity every step; here the running best of a
+ * point is reused across the steps in which it cannot have changed a bit and recomputed in the others, see
+ * et_kmeans.cu).  All K - 1 steps run in ONE persistent cooperative launch while the points fit the SMs' shared memory
+ * (~1.3e6 six-dimensional points on a B200), otherwise one launch per step.  scratch: l*K + 16 uint64. */
 int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_clusters,
                             int64_t first_index, float* centroids, unsigned long long* scratch,
                             et_stream_t stream);
+/* et_kmeans_farthest_init over ROW SHARDS on several GPUs of one node: data (l,d,n_local) holds the global columns
+ * [row_offset, row_offset + n_local) of n_global; first_global_index picks column 0.  Per step every rank's candidate
+ * (similarity bits, GLOBAL index, coordinates) is stored into every rank's exchange buffer through peer memory and the
+ * smallest key wins on every rank -- the (value, index) arg-min exchange and the winner's broadcast inside the kernel.
+ * exchange_peers / stamp_base as et_kmeans_lloyd_sharded (stamp_base must grow by at least K + 2 per call); centroids
+ * (l,d,K) are identical on every rank and equal to the unsharded call's.  scratch: l*K + 16 uint64.  Returns
+ * ET_ERR_UNSUPPORTED when the local points do not fit the resident kernel (the caller then seeds with
+ * et_kmeans_seed_candidate / et_kmeans_seed_fetch + two small all-reduces per step). */
+int et_kmeans_farthest_init_sharded(const float* data, int l, int d, int64_t n_local, int k_clusters,
+                                    int64_t first_global_index, int64_t row_offset, int64_t n_global,
+                                    float* centroids, unsigned long long* scratch, int rank, int world,
+                                    void* const* exchange_peers, unsigned stamp_base, et_stream_t stream);
 
 /* One farthest-point step on a ROW SHARD (kmeans.py:95-98 evaluated on local rows): with the first
  * ncols columns of centroids (l,d,K) given, key_out[l] = min over local points of
@@ -297,6 +316,24 @@ int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, i
                              et_stream_t stream);
 int et_kmeans_seed_fetch(const float* data, int l, int d, int64_t n, int64_t row_offset,
                          const long long* gkey, double* coords, et_stream_t stream);
+
+/* ---- collectives for row-sharded callers ------------------------------------------------
+ * The reference has no multi-GPU path of its own; these are what a host other than the Python mirror uses between the
+ * local passes: et_gram on the local rows -> et_allreduce_f64 on the packed Gram accumulators -> et_eig_jacobi_pair
+ * (identical bases on every rank, no broadcast); per Lloyd iteration et_kmeans_assign_shard -> et_allreduce_f64 on
+ * [sums | counts | simsum] -> et_kmeans_finalize; per seeding step et_kmeans_seed_candidate -> et_allreduce_min_i64 ->
+ * et_kmeans_seed_fetch -> et_allreduce_f64.  One communicator per process and GPU (NCCL underneath, bound at run time
+ * with dlopen("libnccl.so.2"); ET_ERR_NCCL if it is missing).  All calls are enqueued on `stream`, in place. */
+#define ET_COMM_ID_BYTES 128
+typedef struct et_comm* et_comm_t;
+/* rank 0 creates the 128-byte id and hands it to the other ranks by any out-of-band means */
+int et_comm_unique_id(void* id_out);
+/* collective over all ranks; binds the CURRENT CUDA device of the calling thread to `rank` */
+int et_comm_init(int rank, int nranks, const void* unique_id, et_comm_t* comm_out);
+int et_comm_rank(et_comm_t comm, int* rank, int* nranks);
+int et_allreduce_f64(double* buf, size_t n, et_comm_t comm, et_stream_t stream);          /* sum */
+int et_allreduce_min_i64(long long* buf, size_t n, et_comm_t comm, et_stream_t stream);   /* signed minimum */
+int et_comm_destroy(et_comm_t comm);
 
 /* ---- metrics: utils/metrics.py ---------------------------------------------------------- */
 /* compute_batch_ade + compute_batch_fde (metrics.py:73-102) in one pass, optionally with

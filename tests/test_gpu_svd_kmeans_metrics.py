@@ -14,8 +14,8 @@ from conftest import align_signs, load_golden, rel_fro, rel_max, t
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
 # free-running fit vs the reference loop (fp32 cascade sums there, fp64 sums here); measured values + margin, see the tests
-FIT_GOLDEN_MISMATCH, FIT_GOLDEN_CDIFF = 8, 1e-3
-FIT_1E6_MISMATCH, FIT_1E6_CDIFF = 50, 2e-5
+FIT_GOLDEN_MISMATCH, FIT_GOLDEN_CDIFF = 2, 1e-6      # measured on B200: 0 labels of 8192, 5.2e-8
+FIT_1E6_MISMATCH, FIT_1E6_CDIFF = 50, 2e-5         # measured on B200: 20 labels of 1e6, 1.22e-5 (100 iterations)
 HP = dict(obs_len=8, pred_len=12, k=6, num_samples=20, traj_dim=2, static_dist=0.419, obs_svd=True, pred_svd=True)
 
 
@@ -272,6 +272,34 @@ def test_kmeans_assign_large_vs_oracle_bit_exact(et, O):
         o_ms, o_lb = O.kmeans_assign(x, c)
         assert torch.equal(lb.cpu(), o_lb), (d, k, n)
         assert torch.equal(ms.cpu(), o_ms), (d, k, n)
+
+
+@pytest.mark.parametrize("l,d,k,n", [(1, 6, 20, 1_000_000), (1, 6, 20, 1_250_000), (3, 6, 20, 2049), (2, 5, 7, 3000),
+                                     (1, 8, 32, 4099), (2, 16, 64, 5000), (1, 6, 4, 33), (1, 3, 2, 1), (1, 6, 20, 6),
+                                     (1, 6, 20, 2_000_000)])
+def test_kmeans_seeding_persistent_kernel(et, O, l, d, k, n):
+    """All K - 1 farthest-point steps in one persistent launch (running best similarity, recomputed only where the
+    reference's summation order of the centroid norms changes: 4, 8 and 32 columns) == one launch per step (every
+    similarity recomputed every step, as kmeans.py:95-98 does) == the oracle, bit for bit.  2e6 points do not fit the
+    SMs' shared memory: the library falls back to the per-step launches by itself."""
+    gen = torch.Generator().manual_seed(7 * l + d + k)
+    data = (torch.randn(l, d, n, generator=gen) * torch.linspace(4.0, 0.3, d)[None, :, None]).contiguous()
+    first = n // 3
+    lib = et.load_library()
+    launches = et.launch_count()
+    fast = et.ops.kmeans_farthest_init(data.cuda(), k, first)
+    n_fast = et.launch_count() - launches
+    lib.et_tune(5, 1)
+    try:
+        launches = et.launch_count()
+        slow = et.ops.kmeans_farthest_init(data.cuda(), k, first)
+        n_slow = et.launch_count() - launches
+    finally:
+        lib.et_tune(5, 0)
+    assert torch.equal(fast, slow)
+    assert n_slow == k + 1 and (n_fast == 2 or n > 1_400_000)
+    if 8 <= n <= 1_250_000:      # (with fewer than 8 points torch's CPU matmul takes a small-matrix path with another
+        assert torch.equal(fast.cpu(), O.kmeans_farthest_init(data, k, first))       # rounding order: not a parity case)
 
 
 def test_kmeans_fit_free_running(et):
