@@ -1,0 +1,30 @@
+"""GPU: BASELINE.json config 4 -- the reference's own ETSGCNTrainer.test loop (utils/trainer.py:172-195) on the zara1 test
+split with the UNMODIFIED SGCN predictor (baseline/sgcn/model.py, bridge.py) behind the hook seam, run with the
+reference's EigenTrajectory / metrics modules and with eigentrajectory_b200 swapped in, from the same state_dict
+(scripts/run_config4.py).  Needs the staged reference (oracle/make_ref.sh -> oracle/_ref); skipped where it is absent."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+from oracle import ref_loader          # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref not staged")]
+TOL = 1e-5
+
+
+def test_sgcn_zara1_evaluation_loop_matches_reference():
+    import run_config4
+    out = run_config4.main("zara1", quiet=True)
+    print({k: out[k] for k in ("scenes", "pedestrians", "ms_per_scene_reference_l2", "ms_per_scene_ours", "speedup",
+                               "library_launches_per_scene", "ADE", "FDE", "TCC", "COL")})
+    assert out["scenes"] == 602 and out["pedestrians"] == 2253
+    # per-pedestrian scores of the two runs: 1e-5 relative (north_star) on ADE / FDE; COL counts colliding samples
+    # (percent, multiples of 5) and must agree exactly; TCC is a correlation in [-1, 1]
+    assert out["ADE"]["max_rel_diff"] <= TOL and out["FDE"]["max_rel_diff"] <= TOL, (out["ADE"], out["FDE"])
+    assert out["COL"]["max_abs_diff"] == 0.0, out["COL"]
+    assert out["TCC"]["max_abs_diff"] <= 1e-4, out["TCC"]
+    assert out["library_launches_per_scene"] == 4.0      # project + reconstruct, one metrics pass + COL
