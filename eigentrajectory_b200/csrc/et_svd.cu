@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(GG_THREADS) gram_generic(const float* __restri
 //    exact-zero rows/columns -- the normalised last observed frame -- never rotate).
 // =======================================================================================
 constexpr int EIG_MAX_THREADS = 288;
+constexpr double EIGF_REL = 1e-12;      // relative rotation threshold of the compile-time-size solver
 constexpr int EIG_MAX_SWEEPS = 60;
 
 // The solve is latency-bound (a 24 x 24 matrix has 288 work items per phase) and one warp spends ~3 cycles per
@@ -367,6 +368,165 @@ __device__ __forceinline__ void eig_jacobi_body(const double* __restrict__ G, in
   }
 }
 
+// Compile-time sizes (16 x 16 and 24 x 24, the reference's two bases): the same parallel-ordered cyclic Jacobi with TWO
+// block barriers per step instead of four.  One barrier ends the rotation-parameter phase and counts the rotating
+// pairs on the way (__syncthreads_count: no shared counters); then the two-sided update A <- J^T A J is applied in ONE
+// phase, one thread per 2 x 2 block (row pair i, column pair j: right rotation of pair j, then left rotation of pair i,
+// the same operations the column pass followed by the row pass would perform), while a second group of warps applies
+// V <- V J, one thread per (row, pair).  EIGF_THREADS<MP> threads: [0, (MP/2)^2) update A, [AW, AW + MP/2 * MP) update V.
+// Reciprocal and reciprocal square root in float64 from the hardware seeds (rcp / rsqrt.approx.ftz.f64, ~2^-22 relative)
+// and two Newton steps each: full double accuracy up to a few ulp at a third of the latency of the IEEE-rounded
+// division / sqrt sequences.  The Jacobi rotation needs c^2 + s^2 = 1 to rounding, not a correctly rounded angle.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);
+  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);
+  return r;
+}
+
+template <int MP>
+struct EigFast {
+  static constexpr int HALF = MP / 2;
+  static constexpr int AW = (HALF * HALF + 31) & ~31;       // first thread of the V group (warp aligned)
+  static constexpr int THREADS = AW + HALF * MP;
+};
+
+template <int MP>
+__device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, int k, float* __restrict__ U,
+                                                float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
+                                                int* __restrict__ info, double* sm) {
+  constexpr int m = MP, half = MP / 2, ld = MP + 1, AW = EigFast<MP>::AW;
+  double* A = sm;                // MP x MP, row-major with odd pitch
+  double* V = A + MP * ld;
+  double* cs = V + MP * ld;      // half cosines, half sines
+  int* pr = reinterpret_cast<int*>(cs + MP);   // pairs p[half], q[half]
+  int* order = pr + MP;
+  __shared__ double floor2;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int e = tid; e < MP * MP; e += nthr) {
+    const int r = e / MP, c = e % MP;
+    A[r * ld + c] = 0.5 * (G[r * m + c] + G[c * m + r]);
+    V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
+    floor2 = (1e-18 * mx) * (1e-18 * mx);
+  }
+  __syncthreads();
+  int sweeps_done = 0, total_rot = 0;
+  for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
+    int n_rot = 0;
+    for (int step = 0; step < MP - 1; ++step) {
+      bool rotating = false;
+      if (tid < half) {          // round-robin tournament: position 0 fixed, the others rotate
+        const int pi = tid;
+        auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (MP - 1); };
+        int p = player(pi), q = player(MP - 1 - pi);
+        if (p > q) { const int t = p; p = q; q = t; }
+        const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+        double c = 1.0, s = 0.0;
+        // rotate iff |a_pq| > EIGF_REL sqrt(a_pp a_qq) (compared squared) and above the absolute floor (see the generic
+        // body).  1e-12 relative leaves the eigenvectors ~1e-12 from converged -- five orders below what the fp32 outputs
+        // resolve -- and ends the iteration one to two sweeps earlier than 1e-14.
+        if (apq * apq > floor2 && apq * apq > (EIGF_REL * EIGF_REL) * fabs(app * aqq)) {
+          const double o = 2.0 * apq, dd = aqq - app;
+          const double x = fma(dd, dd, o * o);
+          const double h = x * fast_rsqrt(x);
+          const double t = o * fast_rcp(dd + (dd >= 0.0 ? h : -h));
+          c = fast_rsqrt(fma(t, t, 1.0));
+          s = t * c;
+          rotating = true;
+        }
+        cs[pi] = c; cs[half + pi] = s; pr[pi] = p; pr[half + pi] = q;
+      }
+      const int rotated = __syncthreads_count(rotating);      // barrier + number of rotating pairs, block-uniform
+      n_rot += rotated;
+      if (rotated == 0) continue;       // nothing to do in this step (typical for the last, confirming sweep)
+      if (tid < half * half) {
+        const int i = tid / half, j = tid % half;
+        const double ci = cs[i], si = cs[half + i], cj = cs[j], sj = cs[half + j];
+        if (si != 0.0 || sj != 0.0) {
+          const int pi_ = pr[i], qi = pr[half + i], pj = pr[j], qj = pr[half + j];
+          const double x00 = A[pi_ * ld + pj], x01 = A[pi_ * ld + qj], x10 = A[qi * ld + pj], x11 = A[qi * ld + qj];
+          // columns: X J_j
+          const double t00 = cj * x00 - sj * x01, t01 = sj * x00 + cj * x01;
+          const double t10 = cj * x10 - sj * x11, t11 = sj * x10 + cj * x11;
+          // rows: J_i^T T; the rotated off-diagonal pair is zero by construction and is stored as exactly zero
+          const bool diag = (i == j) && si != 0.0;
+          A[pi_ * ld + pj] = ci * t00 - si * t10;
+          A[pi_ * ld + qj] = diag ? 0.0 : ci * t01 - si * t11;
+          A[qi * ld + pj] = diag ? 0.0 : si * t00 + ci * t10;
+          A[qi * ld + qj] = si * t01 + ci * t11;
+        }
+      } else if (tid >= AW && tid < AW + half * MP) {
+        const int e = tid - AW, pi = e / MP, r = e % MP;
+        const double c = cs[pi], s = cs[half + pi];
+        if (s != 0.0) {
+          const int p = pr[pi], q = pr[half + pi];
+          const double vp = V[r * ld + p], vq = V[r * ld + q];
+          V[r * ld + p] = c * vp - s * vq;
+          V[r * ld + q] = s * vp + c * vq;
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps_done;
+    total_rot += n_rot;
+    if (n_rot == 0) break;
+  }
+  if (info && tid == 0) { info[0] = sweeps_done; info[1] = total_rot; }
+
+  // order eigenvalues descending (ties: lower index first), canonical sign, S = sqrt(lambda)
+  if (tid == 0) {
+    for (int i = 0; i < m; ++i) order[i] = i;
+    for (int i = 0; i < m; ++i) {
+      int best = i;
+      for (int j = i + 1; j < m; ++j)
+        if (A[order[j] * ld + order[j]] > A[order[best] * ld + order[best]]) best = j;
+      const int t = order[i]; order[i] = order[best]; order[best] = t;
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < k; j += nthr) {
+    const int col = order[j];
+    const double lam = A[col * ld + col];
+    const double sv = sqrt(lam > 0.0 ? lam : 0.0);
+    int arg = 0;
+    double big = -1.0;
+    for (int r = 0; r < m; ++r) {
+      const double a = fabs(V[r * ld + col]);
+      if (a > big) { big = a; arg = r; }
+    }
+    const double sign = V[arg * ld + col] < 0.0 ? -1.0 : 1.0;
+    for (int r = 0; r < m; ++r) {
+      const double v = sign * V[r * ld + col];
+      U[r * k + j] = (float)v;
+      if (U64) U64[r * k + j] = v;
+    }
+    S[j] = (float)sv;
+    if (S64) S64[j] = sv;
+  }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(EigFast<MP>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
+                                                                               float* __restrict__ U, float* __restrict__ S,
+                                                                               double* __restrict__ U64, double* __restrict__ S64,
+                                                                               int* __restrict__ info) {
+  extern __shared__ double sm[];
+  eig_jacobi_fast<MP>(G, k, U, S, U64, S64, info, sm);
+}
+
 template <int MP, int NT>
 __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const double* __restrict__ G, int m, int k,
                                                                      float* __restrict__ U, float* __restrict__ S,
@@ -378,14 +538,14 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
 
 // Both bases of one descriptor (16 x 16 observation and 24 x 24 prediction Gram matrices) in ONE launch: block 0 / 1
 // solve them side by side on two SMs, so the pair costs what the larger solve costs.
-constexpr int EIG_PAIR_THREADS = 288;
+constexpr int EIG_PAIR_THREADS = EigFast<24>::THREADS;
 __global__ void __launch_bounds__(EIG_PAIR_THREADS) eig_jacobi_pair_kernel(const double* __restrict__ G_a,
                                                                            const double* __restrict__ G_b, int k,
                                                                            float* __restrict__ U_a, float* __restrict__ S_a,
                                                                            float* __restrict__ U_b, float* __restrict__ S_b) {
   extern __shared__ double sm[];
-  if (blockIdx.x == 0) eig_jacobi_body<16, EIG_PAIR_THREADS>(G_a, 16, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
-  else eig_jacobi_body<24, EIG_PAIR_THREADS>(G_b, 24, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
+  if (blockIdx.x == 0) eig_jacobi_fast<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
+  else eig_jacobi_fast<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
 }
 
 // =======================================================================================
@@ -586,8 +746,14 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   cudaStream_t st = as_stream(stream);
   // one work item per thread (measured on B200, 24 x 24: 403 / 211 / 184 / 158 us with 32 / 96 / 144 / 288 threads;
   // 16 x 16: 117 / 90 / 74 us with 32 / 64 / 128; results bit-identical)
-  const int nt = tune_get(ET_TUNE_EIG_THREADS);      // experiments: 32 = the single-warp variant
-  if (mp == 16) {
+  // 16 x 16 / 24 x 24 take the two-barrier body (eig_jacobi_fast: 24 x 24 in ~95 us); ET_TUNE_EIG_THREADS selects the
+  // four-barrier body with that many threads for A/B runs (32 = the single-warp variant)
+  const int nt = tune_get(ET_TUNE_EIG_THREADS);
+  if (m == 16 && nt == 0) {
+    eig_jacobi_fast_kernel<16><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 0) {
+    eig_jacobi_fast_kernel<24><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (mp == 16) {
     if (nt == 32) eig_jacobi_kernel<16, 32><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
     else eig_jacobi_kernel<16, 128><<<1, 128, smem, st>>>(G, m, k, U, S, U64, S64, info);
   } else if (mp == 24) {
