@@ -456,6 +456,27 @@ def main():
     if world > 1:
         dist.all_reduce(rates)
     del ro, rp, co, cp
+    # the raw ceiling of that path on this host: the same bytes as plain pinned copies, both directions at once on all
+    # ranks (no kernel, no chunking) -- what the PCIe fabric of the box delivers at this N
+    raw_in, raw_out = torch.empty(n * 160, dtype=torch.uint8, device=dev), torch.empty(n * 208, dtype=torch.uint8, device=dev)
+    pin_in, pin_out = torch.empty(n * 160, dtype=torch.uint8).pin_memory(), torch.empty(n * 208, dtype=torch.uint8).pin_memory()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    raw_times = []
+    for j in range(7):
+        barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_in):
+            raw_in.copy_(pin_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            pin_out.copy_(raw_out, non_blocking=True)
+        torch.cuda.synchronize()
+        if j >= 2:
+            raw_times.append(time.perf_counter() - t0)
+    raw_t = torch.tensor([sum(raw_times) / len(raw_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(raw_t, op=dist.ReduceOp.MAX)
+    copy_ceiling = world * n / float(raw_t.item())
+    del raw_in, raw_out, pin_in, pin_out
 
     stages = None
     if not args.no_stages:
@@ -481,6 +502,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 208,
                     "api": "ETDescriptor.project_reconstruct(host tensors)", "ms_per_step": 1e3 * float(e2e_t.item()),
                     "pcie_gbs_per_rank": [round(float(v), 2) for v in rates.tolist()],
+                    "raw_copy_ceiling": {"value": copy_ceiling, "unit": UNIT, "frac_of_ceiling": e2e_value / copy_ceiling,
+                                         "what": "plain pinned H2D (160 B/trajectory) + D2H (208 B/trajectory) copies, both "
+                                                 "directions at once on all ranks, no kernel"},
                     "host_numa": et.ops.host_numa_summary()},
             "gpu_launches": launches,
             "clocks": sampler.summary(),

@@ -225,6 +225,13 @@ __device__ __forceinline__ double* xchg_slot(unsigned char* base, int parity, in
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// One flag per peer behind ONE system-scope fence: the fence orders everything before it (this block's record stores,
+// made visible to this thread by the preceding barrier) ahead of all the relaxed flag stores that follow.  A release
+// store per peer would drain the outstanding NVLink writes once per peer -- measured ~2 us each, 16 us per Lloyd
+// iteration at 8 GPUs.
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -311,7 +318,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   const bool accumulate = sums != nullptr || whole_fit;
   if (whole_fit && fit.world > 1 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     // tell every rank that this rank has entered the call (so it has finished reading the previous call's slots)
-    for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_ready(fit.xchg[p]) + fit.rank, fit.stamp_base);
+    __threadfence_system();
+    for (int p = 0; p < fit.world; ++p) st_relaxed_sys(xchg_ready(fit.xchg[p]) + fit.rank, fit.stamp_base);
   }
   const int npair = d >> 1, nsingle = (d & 1) + 1;          // per cluster: d/2 coordinate pairs, then (odd coordinate,) count
   float* lanesingle = lanerec + (size_t)k * npair * 2 * LANES;
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
       else __syncthreads();
       if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
         __threadfence_system();                         // cumulative over the block's stores ordered by the barrier above
-        for (int p = 0; p < fit.world; ++p) st_release_sys(xchg_flag(fit.xchg[p], it & 1, fit.world) + fit.rank, stamp);
+        for (int p = 0; p < fit.world; ++p) st_relaxed_sys(xchg_flag(fit.xchg[p], it & 1, fit.world) + fit.rank, stamp);
       }
       if (tid == 0) xchg_wait_all(xchg_flag(fit.xchg[fit.rank], it & 1, fit.world), fit.world, stamp);
       __syncthreads();
@@ -920,7 +928,10 @@ __global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kerne
   const int64_t goff = sh.col_offset + p0;                        // global index of this block's first point
   unsigned phase = 0;
   if (sharded && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0)
-    for (int p = 0; p < sh.world; ++p) st_release_sys(xchg_ready(sh.xchg[p]) + sh.rank, sh.stamp_base);
+  {
+    __threadfence_system();
+    for (int p = 0; p < sh.world; ++p) st_relaxed_sys(xchg_ready(sh.xchg[p]) + sh.rank, sh.stamp_base);
+  }
 
   for (int r = 0; r < d; ++r)
     for (int t = tid; t < np; t += SEEDP_THREADS) seed_xs[r * P + t] = __ldg(dl + (int64_t)r * n + p0 + t);
@@ -1013,12 +1024,11 @@ __global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kerne
 #pragma unroll
             for (int r = 0; r < (DMAX + 1) / 2; ++r) rec[1 + r] = pack2(xyz[2 * r], 2 * r + 1 < DMAX ? xyz[2 * r + 1] : 0.f);
           }
-          __threadfence_system();
         }
-        __syncthreads();
+        __syncthreads();      // thread 0's fence below is cumulative over the record stores of the other threads
         if (tid == 0) {
           __threadfence_system();
-          for (int p = 0; p < sh.world; ++p) st_release_sys(xchg_flag(sh.xchg[p], i & 1, sh.world) + sh.rank, stamp);
+          for (int p = 0; p < sh.world; ++p) st_relaxed_sys(xchg_flag(sh.xchg[p], i & 1, sh.world) + sh.rank, stamp);
         }
       }
       if (tid == 0) {
