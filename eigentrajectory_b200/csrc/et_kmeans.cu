@@ -210,17 +210,39 @@ struct KmLloyd {
   int64_t n_global;             // columns over all shards (0: this launch holds all of them)
 };
 
-// Exchange buffer of one rank: uint32 ready[world] at byte 0, uint32 flag[2][world] at byte 128, then at byte 256
-// double slot[2][world][l * (K (d+1) + 1)] (two parities: iteration i + 1 writes the other half while a slow peer may
-// still read iteration i).
+// Exchange buffer of one rank: uint32 ready[world] at byte 0 (the "this rank has entered the call" stamps), then at byte
+// 256 slot[2][world][l * (K (d+1) + 1)] 64-bit payload words, each stored as TWO 8-byte packets {32 payload bits, 32-bit
+// stamp} (two parities: iteration i + 1 writes the other half while a slow peer may still read iteration i).  A packet
+// is one naturally atomic 8-byte store, so the stamp travels WITH the data: the receiver polls the packet itself and no
+// fence or separate flag (one more NVLink round trip each) sits between "record stored" and "record usable".
 constexpr int KM_XCHG_HEADER = 256;
 constexpr int KM_XCHG_MAX_WORLD = 16;
 __device__ __forceinline__ unsigned* xchg_ready(unsigned char* base) { return reinterpret_cast<unsigned*>(base); }
-__device__ __forceinline__ unsigned* xchg_flag(unsigned char* base, int parity, int world) {
-  return reinterpret_cast<unsigned*>(base + 128) + parity * world;
+// first packet of payload word `w` of rank r's record (slot_words payload words per rank and parity)
+__device__ __forceinline__ unsigned long long* xchg_packets(unsigned char* base, int parity, int world, int r, size_t slot_words,
+                                                           size_t w) {
+  return reinterpret_cast<unsigned long long*>(base + KM_XCHG_HEADER) + (((size_t)parity * world + r) * slot_words + w) * 2;
 }
-__device__ __forceinline__ double* xchg_slot(unsigned char* base, int parity, int world, int r, size_t slot_doubles) {
-  return reinterpret_cast<double*>(base + KM_XCHG_HEADER) + ((size_t)parity * world + r) * slot_doubles;
+__device__ __forceinline__ void ll_store(unsigned long long* pk, unsigned long long payload, unsigned stamp) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(pk), "r"((unsigned)payload), "r"(stamp) : "memory");
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(pk + 1), "r"((unsigned)(payload >> 32)), "r"(stamp) : "memory");
+}
+// Spin until both packets carry `stamp`; a peer that never arrives traps the kernel after ~10 s instead of hanging it.
+__device__ __forceinline__ unsigned long long ll_load(const unsigned long long* pk, unsigned stamp) {
+  unsigned lo, hi, s0, s1, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(s0) : "l"(pk) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(hi), "=r"(s1) : "l"(pk + 1) : "memory");
+    if (s0 == stamp && s1 == stamp) break;
+    if ((++spins & 0x3ffu) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 10000000000ull) __trap();
+    }
+  }
+  return ((unsigned long long)hi << 32) | lo;
 }
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -617,38 +639,34 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     const size_t slot = (size_t)gridDim.y * out_rec;
     if (sharded) {
       // Row-sharded fit: block 0 of every batch entry stores this rank's folded record straight into every rank's
-      // exchange slot (its own included); one thread then fences at system scope and raises this rank's flag for the
-      // iteration on every peer; every block waits until all `world` flags are up in its OWN buffer.
+      // exchange slot (its own included) as stamped packets; every block then gathers the `world` records from its OWN
+      // buffer, entry by entry, spinning on a packet until it carries this iteration's stamp, and adds them in rank
+      // order -- so all ranks hold bit-identical totals, centroids and convergence decisions without a broadcast.
       const unsigned stamp = fit.stamp_base + 1u + (unsigned)it;
+      const size_t slot_words = (size_t)gridDim.y * out_rec;
       if (blockIdx.x == 0) {
         if (it == 0) {           // peers must have entered this call (they are done reading the previous call's slots)
           if (tid == 0) xchg_wait_all(xchg_ready(fit.xchg[fit.rank]), fit.world, fit.stamp_base);
           __syncthreads();
         }
         for (int e = tid; e < out_rec; e += THREADS) {
-          const double v = blk[e];
+          const unsigned long long v = (unsigned long long)__double_as_longlong(blk[e]);
           for (int p = 0; p < fit.world; ++p)
-            xchg_slot(fit.xchg[p], it & 1, fit.world, fit.rank, slot)[(size_t)l * out_rec + e] = v;
+            ll_store(xchg_packets(fit.xchg[p], it & 1, fit.world, fit.rank, slot_words, (size_t)l * out_rec + e), v, stamp);
         }
-        if (gridDim.y > 1) __threadfence_system();      // the flag is raised by another block: every writer fences
       }
-      if (gridDim.y > 1) km_barrier(barrier_ctr + 2, nblocks, ++phase);     // all batch entries are stored
-      else __syncthreads();
-      if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
-        __threadfence_system();                         // cumulative over the block's stores ordered by the barrier above
-        for (int p = 0; p < fit.world; ++p) st_relaxed_sys(xchg_flag(fit.xchg[p], it & 1, fit.world) + fit.rank, stamp);
+      __syncthreads();           // blk[] is overwritten with the global totals below
+      for (int e = tid; e < out_rec; e += THREADS) {
+        double t = 0.0;
+        for (int r = 0; r < fit.world; ++r)
+          t += __longlong_as_double((long long)ll_load(
+              xchg_packets(fit.xchg[fit.rank], it & 1, fit.world, r, slot_words, (size_t)l * out_rec + e), stamp));
+        blk[e] = t;
       }
-      if (tid == 0) xchg_wait_all(xchg_flag(fit.xchg[fit.rank], it & 1, fit.world), fit.world, stamp);
       __syncthreads();
     }
-    // folded total of record entry idx of this batch entry: this block's fold, or the ranks' records added in rank order
-    auto total_at = [&](int idx) -> double {
-      if (!sharded) return blk[idx];
-      double t = 0.0;
-      for (int r = 0; r < fit.world; ++r)
-        t += __ldcg(xchg_slot(fit.xchg[fit.rank], it & 1, fit.world, r, slot) + (size_t)l * out_rec + idx);
-      return t;
-    };
+    // folded total of record entry idx of this batch entry (this rank's fold, or the ranks' records added in rank order)
+    auto total_at = [&](int idx) -> double { return blk[idx]; };
     double e2 = 0.0;
     for (int e = tid; e < d * k; e += THREADS) {
       const int r = e / k, c = e - r * k;
@@ -1001,8 +1019,8 @@ __global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kerne
     // ---- the winner of this step (column 0: the caller's first index, stored by the init kernel) ----
     if (sharded) {
       const unsigned stamp = sh.stamp_base + 1u + (unsigned)i;
-      const int recd = 1 + (DMAX + 1) / 2;                         // doubles per candidate record: key, coordinates
-      const size_t slot = (size_t)gridDim.y * ((size_t)k * (d + 1) + 1);     // slot stride of the exchange buffer
+      constexpr int recd = 1 + (DMAX + 1) / 2;                     // 64-bit words per candidate record: key, coordinate pairs
+      const size_t slot_words = (size_t)gridDim.y * ((size_t)k * (d + 1) + 1);     // payload words per rank and parity
       if (blockIdx.x == 0 && blockIdx.y == 0) {
         if (i == 0) {
           if (tid == 0) xchg_wait_all(xchg_ready(sh.xchg[sh.rank]), sh.world, sh.stamp_base);
@@ -1018,35 +1036,25 @@ __global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kerne
 #pragma unroll
           for (int r = 0; r < DMAX; ++r) xyz[r] = (mine && r < d) ? __ldg(data + ((int64_t)ll * d + r) * n + local) : 0.f;
           for (int p = 0; p < sh.world; ++p) {
-            unsigned long long* rec =
-                reinterpret_cast<unsigned long long*>(xchg_slot(sh.xchg[p], i & 1, sh.world, sh.rank, slot)) + (size_t)ll * recd;
-            rec[0] = lw;
+            ll_store(xchg_packets(sh.xchg[p], i & 1, sh.world, sh.rank, slot_words, (size_t)ll * recd), lw, stamp);
 #pragma unroll
-            for (int r = 0; r < (DMAX + 1) / 2; ++r) rec[1 + r] = pack2(xyz[2 * r], 2 * r + 1 < DMAX ? xyz[2 * r + 1] : 0.f);
+            for (int r = 0; r < (DMAX + 1) / 2; ++r)
+              ll_store(xchg_packets(sh.xchg[p], i & 1, sh.world, sh.rank, slot_words, (size_t)ll * recd + 1 + r),
+                       pack2(xyz[2 * r], 2 * r + 1 < DMAX ? xyz[2 * r + 1] : 0.f), stamp);
           }
         }
-        __syncthreads();      // thread 0's fence below is cumulative over the record stores of the other threads
-        if (tid == 0) {
-          __threadfence_system();
-          for (int p = 0; p < sh.world; ++p) st_relaxed_sys(xchg_flag(sh.xchg[p], i & 1, sh.world) + sh.rank, stamp);
-        }
       }
-      if (tid == 0) {
-        xchg_wait_all(xchg_flag(sh.xchg[sh.rank], i & 1, sh.world), sh.world, stamp);
+      if (tid == 0) {              // every block: the smallest key over the ranks (rank order), then its coordinates
         unsigned long long bestk = ~0ull;
         int who = 0;
         for (int r = 0; r < sh.world; ++r) {
-          const unsigned long long* rec =
-              reinterpret_cast<const unsigned long long*>(xchg_slot(sh.xchg[sh.rank], i & 1, sh.world, r, slot)) + (size_t)l * recd;
-          const unsigned long long kr = __ldcg(rec);
+          const unsigned long long kr = ll_load(xchg_packets(sh.xchg[sh.rank], i & 1, sh.world, r, slot_words, (size_t)l * recd), stamp);
           if (kr < bestk) { bestk = kr; who = r; }
         }
-        const unsigned long long* rec =
-            reinterpret_cast<const unsigned long long*>(xchg_slot(sh.xchg[sh.rank], i & 1, sh.world, who, slot)) + (size_t)l * recd;
 #pragma unroll
         for (int r = 0; r < (DMAX + 1) / 2; ++r) {
           float lo, hi;
-          unpack2(__ldcg(rec + 1 + r), lo, hi);
+          unpack2(ll_load(xchg_packets(sh.xchg[sh.rank], i & 1, sh.world, who, slot_words, (size_t)l * recd + 1 + r), stamp), lo, hi);
           win_xyz[2 * r] = lo;
           if (2 * r + 1 < DMAX) win_xyz[2 * r + 1] = hi;
         }
@@ -1306,7 +1314,8 @@ int et_kmeans_lloyd(const float* data, const float* centroids, int l, int d, int
 
 size_t et_kmeans_exchange_bytes(int l, int d, int k_clusters, int world) {
   if (l < 1 || d < 1 || k_clusters < 1 || world < 1 || world > KM_XCHG_MAX_WORLD) return 0;
-  return (size_t)KM_XCHG_HEADER + (size_t)2 * world * l * ((size_t)k_clusters * (d + 1) + 1) * sizeof(double);
+  // header + two parities x world records x l (K (d+1) + 1) payload words x two 8-byte packets per word
+  return (size_t)KM_XCHG_HEADER + (size_t)2 * world * l * ((size_t)k_clusters * (d + 1) + 1) * 16;
 }
 
 int et_kmeans_lloyd_sharded(const float* data, const float* centroids, int l, int d, int64_t n_local, int k_clusters,
