@@ -242,7 +242,7 @@ def run_stages(et, dist, dev, rank, world, n_rows, reps):
     # ---- parity 2: k-means over the sharded coefficients: NCCL path == fused peer-memory path == oracle labels ----
     C = ops.project(obs, pred, Uo, Up)[1].unsqueeze(0).contiguous()                  # (1, 6, n_rows) of this rank
     first = 12345
-    cent0 = P.sharded_farthest_init(C, 20, first, a)
+    cent0 = P.sharded_farthest_init(C, 20, first, a, n_total=n_total)
     m = 6
     lab_n, cent_n, it_n, inertia_n = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m, tol=-1.0, row_offset=a)
     _, cent_before, _, _ = P.sharded_kmeans_fit(C, 20, n_total, cent0, max_iter=m - 1, tol=-1.0, row_offset=a)
@@ -280,7 +280,7 @@ def run_stages(et, dist, dev, rank, world, n_rows, reps):
     st = {"rows_per_gpu": n_rows, "rows_total": n_total, "kmeans": "d=6, K=20 on the C_pred coefficients of the rows"}
     st["basis_ms"] = timed(lambda: P.sharded_basis(obs, pred, K_RANK), reps)
     st["gram_pass_ms"] = timed(lambda: ops.gram(obs, pred, True, True, True), reps)
-    st["seed_ms"] = timed(lambda: P.sharded_farthest_init(C, 20, first, a), 3)                 # two small all-reduces per step
+    st["seed_ms"] = timed(lambda: P.sharded_farthest_init(C, 20, first, a, n_total=n_total), 3)                 # two small all-reduces per step
     if fused_ok:
         seeded = P.sharded_farthest_init_fused(C, 20, first, a, n_total)
         assert torch.equal(seeded, cent0), "fused sharded seeding differs from the all-reduce form"

@@ -59,7 +59,7 @@ PROTOTYPES = {
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),
     "et_kmeans_farthest_init_sharded": (_i, [_p, _i, _i, _l, _i, _l, _l, _l, _p, _p, _i, _i, _p, C.c_uint, _p]),
     "et_kmeans_seed_step": (_i, [_p, _p, _i, _i, _l, _i, _i, _p, _p]),
-    "et_kmeans_seed_candidate": (_i, [_p, _p, _i, _i, _l, _i, _i, _l, _p, _p]),
+    "et_kmeans_seed_candidate": (_i, [_p, _p, _i, _i, _l, _i, _i, _l, _l, _p, _p]),
     "et_kmeans_seed_fetch": (_i, [_p, _i, _i, _l, _l, _p, _p, _p]),
     "et_comm_unique_id": (_i, [_p]),
     "et_comm_init": (_i, [_i, _i, _p, _p]),

@@ -783,7 +783,8 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
                                                                       int k, int ncols,
                                                                       unsigned long long* __restrict__ scratch,
                                                                       const float* __restrict__ cent_in,
-                                                                      unsigned long long* __restrict__ key_out) {
+                                                                      unsigned long long* __restrict__ key_out,
+                                                                      int64_t col_offset, int64_t n_all) {
   __shared__ __align__(16) float cs[DMAX * KMAX];
   __shared__ __align__(16) float bn[KMAX];
   __shared__ unsigned long long wmin[KM_WARPS];
@@ -840,7 +841,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_seed_step_kernel(const floa
 #pragma unroll
       for (int r = 0; r < DMAX; ++r) a_next[r] = ((EXACT || r < d) && in < n) ? __ldg(dl + (int64_t)r * n + in) : 0.f;
     }
-    const float an[1] = {sumsq_torch_order<DMAX>(a[0], d, col_is_sequential(i, n))};
+    const float an[1] = {sumsq_torch_order<DMAX>(a[0], d, col_is_sequential(col_offset + i, n_all))};
     float best[1];
     int label[1];
     if (!scalar_only && fabsf(an[0]) <= KM_FAST_NORM_MAX)
@@ -1124,6 +1125,11 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
   unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
   double* parts = workspace ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128) : nullptr;
   if (fit.cent_out) fit.totals = parts + (size_t)sm_count() * 8 * ((size_t)k * (d + 1) + 1);   // behind the partial records
+  if (fit.cent_out) {
+    // whole-fit launches start from a clean barrier header whatever an earlier, aborted launch may have left behind
+    e = cudaMemsetAsync(workspace, 0, 128, st);
+    if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
   if (coop) {
     e = launch_cooperative(kern, grid, dim3(KM_THREADS_L), smem, st, data, centroids, d, n, k, labels, maxsims, sums, counts,
                            simsum, ctr, parts, status, labels_in, fit);
@@ -1194,14 +1200,18 @@ static int km_grid(int64_t n) {
 }
 
 static void launch_seed_step(dim3 grid, cudaStream_t st, const float* data, int d, int64_t n, int k, int ncols,
-                             unsigned long long* scratch, const float* cent_in, unsigned long long* key_out) {
+                             unsigned long long* scratch, const float* cent_in, unsigned long long* key_out,
+                             int64_t col_offset = 0, int64_t n_all = 0) {
+  if (n_all <= 0) n_all = n;      // the launch holds all columns
   if (d == 6 && k <= 32)
-    kmeans_seed_step_kernel<6, 32, true><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out);
+    kmeans_seed_step_kernel<6, 32, true><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out, col_offset,
+                                                                      n_all);
   else if (d <= 8 && k <= 32)
-    kmeans_seed_step_kernel<8, 32, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out);
+    kmeans_seed_step_kernel<8, 32, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch, cent_in, key_out, col_offset,
+                                                                       n_all);
   else
     kmeans_seed_step_kernel<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false><<<grid, KM_THREADS, 0, st>>>(data, d, n, k, ncols, scratch,
-                                                                                               cent_in, key_out);
+                                                                                               cent_in, key_out, col_offset, n_all);
 }
 
 // Launch the persistent seeding kernel if the points fit the blocks' shared memory and registers; returns 1 when the
@@ -1428,11 +1438,16 @@ int et_kmeans_farthest_init_sharded(const float* data, int l, int d, int64_t n_l
   return rc;
 }
 
+static int seed_step_impl(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
+                          unsigned long long* key_out, int64_t row_offset, int64_t n_global, et_stream_t stream);
+
 int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
-                             int64_t row_offset, long long* gkey_out, et_stream_t stream) {
-  ET_REQUIRE(row_offset >= 0 && row_offset + n <= ((int64_t)1 << 32), ET_ERR_UNSUPPORTED,
-             "et_kmeans_seed_candidate: global indices must stay below 2^32");
-  int rc = et_kmeans_seed_step(data, centroids, l, d, n, k_clusters, ncols, reinterpret_cast<unsigned long long*>(gkey_out), stream);
+                             int64_t row_offset, int64_t n_global, long long* gkey_out, et_stream_t stream) {
+  ET_REQUIRE(row_offset >= 0 && row_offset + n <= ((int64_t)1 << 32) && (n_global == 0 || n_global >= row_offset + n),
+             ET_ERR_UNSUPPORTED, "et_kmeans_seed_candidate: columns [%lld, %lld) of %lld: global indices must stay below 2^32",
+             (long long)row_offset, (long long)(row_offset + n), (long long)n_global);
+  int rc = seed_step_impl(data, centroids, l, d, n, k_clusters, ncols, reinterpret_cast<unsigned long long*>(gkey_out), row_offset,
+                          n_global, stream);
   if (rc) return rc;
   kmeans_seed_globalize_kernel<<<(l + 255) / 256, 256, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(gkey_out), l,
                                                                             (unsigned long long)row_offset);
@@ -1450,6 +1465,11 @@ int et_kmeans_seed_fetch(const float* data, int l, int d, int64_t n, int64_t row
 
 int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
                         unsigned long long* key_out, et_stream_t stream) {
+  return seed_step_impl(data, centroids, l, d, n, k_clusters, ncols, key_out, 0, 0, stream);
+}
+
+static int seed_step_impl(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters, int ncols,
+                          unsigned long long* key_out, int64_t row_offset, int64_t n_global, et_stream_t stream) {
   int rc = km_check(l, d, n, k_clusters);
   if (rc) return rc;
   ET_REQUIRE(key_out && (n == 0 || (data && centroids)), ET_ERR_BADARG, "et_kmeans_seed_step: null pointer");
@@ -1459,7 +1479,7 @@ int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d,
   if ((rc = check_launch("fill_u64_kernel"))) return rc;
   if (n == 0) return ET_OK;
   dim3 grid(km_grid(n), l);
-  launch_seed_step(grid, st, data, d, n, k_clusters, ncols, nullptr, centroids, key_out);
+  launch_seed_step(grid, st, data, d, n, k_clusters, ncols, nullptr, centroids, key_out, row_offset, n_global);
   return check_launch("kmeans_seed_step_kernel");
 }
 

@@ -838,12 +838,12 @@ def kmeans_seed_step(data, centroids, ncols):
     return raw.to(torch.uint32).view(torch.float32), idx
 
 
-def kmeans_seed_candidate(data, centroids, ncols, row_offset, out=None):
+def kmeans_seed_candidate(data, centroids, ncols, row_offset, out=None, n_global=0):
     """Global, signed-orderable candidate key (l,) int64 of a row shard (see et_kmeans_seed_candidate)."""
     l, d, n = data.shape
     k = centroids.size(-1)
     key = out if out is not None else torch.empty((l,), dtype=torch.int64, device=data.device)
-    check(load().et_kmeans_seed_candidate(ptr(data), ptr(centroids), l, d, n, k, int(ncols), int(row_offset), ptr(key),
+    check(load().et_kmeans_seed_candidate(ptr(data), ptr(centroids), l, d, n, k, int(ncols), int(row_offset), int(n_global), ptr(key),
                                           stream_of(data.device)), "et_kmeans_seed_candidate")
     return key
 

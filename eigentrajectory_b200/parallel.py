@@ -51,8 +51,8 @@ class CudaBackend:
     def labels(self, data, cent, row_offset=0, n_global=0):
         return ops.kmeans_assign(data, cent, want_labels=True, want_maxsims=False, row_offset=row_offset, n_global=n_global)[1]
 
-    def seed_candidate(self, data, cent, ncols, row_offset, out=None):
-        return ops.kmeans_seed_candidate(data, cent, ncols, row_offset, out=out)
+    def seed_candidate(self, data, cent, ncols, row_offset, out=None, n_global=0):
+        return ops.kmeans_seed_candidate(data, cent, ncols, row_offset, out=out, n_global=n_global)
 
     def seed_fetch(self, data, row_offset, gkey, out=None):
         return ops.kmeans_seed_fetch(data, row_offset, gkey, out=out)
@@ -93,12 +93,14 @@ def sharded_basis(obs_shard, pred_shard, k, ori=True, rot=True, sca=True, group=
     return U_obs, S_obs, U_pred, S_pred
 
 
-def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset, group=None, backend=None):
+def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset, group=None, backend=None, n_total=None):
     """The reference's farthest-point seeding (kmeans.py:78-112) over row shards.
 
     ``data_shard`` (l,d,n_local) holds global columns [row_offset, row_offset + n_local).  Per step: local
     candidate (lowest best-similarity, lowest index on ties) -> all-gather of (value, global index) -> the
-    global winner (lowest value, then lowest global index) -> its coordinates summed in from the owner."""
+    global winner (lowest value, then lowest global index) -> its coordinates summed in from the owner.
+    ``n_total`` (global column count): when given, the similarity arithmetic follows the global column numbering, i.e.
+    the picks are the same bits as seeding the unsharded tensor."""
     backend = backend or CudaBackend()
     rank, world = _world(group)
     l, d, n_local = data_shard.shape
@@ -123,7 +125,8 @@ def sharded_farthest_init(data_shard, n_clusters, first_global_index, row_offset
         coords = torch.empty((l, d), dtype=torch.float64, device=dev)
         for i in range(n_clusters):
             if i > 0:
-                gkey = backend.seed_candidate(data_shard, cent, i, row_offset, gkey)
+                gkey = (backend.seed_candidate(data_shard, cent, i, row_offset, gkey, n_global=int(n_total)) if n_total
+                        else backend.seed_candidate(data_shard, cent, i, row_offset, gkey))
                 if world > 1:
                     dist.all_reduce(gkey, op=dist.ReduceOp.MIN, group=group)
             backend.seed_fetch(data_shard, row_offset, gkey, coords)

@@ -310,10 +310,11 @@ int et_kmeans_seed_step(const float* data, const float* centroids, int l, int d,
  * et_kmeans_seed_step with the key made GLOBAL and signed-orderable (index + row_offset in the low 32 bits, top bit
  * flipped; an empty shard proposes INT64_MAX), so that ONE int64 MIN all-reduce over the ranks elects the winner;
  * et_kmeans_seed_fetch then writes the winner's coordinates (l,d) as float64 on the rank that owns the column and zeros
- * elsewhere, so that ONE SUM all-reduce hands them to every rank.  row_offset + n <= 2^32. */
+ * elsewhere, so that ONE SUM all-reduce hands them to every rank.  row_offset + n <= 2^32.  n_global (0: the shard is
+ * numbered on its own): the |a|^2 summation order then follows the global column numbering (as et_kmeans_assign_shard). */
 int et_kmeans_seed_candidate(const float* data, const float* centroids, int l, int d, int64_t n,
-                             int k_clusters, int ncols, int64_t row_offset, long long* gkey_out,
-                             et_stream_t stream);
+                             int k_clusters, int ncols, int64_t row_offset, int64_t n_global,
+                             long long* gkey_out, et_stream_t stream);
 int et_kmeans_seed_fetch(const float* data, int l, int d, int64_t n, int64_t row_offset,
                          const long long* gkey, double* coords, et_stream_t stream);
 

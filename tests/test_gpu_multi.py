@@ -38,7 +38,7 @@ def _worker(rank, world, port, use_nccl, out):
         # k-means on the pred coefficients of this data, sharded vs single device
         C = ops.to_et_space(ops.normalize(pred.to(dev), *ops.norm_params(obs.to(dev))), Up).unsqueeze(0).contiguous()
         first = 4242
-        cent0 = P.sharded_farthest_init(C[:, :, a:b].contiguous(), 20, first, a)
+        cent0 = P.sharded_farthest_init(C[:, :, a:b].contiguous(), 20, first, a, n_total=n)
         ref0 = ops.kmeans_farthest_init(C, 20, first)
         res["init_equal"] = bool(torch.equal(cent0, ref0))
         if use_nccl and P.peer_exchange_available(dev):       # the same seeding with the exchange inside one persistent kernel
