@@ -511,7 +511,7 @@ def main():
         }
         if stages is not None:
             line["stages"] = stages
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:       # (the CPU baseline is taken at N = 1 only: idle host cores)
             threads = os.cpu_count() or 1
             times, kind, what, used = cpu_times(n, 5, 1, threads)
             line["cpu_baseline"] = {"value": n / min(times), "unit": UNIT, "cores": used, "kind": kind,

@@ -1214,6 +1214,176 @@ static void launch_seed_step(dim3 grid, cudaStream_t st, const float* data, int 
                                                                                                cent_in, key_out, col_offset, n_all);
 }
 
+// ---- k-means++ seeding by D^2 sampling with greedy local trials, all K - 1 steps in ONE persistent launch -------------
+// What sklearn's KMeans(init="k-means++") does for ETAnchor.anchor_generation (anchor.py:65-71): the next centre is
+// drawn with probability proportional to the squared distance to the nearest centre chosen so far; `trials` candidates
+// are drawn per step and the one that lowers the total potential most is kept.  The random numbers come from the host
+// (uniform[l][K][trials] in [0, 1): [.,0,0] picks the first centre, [.,i,j] the j-th candidate of step i), everything
+// else runs here, deterministically: points resident in shared memory (a contiguous run of M points per thread, so the
+// cumulative sum that the sampling inverts runs in point order), the running D^2 in registers, all sums in float64 in
+// a fixed order.  Per step: block sums of D^2 -> grid barrier -> every block derives the total and its own offset, the
+// owners of the `trials` thresholds locate their candidates -> barrier -> potentials of the candidates -> barrier ->
+// every block picks the best candidate and updates its D^2.  (The algorithm, restated in numpy: oracle.kmeans_d2_seeding.)
+constexpr int SEEDD_THREADS = 1024;
+constexpr int SEEDD_MMAX = 9;               // resident points per thread (odd: the strided shared-memory reads are conflict-free)
+constexpr int SEEDD_TRIALS_MAX = 8;
+
+template <int DMAX, int KMAX, bool EXACT>
+__global__ void __launch_bounds__(SEEDD_THREADS, 1) kmeans_seed_d2_kernel(
+    const float* __restrict__ data, int d, int64_t n, int k, int trials, const double* __restrict__ uniform,
+    float* __restrict__ centroids, unsigned* __restrict__ barrier_ctr, double* __restrict__ partial /* [l][grid.x][trials] */,
+    long long* __restrict__ cand /* [l][trials] */, int pts_per_block) {
+  extern __shared__ __align__(16) float seedd_xs[];             // [d][pts_per_block]
+  __shared__ double wsum[SEEDD_THREADS / 32][SEEDD_TRIALS_MAX];
+  __shared__ double bvals[SEEDD_TRIALS_MAX + 2];
+  __shared__ float cxyz[SEEDD_TRIALS_MAX][DMAX];
+  if (EXACT) d = DMAX;
+  const int l = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = pts_per_block, M = SEEDD_MMAX;
+  const int64_t p0 = (int64_t)blockIdx.x * P;
+  const int np = (int)(n - p0 < P ? (n - p0 > 0 ? n - p0 : 0) : P);
+  const float* dl = data + (int64_t)l * d * n;
+  const double* ul = uniform + (size_t)l * k * trials;
+  double* pl = partial + (size_t)l * gridDim.x * trials;
+  long long* cl = cand + (size_t)l * trials;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  unsigned phase = 0;
+  for (int r = 0; r < d; ++r)
+    for (int t = tid; t < np; t += SEEDD_THREADS) seedd_xs[r * P + t] = __ldg(dl + (int64_t)r * n + p0 + t);
+  __syncthreads();
+
+  auto dist2 = [&](int t, const float* c) -> float {          // squared distance of resident point t to c[0..d)
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < DMAX; ++r)
+      if (EXACT || r < d) {
+        const float df = seedd_xs[r * P + t] - c[r];
+        acc = fmaf(df, df, acc);
+      }
+    return acc;
+  };
+  // block-wide sums of up to `cnt` doubles per thread, fixed order (xor tree inside a warp, then warps ascending)
+  auto block_sums = [&](double (&v)[SEEDD_TRIALS_MAX], int cnt) {
+    for (int j = 0; j < cnt; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+      if (lane == 0) wsum[warp][j] = v[j];
+    }
+    __syncthreads();
+    if (tid < cnt) {
+      double sacc = 0.0;
+      for (int w = 0; w < SEEDD_THREADS / 32; ++w) sacc += wsum[w][tid];
+      bvals[tid] = sacc;
+    }
+    __syncthreads();
+  };
+  auto load_centre = [&](int slot, int64_t gidx) {            // coordinates of global column gidx -> cxyz[slot]
+    if (tid < d) cxyz[slot][tid] = __ldg(dl + (int64_t)tid * n + gidx);
+  };
+
+  // centre 0: the point the first random number selects
+  int64_t first = (int64_t)(ul[0] * (double)n);
+  if (first > n - 1) first = n - 1;
+  if (first < 0) first = 0;
+  load_centre(0, first);
+  __syncthreads();
+  float d2[SEEDD_MMAX];
+#pragma unroll
+  for (int m = 0; m < SEEDD_MMAX; ++m) {
+    const int t = tid * M + m;
+    d2[m] = t < np ? dist2(t, cxyz[0]) : 0.f;
+  }
+  if (blockIdx.x == 0 && tid < d) centroids[((int64_t)l * d + tid) * k] = cxyz[0][tid];
+  __syncthreads();
+
+  for (int i = 1; i < k; ++i) {
+    // ---- A: block sum of D^2 ----
+    double v[SEEDD_TRIALS_MAX];
+    double mine = 0.0;
+#pragma unroll
+    for (int m = 0; m < SEEDD_MMAX; ++m) mine += (double)d2[m];
+    v[0] = mine;
+    block_sums(v, 1);
+    const double bsum = bvals[0];
+    if (tid == 0) pl[blockIdx.x * trials] = bsum;
+    km_barrier(barrier_ctr, nblocks, ++phase);
+    // ---- B: total, this block's offset, and the candidates whose thresholds fall into this block ----
+    double offset = 0.0, total = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) {
+      const double pb = __ldcg(pl + (size_t)b * trials);
+      if (b < (int)blockIdx.x) offset += pb;
+      total += pb;
+    }
+    // exclusive prefix of the per-thread sums in thread order (= point order)
+    double incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp][0] = incl;
+    __syncthreads();
+    double wpre = 0.0;
+    for (int w = 0; w < warp; ++w) wpre += wsum[w][0];
+    const double tpre = offset + wpre + (incl - mine);          // cumulative D^2 before this thread's first point
+    const bool last_block = blockIdx.x == gridDim.x - 1;
+    const bool last_thread = (int64_t)(tid + 1) * M >= np && (int64_t)tid * M < np;   // owns the block's last resident point
+    for (int j = 0; j < trials; ++j) {
+      const double thr = ul[(size_t)i * trials + j] * total;
+      // first point whose inclusive cumulative sum exceeds thr; the very last point catches rounding at the top end
+      const bool in_range = (thr >= tpre && thr < tpre + mine) || (last_block && last_thread && thr >= tpre + mine);
+      if (in_range && (int64_t)tid * M < np) {
+        double acc = tpre;
+        int pick = -1;
+#pragma unroll
+        for (int m = 0; m < SEEDD_MMAX; ++m) {
+          const int t = tid * M + m;
+          acc += (double)d2[m];
+          if (pick < 0 && t < np && acc > thr) pick = t;
+        }
+        if (pick < 0) pick = (np - 1 < tid * M + M - 1) ? np - 1 : tid * M + M - 1;
+        cl[j] = p0 + pick;
+      }
+    }
+    if (total <= 0.0 && blockIdx.x == 0 && tid == 0)            // every point coincides with a centre: take point 0
+      for (int j = 0; j < trials; ++j) cl[j] = 0;
+    km_barrier(barrier_ctr, nblocks, ++phase);
+    // ---- C: potential of every candidate ----
+    for (int j = 0; j < trials; ++j) load_centre(j, (int64_t)__ldcg(cl + j));
+    __syncthreads();
+    int best = 0;
+    if (trials > 1) {
+      for (int j = 0; j < trials; ++j) v[j] = 0.0;
+#pragma unroll
+      for (int m = 0; m < SEEDD_MMAX; ++m) {
+        const int t = tid * M + m;
+        if (t < np)
+          for (int j = 0; j < trials; ++j) v[j] += (double)fminf(d2[m], dist2(t, cxyz[j]));
+      }
+      block_sums(v, trials);
+      if (tid < trials) pl[blockIdx.x * trials + tid] = bvals[tid];
+      km_barrier(barrier_ctr, nblocks, ++phase);
+      // ---- D: the candidate with the lowest potential (lowest trial index on ties) ----
+      double best_pot = 0.0;
+      for (int j = 0; j < trials; ++j) {
+        double pot = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) pot += __ldcg(pl + (size_t)b * trials + j);
+        if (j == 0 || pot < best_pot) { best_pot = pot; best = j; }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SEEDD_MMAX; ++m) {
+      const int t = tid * M + m;
+      if (t < np) d2[m] = fminf(d2[m], dist2(t, cxyz[best]));
+    }
+    if (blockIdx.x == 0 && tid < d) centroids[((int64_t)l * d + tid) * k + i] = cxyz[best][tid];
+    // (the partial sums and candidate slots are rewritten only after the next barrier: no block can still be reading)
+    __syncthreads();
+  }
+  km_barrier_exit(barrier_ctr, nblocks);
+}
+
 // Launch the persistent seeding kernel if the points fit the blocks' shared memory and registers; returns 1 when the
 // caller has to take the launch-per-step path instead.
 template <int DMAX, int KMAX, bool EXACT>

@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 tag = sys.argv[1]
-pre = sys.argv[2] if len(sys.argv) > 2 else "r01"
+pre = sys.argv[2] if len(sys.argv) > 2 else "r02"
 
 
 def last_json_line(path):
@@ -35,6 +35,28 @@ shutil.copy(os.path.join(OUT, f"kernels_{tag}.json"), os.path.join(PROF, f"{pre}
 fl = [json.loads(x) for x in open(os.path.join(OUT, f"forward_latency_{tag}.log")) if x.startswith("{")]
 json.dump(fl, open(os.path.join(PROF, f"{pre}_forward_latency.json"), "w"), indent=1)
 
+# config 4, k-means / init quick numbers, sanitizer summaries, full test log tail
+for src, dst in ((f"config4_{tag}.log", f"{pre}_config4.jsonl"),):
+    if os.path.exists(os.path.join(OUT, src)):
+        open(os.path.join(PROF, dst), "w").write(last_json_line(os.path.join(OUT, src)) + "\n")
+for src, dst in ((f"km_quick_{tag}.log", f"{pre}_kmeans_quick.txt"), (f"init_quick_{tag}.log", f"{pre}_init_quick.txt")):
+    if os.path.exists(os.path.join(OUT, src)):
+        shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
+if os.path.exists(os.path.join(OUT, f"t_all_{tag}.log")):
+    keep = [x for x in open(os.path.join(OUT, f"t_all_{tag}.log")) if any(k in x for k in ("passed", "failed", "label mismatches", "worst relative", "scenes"))]
+    open(os.path.join(PROF, f"{pre}_gpu_tests.txt"), "w").write("".join(keep))
+san = []
+for tool in ("memcheck", "racecheck", "synccheck"):
+    path = os.path.join(OUT, f"r2_sanitize_{tool}.log")
+    if os.path.exists(path):
+        lines = [x.strip() for x in open(path) if "SUMMARY" in x or "sanitize target done" in x or "Internal Sanitizer Error" in x]
+        internal = sum("Internal Sanitizer Error" in x for x in lines)
+        lines = [x for x in lines if "Internal Sanitizer Error" not in x]
+        san.append(f"* `compute-sanitizer --tool {tool}` over `scripts/sanitize_target.py` (one small-N pass through every CUDA entry "
+                   f"point): {' / '.join(lines)}" + (f" ({internal} launches not tracked by the tool)" if internal else ""))
+if san:
+    open(os.path.join(PROF, f"{pre}_sanitizer.md"), "w").write(f"# {pre} compute-sanitizer summaries (scripts/gpu_sanitize.sh)\n\n" + "\n".join(san) + "\n")
+
 # launch list of the bench command
 src = os.path.join(OUT, f"launches_{tag}.csv")
 shutil.copy(src, os.path.join(PROF, f"{pre}_launches_bench.csv"))
@@ -56,7 +78,10 @@ with open(os.path.join(PROF, f"{pre}_launches_bench_summary.md"), "w") as f:
         f.write(f"| {name} | {cnt} | {us:.1f} | {100 * us / total:.1f}% |\n")
 
 # ncu summaries
-for rep, dst in ((f"prof_pr_{tag}.ncu-rep", f"{pre}_ncu_project_reconstruct_tma.md"), (f"prof_ops_{tag}.ncu-rep", f"{pre}_ncu_ops_{tag}.md")):
+for rep, dst in ((f"prof_pr_{tag}.ncu-rep", f"{pre}_ncu_project_reconstruct_tma.md"), (f"prof_ops_{tag}.ncu-rep", f"{pre}_ncu_ops.md"),
+                 (f"prof_lloyd_{tag}.ncu-rep", f"{pre}_ncu_kmeans_whole_fit.md")):
+    if not os.path.exists(os.path.join(OUT, rep)):
+        continue
     md = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), os.path.join(OUT, rep), "--md"],
                         capture_output=True, text=True).stdout
     open(os.path.join(PROF, dst), "w").write(md)

@@ -24,12 +24,12 @@ def per_iter(iters=100, reps=7):
         ts.append(e0.elapsed_time(e1) * 1e3 / iters)
     return [round(t, 2) for t in ts]
 
-print("whole-fit kernel, 12 warps, tournament arg-max: us per Lloyd iteration", per_iter())
+print("whole-fit kernel, 12 warps, ascending arg-max scan (default): us per Lloyd iteration", per_iter())
 lib.et_tune(6, 1)
-print("whole-fit kernel, 12 warps, serial arg-max:     us per Lloyd iteration", per_iter())
+print("whole-fit kernel, 12 warps, per-group tournament arg-max:     us per Lloyd iteration", per_iter())
 lib.et_tune(6, 0)
 ref_labels, ref_cent = ops.kmeans_lloyd(data, cent, acc, 30, -1.0)
-for w in (16, 20, 24):
+for w in (16,):
     lib.et_tune(7, w)
     print(f"whole-fit kernel, {w} warps on shared record columns: us per Lloyd iteration", per_iter())
     lab, c = ops.kmeans_lloyd(data, cent, acc, 30, -1.0)
