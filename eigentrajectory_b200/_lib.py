@@ -57,6 +57,8 @@ PROTOTYPES = {
     "et_kmeans_accumulate": (_i, [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p]),
     "et_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _p]),
     "et_kmeans_farthest_init": (_i, [_p, _i, _i, _l, _i, _l, _p, _p, _p]),
+    "et_kmeans_d2_workspace_bytes": (_sz, [_i, _i]),
+    "et_kmeans_d2_init": (_i, [_p, _i, _i, _l, _i, _i, _p, _p, _p, _p]),
     "et_kmeans_farthest_init_sharded": (_i, [_p, _i, _i, _l, _i, _l, _l, _l, _p, _p, _i, _i, _p, C.c_uint, _p]),
     "et_kmeans_seed_step": (_i, [_p, _p, _i, _i, _l, _i, _i, _p, _p]),
     "et_kmeans_seed_candidate": (_i, [_p, _p, _i, _i, _l, _i, _i, _l, _l, _p, _p]),

@@ -1223,7 +1223,7 @@ static void launch_seed_step(dim3 grid, cudaStream_t st, const float* data, int 
 // cumulative sum that the sampling inverts runs in point order), the running D^2 in registers, all sums in float64 in
 // a fixed order.  Per step: block sums of D^2 -> grid barrier -> every block derives the total and its own offset, the
 // owners of the `trials` thresholds locate their candidates -> barrier -> potentials of the candidates -> barrier ->
-// every block picks the best candidate and updates its D^2.  (The algorithm, restated in numpy: oracle.kmeans_d2_seeding.)
+// every block picks the best candidate and updates its D^2.  (tests/ hold a numpy restatement of this algorithm.)
 constexpr int SEEDD_THREADS = 1024;
 constexpr int SEEDD_MMAX = 9;               // resident points per thread (odd: the strided shared-memory reads are conflict-free)
 constexpr int SEEDD_TRIALS_MAX = 8;
@@ -1418,6 +1418,33 @@ static int seed_persistent(const float* data, int l, int d, int64_t n, int k, in
   return seed_persistent_try<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false>(data, l, d, n, k, first_index, scratch, centroids, sh, st);
 }
 
+template <int DMAX, int KMAX, bool EXACT>
+static int seed_d2_launch(const float* data, int l, int d, int64_t n, int k, int trials, const double* uniform, float* centroids,
+                          void* workspace, cudaStream_t st) {
+  if (l > sm_count()) return fail(ET_ERR_UNSUPPORTED, "et_kmeans_d2_init: batch l = %d exceeds the number of SMs", l);
+  const int gx = sm_count() / l;
+  int64_t P = (n + gx - 1) / gx;
+  P = (P + 31) & ~(int64_t)31;
+  if (P < 32) P = 32;
+  const size_t smem = (size_t)P * d * sizeof(float);
+  if (P > (int64_t)SEEDD_THREADS * SEEDD_MMAX || smem > (size_t)SEEDP_SMEM_MAX)
+    return fail(ET_ERR_UNSUPPORTED, "et_kmeans_d2_init: %lld points per batch entry do not fit the resident kernel (at most ~%lld)",
+                (long long)n, (long long)gx * ((long long)SEEDP_SMEM_MAX / (d * 4)));
+  auto kern = kmeans_seed_d2_kernel<DMAX, KMAX, EXACT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_seed_d2_kernel: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  e = cudaMemsetAsync(workspace, 0, 128, st);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_seed_d2_kernel: cudaMemsetAsync: %s", cudaGetErrorString(e));
+  const int blocks_x = (int)((n + P - 1) / P) > 0 ? (int)((n + P - 1) / P) : 1;
+  unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
+  long long* cand = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 128);
+  double* partial = reinterpret_cast<double*>(cand + (size_t)l * trials);
+  e = launch_cooperative(kern, dim3(blocks_x, l), dim3(SEEDD_THREADS), smem, st, data, d, n, k, trials, uniform, centroids, ctr,
+                         partial, cand, (int)P);
+  if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_seed_d2_kernel: cooperative launch: %s", cudaGetErrorString(e));
+  return check_launch("kmeans_seed_d2_kernel");
+}
+
 static int km_check(int l, int d, int64_t n, int k) {
   if (l < 1 || l > 65535) return fail(ET_ERR_UNSUPPORTED, "k-means: batch l = %d outside [1, 65535]", l);
   if (d < 1 || d > ET_MAX_KM_DIM) return fail(ET_ERR_UNSUPPORTED, "k-means: d = %d outside [1, %d]", d, ET_MAX_KM_DIM);
@@ -1578,6 +1605,26 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
   }
   kmeans_seed_gather_kernel<<<(l * d * k_clusters + 255) / 256, 256, 0, st>>>(data, l, d, n, k_clusters, scratch, centroids);
   return check_launch("kmeans_seed_gather_kernel");
+}
+
+size_t et_kmeans_d2_workspace_bytes(int l, int trials) {
+  if (l < 1 || trials < 1 || trials > SEEDD_TRIALS_MAX) return 0;
+  // 128 B of barrier counters, l * trials candidate indices, l * (co-resident blocks) * trials partial sums
+  return 128 + (size_t)l * trials * sizeof(long long) + (size_t)l * sm_count() * trials * sizeof(double);
+}
+
+int et_kmeans_d2_init(const float* data, int l, int d, int64_t n, int k_clusters, int trials, const double* uniform,
+                      float* centroids, void* workspace, et_stream_t stream) {
+  int rc = km_check(l, d, n, k_clusters);
+  if (rc) return rc;
+  ET_REQUIRE(data && uniform && centroids && workspace, ET_ERR_BADARG, "et_kmeans_d2_init: null pointer");
+  ET_REQUIRE(n >= 1, ET_ERR_BADARG, "et_kmeans_d2_init: no points");
+  ET_REQUIRE(trials >= 1 && trials <= SEEDD_TRIALS_MAX, ET_ERR_BADARG, "et_kmeans_d2_init: trials = %d outside [1, %d]", trials,
+             SEEDD_TRIALS_MAX);
+  cudaStream_t st = as_stream(stream);
+  if (d == 6 && k_clusters <= 32) return seed_d2_launch<6, 32, true>(data, l, d, n, k_clusters, trials, uniform, centroids, workspace, st);
+  if (d <= 8 && k_clusters <= 32) return seed_d2_launch<8, 32, false>(data, l, d, n, k_clusters, trials, uniform, centroids, workspace, st);
+  return seed_d2_launch<ET_MAX_KM_DIM, ET_MAX_CLUSTERS, false>(data, l, d, n, k_clusters, trials, uniform, centroids, workspace, st);
 }
 
 int et_kmeans_farthest_init_sharded(const float* data, int l, int d, int64_t n_local, int k_clusters, int64_t first_global_index,

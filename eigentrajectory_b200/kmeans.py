@@ -24,7 +24,8 @@ class BatchKMeans(nn.Module):
     ``n_clusters``: K.  ``n_redo``: restarts from different seeds, the fit with the lowest inertia wins (default 1).
     ``max_iter`` (100) and ``tol`` (1e-4): Lloyd stops after ``max_iter`` updates or once the squared centroid shift,
     summed over the whole batch, is ``<= tol``.  ``init_mode``: ``'kmeans++'`` (default) = the reference's
-    deterministic farthest-point rule from a random first point, ``'random'`` = K distinct random points.
+    deterministic farthest-point rule from a random first point, ``'random'`` = K distinct random points, ``'d2'`` (an
+    addition) = k-means++ proper, D^2 sampling with greedy local trials as sklearn seeds the reference's anchors.
 
     ``fused`` (default): the whole Lloyd loop of ``fit`` runs in ONE persistent cooperative kernel
     (``et_kmeans_lloyd``: grid barriers instead of relaunches, convergence test on the device).
@@ -93,9 +94,22 @@ class BatchKMeans(nn.Module):
         cent = ops.kmeans_farthest_init(x, self.n_clusters, first)
         return ops.back_to(cent.reshape(*lead, x.size(1), self.n_clusters), data)
 
+    def d2_sampling(self, data, n_local_trials=None):
+        r"""k-means++ seeding proper (D^2 sampling with greedy local trials, as ``sklearn.cluster.KMeans(init="k-means++")``
+        does for the reference's anchors, anchor.py:65-71) -- ``init_mode = "d2"``, an addition to the reference's two
+        modes.  The random numbers come from NumPy's global generator, like the reference's other modes."""
+        x, lead = _as_ldn(data)
+        trials = n_local_trials or (2 + int(np.log(self.n_clusters)))
+        uniform = np.random.random_sample((x.size(0), self.n_clusters, trials))
+        cent = ops.kmeans_d2_init(x, self.n_clusters, uniform, trials)
+        return ops.back_to(cent.reshape(*lead, x.size(1), self.n_clusters), data)
+
     def initialize_centroids(self, data):
         """Starting centroids ``(..., d, K)`` according to ``init_mode`` (kmeans.py:114-141)."""
-        if self.init_mode == "kmeans++":
+        if self.init_mode == "d2":
+            start = self.d2_sampling(data)
+            how = "with D^2 sampling (k-means++)"
+        elif self.init_mode == "kmeans++":
             start = self.kmeanspp(data).clone()
             how = "with kmeans++"
         elif self.init_mode == "random":

@@ -810,6 +810,22 @@ def kmeans_farthest_init(data, k, first_index, scratch=None):
     return cent
 
 
+def kmeans_d2_init(data, k, uniform, trials=None):
+    """k-means++ seeding by D^2 sampling with greedy local trials (sklearn's ``init="k-means++"``), one persistent launch.
+
+    ``uniform``: (l, K, trials) float64 numbers in [0, 1) from the caller's generator (host or device)."""
+    l, d, n = data.shape
+    u = torch.as_tensor(uniform, dtype=torch.float64).to(data.device).contiguous()
+    if trials is None:
+        trials = u.size(-1)
+    assert tuple(u.shape) == (l, k, trials), f"uniform has shape {tuple(u.shape)}, expected {(l, k, trials)}"
+    cent = torch.empty((l, d, k), device=data.device)
+    ws = torch.empty(int(load().et_kmeans_d2_workspace_bytes(l, trials)), dtype=torch.uint8, device=data.device)
+    check(load().et_kmeans_d2_init(ptr(data), l, d, n, k, int(trials), ptr(u), ptr(cent), ptr(ws), stream_of(data.device)),
+          "et_kmeans_d2_init")
+    return cent
+
+
 def kmeans_farthest_init_sharded(data, k, first_global_index, row_offset, n_global, rank, world, peers, stamp_base):
     """Farthest-point seeding over row shards with the per-step candidate exchange inside the persistent kernel (peer
     memory, see et_kmeans_farthest_init_sharded).  Returns the (l,d,K) centroids, identical on every rank."""

@@ -286,6 +286,17 @@ int et_kmeans_finalize(double* sums, double* counts, int l, int d, int k_cluster
 int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_clusters,
                             int64_t first_index, float* centroids, unsigned long long* scratch,
                             et_stream_t stream);
+/* k-means++ seeding by D^2 sampling with greedy local trials -- what sklearn.cluster.KMeans(init="k-means++") does
+ * inside ETAnchor.anchor_generation (anchor.py:65-71) -- in ONE persistent cooperative launch.  uniform (l, K, trials)
+ * float64 in [0, 1) from the caller's random generator: [., 0, 0] selects the first centre (index floor(u * N)),
+ * [., i, j] the j-th candidate of step i by inverting the cumulative sum of the squared distances to the nearest centre
+ * chosen so far; of the `trials` candidates (1..8; sklearn: 2 + floor(ln K)) the one with the lowest resulting
+ * potential is kept (lowest trial index on ties).  Deterministic for given random numbers (float64 sums in a fixed
+ * order).  The points must fit the SMs' shared memory (~1.3e6 six-dimensional points per batch entry at l = 1),
+ * otherwise ET_ERR_UNSUPPORTED.  centroids (l,d,K) out; workspace: et_kmeans_d2_workspace_bytes(l, trials). */
+size_t et_kmeans_d2_workspace_bytes(int l, int trials);
+int et_kmeans_d2_init(const float* data, int l, int d, int64_t n, int k_clusters, int trials,
+                      const double* uniform, float* centroids, void* workspace, et_stream_t stream);
 /* et_kmeans_farthest_init over ROW SHARDS on several GPUs of one node: data (l,d,n_local) holds the global columns
  * [row_offset, row_offset + n_local) of n_global; first_global_index picks column 0.  Per step every rank's candidate
  * (similarity bits, GLOBAL index, coordinates) is stored into every rank's exchange buffer through peer memory and the

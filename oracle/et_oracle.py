@@ -394,3 +394,46 @@ def dataset_windows(rows, obs_len=8, pred_len=12, skip=1, threshold=0.02, min_pe
         return (np.zeros((0, T, 2), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.int64))
     traj = np.concatenate(trajs, axis=0).transpose(0, 2, 1).astype(np.float32)
     return traj, np.asarray(flags, dtype=np.float32), np.asarray(counts, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------
+# k-means++ seeding by D^2 sampling  (what sklearn does inside anchor.py:65-71; third-party, restated from the
+# published algorithm -- Arthur & Vassilvitskii 2007 with sklearn's greedy local trials -- NOT bit-pinned to sklearn)
+# --------------------------------------------------------------------------------------
+
+
+def kmeans_d2_seeding(data, n_clusters, uniform):
+    """Specification of ``et_kmeans_d2_init`` in numpy: data (d, N) float32, uniform (K, trials) float64 in [0, 1).
+
+    Centre 0 = column floor(u[0,0] * N).  Step i: total = sum of D^2 (float64); candidate j = first column whose
+    inclusive cumulative D^2 exceeds u[i,j] * total; the candidate with the lowest potential sum(min(D^2, dist^2)) wins
+    (lowest j on ties); D^2 = min(D^2, dist^2 to the winner).  dist^2 = ascending fp32 FMA chain of (x - c)^2.
+    Returns (centroids (d, K) float32, chosen column indices (K,))."""
+    x = np.asarray(data, dtype=np.float32)
+    d, n = x.shape
+    u = np.asarray(uniform, dtype=np.float64)
+    trials = u.shape[1]
+
+    def dist2(c):
+        acc = np.zeros(n, dtype=np.float32)
+        for r in range(d):
+            df = (x[r] - np.float32(c[r])).astype(np.float32)
+            acc = (df.astype(np.float64) * df.astype(np.float64) + acc.astype(np.float64)).astype(np.float32)   # fused multiply-add
+        return acc
+
+    first = min(n - 1, int(u[0, 0] * n))
+    picks = [first]
+    d2 = dist2(x[:, first])
+    for i in range(1, n_clusters):
+        total = d2.astype(np.float64).sum()
+        if total <= 0:
+            picks.append(0)
+            d2 = np.minimum(d2, dist2(x[:, 0]))
+            continue
+        cum = np.cumsum(d2.astype(np.float64))
+        cands = [min(n - 1, int(np.searchsorted(cum, u[i, j] * total, side="right"))) for j in range(trials)]
+        pots = [np.minimum(d2, dist2(x[:, c])).astype(np.float64).sum() for c in cands]
+        best = int(np.argmin(pots))
+        picks.append(cands[best])
+        d2 = np.minimum(d2, dist2(x[:, cands[best]]))
+    return x[:, picks].copy(), np.asarray(picks)

@@ -608,15 +608,71 @@ def test_model_forward_empty_groups_and_host_tensors(et):
 
 
 def test_anchor_generation_quality_vs_sklearn(et):
-    """anchor.py:65-71 uses sklearn KMeans (n_init = 10): parity is statistical -- our inertia must be comparable."""
-    sk = pytest.importorskip("sklearn.cluster")
+    """anchor.py:65-71 calls sklearn KMeans(random_state=0, init="k-means++", n_init=10): third-party, not bit-reproducible
+    -- parity is statistical.  The GPU anchor fit (ten D^2-sampling restarts + ten farthest-point restarts, best inertia)
+    must reach sklearn's inertia, frozen in tests/golden/anchor_inertia.json for every scene x group, within 1 %
+    (measured: 0.998 .. 1.003 for the farthest-point restarts alone on nine of the ten groups, 1.06 on univ/static, which
+    the D^2-sampling restarts bring to 1.005)."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "anchor_inertia.json")))["groups"]
     obs, pred, mask = eth_init_groups()
-    d = et.ETDescriptor(et.DotDict(HP), norm_sca=True).cuda()
-    pred_norm, U_pred = d.parameter_initialization(obs[mask].cuda(), pred[mask].cuda())
-    a = et.ETAnchor(et.DotDict(HP)).cuda()
-    a.anchor_generation(pred_norm, U_pred)
-    assert a.C_anchor.shape == (6, 20) and torch.isfinite(a.C_anchor).all()
-    C = d.to_ET_space(pred_norm, U_pred).T.cpu().numpy()                       # (N, 6)
-    ours = ((C[:, None, :] - a.C_anchor.detach().cpu().numpy().T[None]) ** 2).sum(-1).min(1).sum()
-    ref = sk.KMeans(n_clusters=20, random_state=0, init="k-means++", n_init=10).fit(C).inertia_
-    assert ours <= 1.10 * ref, (ours, ref)
+    for tag, m, sca in (("moving", mask, True), ("static", ~mask, False)):
+        d = et.ETDescriptor(et.DotDict(HP), norm_sca=sca).cuda()
+        pred_norm, U_pred = d.parameter_initialization(obs[m].cuda(), pred[m].cuda())
+        a = et.ETAnchor(et.DotDict(HP)).cuda()
+        a.anchor_generation(pred_norm, U_pred)
+        assert a.C_anchor.shape == (6, 20) and torch.isfinite(a.C_anchor).all()
+        C = d.to_ET_space(pred_norm, U_pred).T.cpu().double().numpy()                     # (N, 6)
+        ours = ((C[:, None, :] - a.C_anchor.detach().cpu().double().numpy().T[None]) ** 2).sum(-1).min(1).sum()
+        ref = gold[f"eth/{tag}"]
+        assert C.shape[0] == ref["n"]
+        ratio = ours / ref["sklearn_inertia"]
+        print(f"anchors eth/{tag}: inertia {ours:.2f} vs sklearn {ref['sklearn_inertia']:.2f} (ratio {ratio:.4f})")
+        assert ratio <= 1.01, (tag, ours, ref)
+        assert abs(a.inertia_ - ours) <= 1e-3 * ours
+        # each seeding family alone
+        for mode in ("d2", "kmeans++"):
+            b = et.ETAnchor(et.DotDict(HP)).cuda()
+            b.init_modes = (mode,)
+            b.anchor_generation(pred_norm, U_pred)
+            assert b.inertia_ <= 1.03 * ref["sklearn_inertia"], (tag, mode, b.inertia_)
+
+
+@pytest.mark.parametrize("l,d,k,n,trials", [(1, 6, 20, 5000, 4), (1, 6, 20, 1, 4), (1, 6, 20, 37, 1), (2, 5, 7, 3000, 3),
+                                            (1, 16, 40, 2000, 2), (1, 6, 20, 1_000_000, 4), (3, 6, 20, 9000, 8)])
+def test_kmeans_d2_seeding_exact_on_integer_data(et, O, l, d, k, n, trials):
+    """et_kmeans_d2_init against its numpy specification (oracle.kmeans_d2_seeding).  On integer-valued data every squared
+    distance and every float64 sum is exact whatever the summation order, so the picks must be identical."""
+    rng = np.random.RandomState(l * 100 + d + k + trials)
+    data = torch.from_numpy(rng.randint(-8, 9, size=(l, d, n)).astype(np.float32))
+    uniform = rng.random_sample((l, k, trials))
+    cent = et.ops.kmeans_d2_init(data.cuda(), k, uniform, trials)
+    again = et.ops.kmeans_d2_init(data.cuda(), k, uniform, trials)
+    assert torch.equal(cent, again)
+    for li in range(l):
+        want, picks = O.kmeans_d2_seeding(data[li].numpy(), k, uniform[li])
+        assert np.array_equal(cent[li].cpu().numpy(), want), (li, picks[:5])
+
+
+def test_kmeans_d2_seeding_properties(et):
+    """Real-valued data: deterministic for given random numbers, every centre is a data column, the first one is the
+    column the first random number selects, and well separated blobs each receive a centre."""
+    rng = np.random.RandomState(3)
+    centres = rng.randn(20, 6) * 30
+    data = (centres[rng.randint(0, 20, size=40_000)] + rng.randn(40_000, 6)).T.astype(np.float32)     # (6, N)
+    x = torch.from_numpy(np.ascontiguousarray(data))[None].cuda()
+    u = rng.random_sample((1, 20, 4))
+    c1 = et.ops.kmeans_d2_init(x, 20, u)
+    assert torch.equal(c1, et.ops.kmeans_d2_init(x, 20, u))
+    cols = c1[0].T.cpu().numpy()                                           # (20, 6)
+    first = min(40_000 - 1, int(u[0, 0, 0] * 40_000))
+    assert np.array_equal(cols[0], data[:, first])
+    for c in cols:
+        assert (np.abs(data.T - c).max(axis=1) == 0).any()                 # exactly one of the points
+    nearest = ((cols[:, None, :] - centres[None]) ** 2).sum(-1).argmin(1)
+    assert len(set(nearest.tolist())) >= 19                                 # (k-means++ hits every blob almost surely)
+    km = et.BatchKMeans(n_clusters=20, init_mode="d2", max_iter=20)
+    np.random.seed(0)
+    labels = km.fit(x)
+    assert labels.shape == (1, 40_000) and km.inertia_ < 8.0                # ~6 = the blobs' own variance in 6-D
