@@ -1231,7 +1231,7 @@ constexpr int SEEDD_TRIALS_MAX = 8;
 template <int DMAX, int KMAX, bool EXACT>
 __global__ void __launch_bounds__(SEEDD_THREADS, 1) kmeans_seed_d2_kernel(
     const float* __restrict__ data, int d, int64_t n, int k, int trials, const double* __restrict__ uniform,
-    float* __restrict__ centroids, unsigned* __restrict__ barrier_ctr, double* __restrict__ partial /* [l][grid.x][trials] */,
+    float* __restrict__ centroids, unsigned* __restrict__ barrier_ctr, double* __restrict__ partial /* [l][grid.x][trials + 1] */,
     long long* __restrict__ cand /* [l][trials] */, int pts_per_block) {
   extern __shared__ __align__(16) float seedd_xs[];             // [d][pts_per_block]
   __shared__ double wsum[SEEDD_THREADS / 32][SEEDD_TRIALS_MAX];
@@ -1244,7 +1244,10 @@ __global__ void __launch_bounds__(SEEDD_THREADS, 1) kmeans_seed_d2_kernel(
   const int np = (int)(n - p0 < P ? (n - p0 > 0 ? n - p0 : 0) : P);
   const float* dl = data + (int64_t)l * d * n;
   const double* ul = uniform + (size_t)l * k * trials;
-  double* pl = partial + (size_t)l * gridDim.x * trials;
+  // block partials: the D^2 sums (phase A) and the candidate potentials (phase C) live in separate arrays -- a block that
+  // is already in phase A of the next step must not overwrite what a slower block still reads in phase D of this one
+  double* sl = partial + (size_t)l * gridDim.x * (trials + 1);       // [grid.x] sums of D^2
+  double* pl = sl + gridDim.x;                                        // [grid.x][trials] potentials
   long long* cl = cand + (size_t)l * trials;
   const unsigned nblocks = gridDim.x * gridDim.y;
   unsigned phase = 0;
@@ -1305,12 +1308,12 @@ __global__ void __launch_bounds__(SEEDD_THREADS, 1) kmeans_seed_d2_kernel(
     v[0] = mine;
     block_sums(v, 1);
     const double bsum = bvals[0];
-    if (tid == 0) pl[blockIdx.x * trials] = bsum;
+    if (tid == 0) sl[blockIdx.x] = bsum;
     km_barrier(barrier_ctr, nblocks, ++phase);
     // ---- B: total, this block's offset, and the candidates whose thresholds fall into this block ----
     double offset = 0.0, total = 0.0;
     for (int b = 0; b < (int)gridDim.x; ++b) {
-      const double pb = __ldcg(pl + (size_t)b * trials);
+      const double pb = __ldcg(sl + b);
       if (b < (int)blockIdx.x) offset += pb;
       total += pb;
     }
@@ -1378,7 +1381,8 @@ __global__ void __launch_bounds__(SEEDD_THREADS, 1) kmeans_seed_d2_kernel(
       if (t < np) d2[m] = fminf(d2[m], dist2(t, cxyz[best]));
     }
     if (blockIdx.x == 0 && tid < d) centroids[((int64_t)l * d + tid) * k + i] = cxyz[best][tid];
-    // (the partial sums and candidate slots are rewritten only after the next barrier: no block can still be reading)
+    // (sl[] is next written after this step's last barrier and read before the next step's second one; pl[] and the
+    // candidate slots are written only behind the next step's first barrier: no block can still be reading them)
     __syncthreads();
   }
   km_barrier_exit(barrier_ctr, nblocks);
@@ -1610,7 +1614,7 @@ int et_kmeans_farthest_init(const float* data, int l, int d, int64_t n, int k_cl
 size_t et_kmeans_d2_workspace_bytes(int l, int trials) {
   if (l < 1 || trials < 1 || trials > SEEDD_TRIALS_MAX) return 0;
   // 128 B of barrier counters, l * trials candidate indices, l * (co-resident blocks) * trials partial sums
-  return 128 + (size_t)l * trials * sizeof(long long) + (size_t)l * sm_count() * trials * sizeof(double);
+  return 128 + (size_t)l * trials * sizeof(long long) + (size_t)l * sm_count() * (trials + 1) * sizeof(double);
 }
 
 int et_kmeans_d2_init(const float* data, int l, int d, int64_t n, int k_clusters, int trials, const double* uniform,

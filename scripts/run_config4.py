@@ -75,6 +75,7 @@ def main(scene="zara1", quiet=False):
     torch.cuda.synchronize()
     init_ours_s = time.perf_counter() - t0
     state = {k: v.detach().clone() for k, v in ours.model.state_dict().items()}
+    anchors = {"moving": ours.model.ET_m_anchor.inertia_, "static": ours.model.ET_s_anchor.inertia_}
     launches = et.launch_count()
     vals_b, means_b, t_b = run_test(ours)
     launches = et.launch_count() - launches
@@ -92,7 +93,7 @@ def main(scene="zara1", quiet=False):
     out = {"config": "configs[3]: ET-SGCN evaluation loop, " + scene + " test split", "scenes": scenes, "pedestrians": peds,
            "init_descriptor_ours_ms": 1e3 * init_ours_s, "init_rows": int(obs.shape[0]),
            "ms_per_scene_reference_l2": 1e3 * t_a / scenes, "ms_per_scene_ours": 1e3 * t_b / scenes,
-           "speedup": t_a / t_b, "library_launches_per_scene": launches / (2 * scenes)}
+           "speedup": t_a / t_b, "library_launches_per_scene": launches / (2 * scenes), "anchor_inertia": anchors}
     for k in ("ADE", "FDE", "TCC", "COL"):
         a, b = vals_a[k], vals_b[k]
         assert a.shape == b.shape

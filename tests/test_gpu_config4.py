@@ -28,3 +28,11 @@ def test_sgcn_zara1_evaluation_loop_matches_reference():
     assert out["COL"]["max_abs_diff"] == 0.0, out["COL"]
     assert out["TCC"]["max_abs_diff"] <= 1e-4, out["TCC"]
     assert out["library_launches_per_scene"] == 4.0      # project + reconstruct, one metrics pass + COL
+    # the anchors of the initialisation (GPU k-means, D^2-sampling + farthest-point restarts) against sklearn's inertia on
+    # the same train + val coefficients, frozen in tests/golden/anchor_inertia.json
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "anchor_inertia.json")))["groups"]
+    for tag in ("moving", "static"):
+        ratio = out["anchor_inertia"][tag] / gold[f"zara1/{tag}"]["sklearn_inertia"]
+        print(f"anchors zara1/{tag}: ratio to sklearn {ratio:.4f}")
+        assert ratio <= 1.01, (tag, ratio)
