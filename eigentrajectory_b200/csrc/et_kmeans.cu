@@ -972,8 +972,9 @@ __global__ void __launch_bounds__(SEEDP_THREADS, 1) kmeans_seed_persistent_kerne
   for (int i = 0; i < k; ++i) {                                    // elect column i
     if (i > 0) {
       // columns whose similarities must be (re)computed this step: all of them when a norm changes its summation order
-      bool full = (i == 1);
-      for (int j = 0; j + 1 < i; ++j) full = full || (col_is_sequential(j, i - 1) != col_is_sequential(j, i));
+      // (col_is_sequential(j, ncols) changes for an existing column j exactly when ncols reaches 4, 8 or 32)
+      const bool full = i == 1 || i == 4 || i == 8 || i == 32;
+      static_assert(ET_MAX_CLUSTERS <= 64, "the regime boundaries above cover up to 64 columns");
       const int jlo = full ? 0 : i - 1;
       if (tid >= jlo && tid < i) {
         float v[DMAX];
