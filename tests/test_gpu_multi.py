@@ -100,7 +100,9 @@ def test_sharded_basis_kmeans_metrics(world):
     mp.spawn(_worker, args=(world, port, use_nccl, out), nprocs=world, join=True)
     rs = [out[r] for r in range(world)]
     for r in rs:
-        assert r["S_err"] < 1e-6 and r["P_err"] < 1e-6
+        # sharded vs unsharded basis: the fp64 Gram sums differ in their last bits with the partition, which moves single
+        # fp32 ulps of U (24 x 6 entries, 6e-8 each: projector distance up to ~2e-6, measured 1.3e-6 at 8 ranks)
+        assert r["S_err"] < 1e-6 and r["P_err"] < 5e-6, (r["S_err"], r["P_err"])
         assert r["init_equal"] and r["init_vs_oracle"] in (None, True)
         assert r["label_mismatch"] <= 4 and r["cent_err"] < 1e-4
         assert r["iters"][0] == r["iters"][1]
