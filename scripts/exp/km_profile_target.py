@@ -1,6 +1,6 @@
 """ncu target: one whole-fit launch (10 Lloyd iterations, 1e6 points, K = 20) after two warm-up launches."""
 import os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import eigentrajectory_b200 as et
 from eigentrajectory_b200 import ops
 dev = torch.device("cuda")

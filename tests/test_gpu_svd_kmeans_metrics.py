@@ -535,6 +535,7 @@ def test_model_forward_matches_reference(et):
     hp = et.DotDict(dict(HP))
     sd = {k[3:]: t(g[k]) for k in g.files if k.startswith("sd_")}
     obs, pred = t(g["obs"]).cuda(), t(g["pred"]).cuda()
+    states = {}
     for fused in (True, False):          # two kernels without mask gathers / the reference's gather-scatter structure
         model = et.EigenTrajectory(Stub(), hook, hp).cuda()
         model.fused = fused
@@ -552,6 +553,17 @@ def test_model_forward_matches_reference(et):
         assert rel_max(model.baseline_model.W.grad.cpu(), g["grad_W"]) < 2e-5
         test_out = model(obs)
         assert rel_max(test_out["recon_traj"].detach().cpu(), g["recon_test"]) < TOL and "loss_eigentraj" not in test_out
+        # after a forward each group's normaliser holds the state of ITS rows, as after the reference's projection()
+        # calls (model.py:80-81) -- in the fused path as a deferred row selection that materialises on first read
+        moving = model._moving_mask(obs)
+        states[fused] = [(getattr(dsc.traj_normalizer, name), int(rows.sum())) for dsc, rows in
+                         ((model.ET_m_descriptor, moving), (model.ET_s_descriptor, ~moving)) for name in ("traj_ori", "traj_rot")]
+        assert all(v.shape[0] == n_rows for v, n_rows in states[fused])
+        assert model.ET_s_descriptor.traj_normalizer.traj_sca is None or not model.ET_s_descriptor.traj_normalizer.sca
+        rec_again = model.ET_m_descriptor.reconstruction(torch.zeros(6, int(moving.sum()), 20, device="cuda"))
+        assert rec_again.shape == (20, int(moving.sum()), 12, 2)
+    for (a, _), (b, _) in zip(states[True], states[False]):
+        assert rel_max(a.cpu(), b.cpu()) < 1e-6
     # calculate_parameters runs end to end on the device and yields orthonormal bases + finite anchors
     model2 = et.EigenTrajectory(Stub(), hook, hp).cuda()
     model2.calculate_parameters(t(g["init_obs"]).cuda(), t(g["init_pred"]).cuda())
