@@ -183,6 +183,7 @@ __device__ __forceinline__ void best_centroid_packed(const float (&a)[PPL][DMAX]
 constexpr int KM_WARPS = 4;                 // warps per block of the seeding kernel and the default assign kernel
 constexpr int KM_THREADS = KM_WARPS * 32;
 constexpr float KM_FAST_NORM_MAX = 1.0e37f;   // squared norms up to here take the packed fast path
+constexpr int KM_FOLD_GROUP = 4;     // blocks that share the grid fold of the whole-fit kernel (each folds a quarter of the entries)
 constexpr int KM_FLUSH_EVERY = 64;   // batches of 32 points a lane accumulates in fp32 before folding into fp64
 
 // Whole-fit mode of the assign kernel: with cent_out != null the kernel runs the complete Lloyd loop of
@@ -193,6 +194,9 @@ struct KmLloyd {
   double tol;
   float* cent_out;          // (l,d,K) centroids after the last update
   double* totals;           // scratch: l * (K (d+1) + 1) folded sums, then l per-entry errors
+  size_t part_stride;       // doubles between the two alternating partial arrays of the whole-fit mode
+  double* gtot;             // scratch: one folded record per group of KM_FOLD_GROUP blocks
+  unsigned* gctr;           // one arrival counter per group (zeroed before the launch)
   double* err;              // [1] sum (old - new)^2 of the last iteration (over all l, as calculate_error)
   int32_t* status;          // [2] {converged, iterations done}
   double* simsum_last;      // (l) sum of best similarities of the last assignment
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
   const float* dl = data + (int64_t)l * d * n;
   const int out_rec = rec + 1;
   const unsigned nblocks = gridDim.x * gridDim.y;
-  unsigned phase = 0;
+  unsigned phase = 0, gphase = 1;
   double accp[NJP][2], accs[NJS];
   double sim_acc = 0.0;
 
@@ -593,7 +597,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     __syncthreads();
     for (int e = lane; e < 2 * (rec + 1); e += 32) lanerec[e] = 0.f;        // the staging words are lane records again
     // partial records are stored entry-major ([l][entry][block]) so that the fold below reads contiguous doubles
-    double* lpart = partials + (size_t)l * gridDim.x * out_rec;
+    // (whole-fit mode alternates between two partial arrays: a block that is already writing the partials of iteration
+    // it + 1 must not disturb a slower block that still folds those of iteration it -- only ONE grid barrier separates them)
+    double* lpart = partials + (whole_fit ? (size_t)(it & 1) * fit.part_stride : 0) + (size_t)l * gridDim.x * out_rec;
     for (int e = tid; e < out_rec; e += THREADS) lpart[(size_t)e * gridDim.x + blockIdx.x] = blk[e];
     if (!whole_fit) {
       // ---- grid fold: every warp of this batch entry's blocks sums a few record entries over its blocks' partials ----
@@ -613,16 +619,26 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
       break;
     }
 
-    // ---- whole-fit mode: ONE grid barrier per iteration.  Behind it every block folds ALL record entries of its batch
-    // entry itself (same warp_fold_contig over the same entry-major partials as the launch-per-iteration path, hence the
-    // same bits) into its own shared memory -- no folded totals travel through global memory and no second barrier
-    // separates "fold" from "use".  Then division, error and convergence test, identically in every block
+    // ---- whole-fit mode: ONE grid barrier per iteration.  Behind it the blocks fold the record entries in groups of
+    // KM_FOLD_GROUP: every member folds its share of the entries over ALL block partials (the same warp_fold_contig over
+    // the same entry-major partials as the launch-per-iteration path, hence the same bits), writes them to the group's
+    // record, the group synchronises among its few members, and every member reads the complete record.  Every group
+    // computes the same totals, so no result crosses groups and no second GRID barrier is needed; compared with every
+    // block folding everything (148 x 141 x 148 doubles = 24.7 MB of L2 reads per iteration, 4.4 us) the fold traffic
+    // drops by the group size.  Then division, error and convergence test, identically in every block
     // (compute_centroids' division kmeans.py:183, calculate_error kmeans.py:45-51, `if error <= self.tol: break` :239).
     km_barrier(barrier_ctr + 2, nblocks, ++phase);
     {
-      constexpr int NE = 8;                       // entries folded together (their loads overlap)
-      const int per_warp = (out_rec + WARPS - 1) / WARPS;
-      const int e_lo = warp * per_warp, e_hi = e_lo + per_warp < out_rec ? e_lo + per_warp : out_rec;
+      const int gid = blockIdx.x / KM_FOLD_GROUP, g0 = gid * KM_FOLD_GROUP;
+      const int gsz = (int)gridDim.x - g0 < KM_FOLD_GROUP ? (int)gridDim.x - g0 : KM_FOLD_GROUP;
+      const int ngroups = ((int)gridDim.x + KM_FOLD_GROUP - 1) / KM_FOLD_GROUP;
+      const int member = blockIdx.x - g0;
+      const int per_member = (out_rec + gsz - 1) / gsz;
+      const int m_lo = member * per_member, m_hi = m_lo + per_member < out_rec ? m_lo + per_member : out_rec;
+      double* grec = fit.gtot + ((size_t)l * ngroups + gid) * out_rec;
+      constexpr int NE = 4;                       // entries folded together (their loads overlap)
+      const int per_warp = (m_hi - m_lo + WARPS - 1) / WARPS;
+      const int e_lo = m_lo + warp * per_warp, e_hi = e_lo + per_warp < m_hi ? e_lo + per_warp : m_hi;
       for (int e = e_lo; e < e_hi; e += NE) {
         double tot[NE];
         const int valid = e_hi - e < NE ? e_hi - e : NE;
@@ -630,9 +646,13 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
         if (lane == 0) {
 #pragma unroll
           for (int u = 0; u < NE; ++u)
-            if (u < valid) blk[e + u] = tot[u];
+            if (u < valid) grec[e + u] = tot[u];
         }
       }
+      if (gsz > 1) km_barrier(fit.gctr + (size_t)l * ngroups + gid, (unsigned)gsz, gphase);      // the group's members only
+      else __syncthreads();
+      ++gphase;
+      for (int e = tid; e < out_rec; e += THREADS) blk[e] = __ldcg(grec + e);
     }
     __syncthreads();
     const bool sharded = fit.world > 1;
@@ -1125,10 +1145,17 @@ static int km_launch_k(const float* data, const float* centroids, int l, int d, 
   dim3 grid((unsigned)gx, (unsigned)l);
   unsigned* ctr = reinterpret_cast<unsigned*>(workspace);
   double* parts = workspace ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 128) : nullptr;
-  if (fit.cent_out) fit.totals = parts + (size_t)sm_count() * 8 * ((size_t)k * (d + 1) + 1);   // behind the partial records
+  if (fit.cent_out) {      // whole-fit scratch behind the partial records: totals / errors, group records, group counters
+    const size_t rec1 = (size_t)k * (d + 1) + 1, slots = (size_t)sm_count() * 8;
+    fit.part_stride = slots * rec1;
+    fit.totals = parts + 2 * slots * rec1;
+    fit.gtot = fit.totals + (size_t)l * (rec1 + 1);
+    fit.gctr = reinterpret_cast<unsigned*>(fit.gtot + slots * rec1);
+  }
   if (fit.cent_out) {
     // whole-fit launches start from a clean barrier header whatever an earlier, aborted launch may have left behind
     e = cudaMemsetAsync(workspace, 0, 128, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(fit.gctr, 0, (size_t)sm_count() * 8 * sizeof(unsigned), st);
     if (e != cudaSuccess) return fail(ET_ERR_CUDA, "kmeans_assign_kernel: cudaMemsetAsync: %s", cudaGetErrorString(e));
   }
   if (coop) {
@@ -1467,10 +1494,11 @@ extern "C" {
 
 size_t et_kmeans_workspace_bytes(int l, int d, int k_clusters) {
   if (l < 1 || d < 1 || k_clusters < 1) return 0;
-  // 128 B of barrier counters + one partial record per co-resident block (at most 8 per SM in total) + the whole-fit
-  // scratch of et_kmeans_lloyd (l folded records and l per-entry errors)
-  const size_t rec = (size_t)k_clusters * (d + 1) + 1;
-  return 128 + ((size_t)sm_count() * 8 * rec + (size_t)l * (rec + 1)) * sizeof(double);
+  // 128 B of barrier counters + two alternating arrays of one partial record per co-resident block (at most 8 per SM in
+  // total) + the whole-fit scratch of et_kmeans_lloyd (l folded records and l per-entry errors, one record and one
+  // counter per fold group)
+  const size_t rec = (size_t)k_clusters * (d + 1) + 1, slots = (size_t)sm_count() * 8;
+  return 128 + (2 * slots * rec + (size_t)l * (rec + 1) + slots * rec) * sizeof(double) + slots * sizeof(unsigned);
 }
 
 int et_kmeans_assign(const float* data, const float* centroids, int l, int d, int64_t n, int k_clusters,
