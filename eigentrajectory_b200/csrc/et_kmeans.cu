@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
     float* sim_out = maxsims_out ? maxsims_out + (int64_t)l * n : nullptr;
     const int64_t* lab_in = labels_in ? labels_in + (int64_t)l * n : nullptr;
     int since_flush = 0;
+    const bool any_out = lab_out != nullptr || sim_out != nullptr;
     // all lanes of a warp iterate together (the loop bound is warp-uniform)
     const uint32_t base0 = ((uint32_t)blockIdx.x * WARPS + warp) * (32 * PPL);
     float a_next[PPL][DMAX];
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 4 ? 4 : 1) kmeans_assign_
 #pragma unroll
       for (int u = 0; u < PPL; ++u) {
         const bool live = idx[u] < n32;
-        if (live) {
+        if (any_out && live) {                            // (any_out is warp-uniform: accumulation passes skip this block)
           if (lab_out) lab_out[idx[u]] = label[u];
           if (sim_out) sim_out[idx[u]] = best[u];
         }

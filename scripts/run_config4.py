@@ -97,7 +97,7 @@ def main(scene="zara1", quiet=False):
     for k in ("ADE", "FDE", "TCC", "COL"):
         a, b = vals_a[k], vals_b[k]
         assert a.shape == b.shape
-        out[k] = {"mean_reference": means_a[k], "mean_ours": means_b[k],
+        out[k] = {"mean_reference": means_a[k], "mean_ours": means_b[k], "pedestrians_differing": int((a != b).sum()),
                   "max_abs_diff": float(np.abs(a - b).max()), "max_rel_diff": float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-30))}
     if not quiet:
         print(json.dumps(out), flush=True)
