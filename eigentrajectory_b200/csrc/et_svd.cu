@@ -387,8 +387,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);
-  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);
+  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);     // ~2^-44 after the first step
+  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);     // rounding level
   return r;
 }
 
@@ -439,12 +439,15 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
         // body).  1e-12 relative leaves the eigenvectors ~1e-12 from converged -- five orders below what the fp32 outputs
         // resolve -- and ends the iteration one to two sweeps earlier than 1e-14.
         if (apq * apq > floor2 && apq * apq > (EIGF_REL * EIGF_REL) * fabs(app * aqq)) {
+          // inner rotation (|theta| <= pi/4) from the double angle: cos 2theta = |dd| / h, h = sqrt(dd^2 + o^2), hence
+          // c^2 = (h + |dd|) / (2h), s = sign(dd) o / (2 h c) -- two reciprocal square roots on the dependency chain
+          // (14 dependent float64 operations) instead of sqrt, division and rsqrt of the tangent form (26)
           const double o = 2.0 * apq, dd = aqq - app;
-          const double x = fma(dd, dd, o * o);
-          const double h = x * fast_rsqrt(x);
-          const double t = o * fast_rcp(dd + (dd >= 0.0 ? h : -h));
-          c = fast_rsqrt(fma(t, t, 1.0));
-          s = t * c;
+          const double rh = fast_rsqrt(fma(dd, dd, o * o));           // 1 / h
+          const double c2 = fma(0.5 * fabs(dd), rh, 0.5);
+          const double rc = fast_rsqrt(c2);                            // 1 / c
+          c = c2 * rc;
+          s = (dd >= 0.0 ? 0.5 : -0.5) * o * rh * rc;
           rotating = true;
         }
         cs[pi] = c; cs[half + pi] = s; pr[pi] = p; pr[half + pi] = q;

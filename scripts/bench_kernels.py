@@ -186,7 +186,7 @@ def main():
         np.random.seed(0)
         km.initialize_centroids(data)
     a, m = time_op(seed, reps=5, flush=False)
-    add("kmeans farthest-point init (K=20: 21 launches)", n, 24 * 19, a, m, "point", launches=21)
+    add("kmeans farthest-point init (K=20, one persistent launch; cold L2)", n, 24 * 19, a, m, "point", launches=2)
 
     def fit():
         np.random.seed(0)
