@@ -30,7 +30,7 @@ timeout -k 5 900 ncu --set full --clock-control none --import-source on -k regex
 echo "ncu headline exit $?"
 timeout -k 5 900 ncu --set full --clock-control none --import-source on \
   -k regex:'gram_fast|kmeans_assign|kmeans_seed|ade_fde_fast|reconstruct_fast|reconstruct_bwd_fast|eig_jacobi|svd_small' \
-  -s 24 -c 30 -f -o gpurun_out/prof_ops_$TAG python scripts/exp/run_ops_once.py > gpurun_out/ncu_ops_$TAG.log 2>&1
+  -s 9 -c 12 -f -o gpurun_out/prof_ops_$TAG python scripts/exp/run_ops_once.py > gpurun_out/ncu_ops_$TAG.log 2>&1
 echo "ncu ops exit $?"; tail -2 gpurun_out/ncu_ops_$TAG.log
 timeout -k 5 600 ncu --set full --clock-control none --import-source on -k regex:kmeans_assign -s 2 -c 1 -f -o gpurun_out/prof_lloyd_$TAG python scripts/exp/km_profile_target.py > gpurun_out/ncu_lloyd_$TAG.log 2>&1
 echo "ncu lloyd exit $?"
