@@ -1,4 +1,10 @@
-"""A/B: whole-fit k-means kernel of this build vs the round-1 library (scripts/exp/old/libet_b200_r01.so), raw ctypes calls."""
+"""A/B: whole-fit k-means kernel of this build vs the round-1 library, raw ctypes calls.
+
+The round-1 library is not kept in the tree; build it next to this script first:
+    mkdir -p /tmp/r01 && git archive 5235d0c | tar -x -C /tmp/r01 && make -C /tmp/r01 eigentrajectory_b200/libet_b200.so
+    mkdir -p scripts/exp/old && cp /tmp/r01/eigentrajectory_b200/libet_b200.so scripts/exp/old/libet_b200_r01.so
+Measured (B200, us per Lloyd iteration, r01 / single barrier + every block folds): gauss 1e6 21.56 / 21.31, C_pred 1e6
+21.57 / 21.46, C_pred 1.25e6 24.28 / 23.97; with the fold shared by groups of four: 19.6 (1e6), 21.9 (1.25e6)."""
 import ctypes as C, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import eigentrajectory_b200 as et
