@@ -54,3 +54,26 @@ def align_signs(U, U_ref):
     s = torch.sign((U * U_ref).sum(dim=0))
     s[s == 0] = 1
     return U * s, s
+
+
+def spawn_ranks(worker, world, extra_args, attempts=3):
+    """``mp.spawn(worker, (world, port, *extra_args))`` on a free localhost port.  A rendezvous that fails on the NETWORK
+    level (the port was taken between probing and binding, a connection reset while the ranks find each other) is
+    retried on a fresh port; every other failure -- anything raised by the code under test -- propagates unchanged."""
+    import socket
+    import torch.multiprocessing as mp
+    network = ("address already in use", "eaddrinuse", "connection refused", "connection reset", "timed out", "broken pipe",
+               "socket", "connect() ")
+    for attempt in range(attempts):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        try:
+            mp.spawn(worker, args=(world, port, *extra_args), nprocs=world, join=True)
+            return
+        except Exception as exc:      # noqa: BLE001 - inspected and re-raised below
+            text = str(exc).lower()
+            if attempt + 1 < attempts and any(k in text for k in network):
+                print(f"rendezvous failed on port {port} ({type(exc).__name__}); retrying on a new port")
+                continue
+            raise

@@ -18,6 +18,7 @@ pytestmark = pytest.mark.gpu
 
 def _worker(rank, world, port, use_nccl, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # loopback: the box's hostname need not resolve
     dev = torch.device("cuda", rank if use_nccl else 0)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
@@ -91,13 +92,11 @@ WORLDS = [w for w in (2, 4, 8) if w == 2 or torch.cuda.device_count() >= w]
 
 @pytest.mark.parametrize("world", WORLDS)
 def test_sharded_basis_kmeans_metrics(world):
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+    from conftest import spawn_ranks
     use_nccl = torch.cuda.device_count() >= world
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, use_nccl, out), nprocs=world, join=True)
+    spawn_ranks(_worker, world, (use_nccl, out))
     rs = [out[r] for r in range(world)]
     for r in rs:
         # sharded vs unsharded basis: the fp64 Gram sums differ in their last bits with the partition, which moves single

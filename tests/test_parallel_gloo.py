@@ -80,6 +80,7 @@ class OracleBackend:
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # loopback: the box's hostname need not resolve
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from eigentrajectory_b200 import parallel as P
@@ -129,13 +130,10 @@ def test_shard_bounds_partition():
 
 
 def test_sharded_basis_and_kmeans_world2():
-    import socket
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
+    from conftest import spawn_ranks
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    spawn_ranks(_worker, 2, (out,))
     r0, r1 = out[0], out[1]
     for r in (r0, r1):
         assert r["S_obs_err"] < 1e-6 and r["P_pred_err"] < 1e-5
