@@ -56,10 +56,11 @@ def align_signs(U, U_ref):
     return U * s, s
 
 
-def spawn_ranks(worker, world, extra_args, attempts=3):
-    """``mp.spawn(worker, (world, port, *extra_args))`` on a free localhost port.  A rendezvous that fails on the NETWORK
-    level (the port was taken between probing and binding, a connection reset while the ranks find each other) is
-    retried on a fresh port; every other failure -- anything raised by the code under test -- propagates unchanged."""
+def spawn_ranks(worker, world, extra_args, out=None, attempts=3):
+    """``mp.spawn(worker, (world, port, *extra_args))`` on a free localhost port.  A run that fails BEFORE all ranks have
+    found each other (the worker sets ``out["ready", rank]`` right after ``init_process_group``) or with a network-level
+    message (port taken between probing and binding, connection reset) is infrastructure, not the code under test, and
+    is retried on a fresh port; every other failure propagates unchanged."""
     import socket
     import torch.multiprocessing as mp
     network = ("address already in use", "eaddrinuse", "connection refused", "connection reset", "timed out", "broken pipe",
@@ -73,7 +74,10 @@ def spawn_ranks(worker, world, extra_args, attempts=3):
             return
         except Exception as exc:      # noqa: BLE001 - inspected and re-raised below
             text = str(exc).lower()
-            if attempt + 1 < attempts and any(k in text for k in network):
-                print(f"rendezvous failed on port {port} ({type(exc).__name__}); retrying on a new port")
+            met = out is not None and all(out.get(("ready", r)) for r in range(world))
+            if attempt + 1 < attempts and (any(k in text for k in network) or (out is not None and not met)):
+                print(f"rendezvous failed on port {port} ({type(exc).__name__}: {text[:200]}); retrying on a new port")
+                if out is not None:
+                    out.clear()
                 continue
             raise

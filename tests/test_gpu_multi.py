@@ -22,6 +22,7 @@ def _worker(rank, world, port, use_nccl, out):
     dev = torch.device("cuda", rank if use_nccl else 0)
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl" if use_nccl else "gloo", rank=rank, world_size=world)
+    out[("ready", rank)] = True
     try:
         import eigentrajectory_b200 as et
         from eigentrajectory_b200 import ops, parallel as P
@@ -96,7 +97,7 @@ def test_sharded_basis_kmeans_metrics(world):
     use_nccl = torch.cuda.device_count() >= world
     mgr = mp.Manager()
     out = mgr.dict()
-    spawn_ranks(_worker, world, (use_nccl, out))
+    spawn_ranks(_worker, world, (use_nccl, out), out=out)
     rs = [out[r] for r in range(world)]
     for r in rs:
         # sharded vs unsharded basis: the fp64 Gram sums differ in their last bits with the partition, which moves single

@@ -82,6 +82,7 @@ def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")       # loopback: the box's hostname need not resolve
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    out[("ready", rank)] = True
     try:
         from eigentrajectory_b200 import parallel as P
         from oracle import et_oracle as O
@@ -133,7 +134,7 @@ def test_sharded_basis_and_kmeans_world2():
     from conftest import spawn_ranks
     mgr = mp.Manager()
     out = mgr.dict()
-    spawn_ranks(_worker, 2, (out,))
+    spawn_ranks(_worker, 2, (out,), out=out)
     r0, r1 = out[0], out[1]
     for r in (r0, r1):
         assert r["S_obs_err"] < 1e-6 and r["P_pred_err"] < 1e-5
