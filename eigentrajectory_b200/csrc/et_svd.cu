@@ -373,7 +373,8 @@ __device__ __forceinline__ void eig_jacobi_body(const double* __restrict__ G, in
 // pairs on the way (__syncthreads_count: no shared counters); then the two-sided update A <- J^T A J is applied in ONE
 // phase, one thread per 2 x 2 block (row pair i, column pair j: right rotation of pair j, then left rotation of pair i,
 // the same operations the column pass followed by the row pass would perform), while a second group of warps applies
-// V <- V J, one thread per (row, pair).  EIGF_THREADS<MP> threads: [0, (MP/2)^2) update A, [AW, AW + MP/2 * MP) update V.
+// V <- V J, one thread per (VR rows, pair).  EigFast<MP>::THREADS threads: [0, (MP/2)^2) update A, [AW, AW + MP/2 * MP/VR)
+// update V (304 threads for 24 x 24 with VR = 2).
 // Reciprocal and reciprocal square root in float64 from the hardware seeds (rcp / rsqrt.approx.ftz.f64, ~2^-22 relative)
 // and two Newton steps each: full double accuracy up to a few ulp at a third of the latency of the IEEE-rounded
 // division / sqrt sequences.  The Jacobi rotation needs c^2 + s^2 = 1 to rounding, not a correctly rounded angle.
@@ -384,26 +385,28 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, fma(-x, r, 1.0), r);
   return r;
 }
+template <int NR = 2>
 __device__ __forceinline__ double fast_rsqrt(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);     // ~2^-44 after the first step
-  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);     // rounding level
+  r = fma(r * 0.5, fma(-x * r, r, 1.0), r);                       // ~2^-44 after the first step
+  if (NR > 1) r = fma(r * 0.5, fma(-x * r, r, 1.0), r);           // rounding level
   return r;
 }
 
-template <int MP>
+template <int MP, int VR = 2>
 struct EigFast {
   static constexpr int HALF = MP / 2;
   static constexpr int AW = (HALF * HALF + 31) & ~31;       // first thread of the V group (warp aligned)
-  static constexpr int THREADS = AW + HALF * MP;
+  static constexpr int VROWS = MP / VR;                     // rows per pair handled by different threads (VR rows each)
+  static constexpr int THREADS = AW + HALF * VROWS;
 };
 
-template <int MP>
+template <int MP, int NR = 2, int VR = 2>
 __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, int k, float* __restrict__ U,
                                                 float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
                                                 int* __restrict__ info, double* sm) {
-  constexpr int m = MP, half = MP / 2, ld = MP + 1, AW = EigFast<MP>::AW;
+  constexpr int m = MP, half = MP / 2, ld = MP + 1, AW = EigFast<MP, VR>::AW, VROWS = EigFast<MP, VR>::VROWS;
   double* A = sm;                // MP x MP, row-major with odd pitch
   double* V = A + MP * ld;
   double* cs = V + MP * ld;      // half cosines, half sines
@@ -443,9 +446,9 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
           // c^2 = (h + |dd|) / (2h), s = sign(dd) o / (2 h c) -- two reciprocal square roots on the dependency chain
           // (14 dependent float64 operations) instead of sqrt, division and rsqrt of the tangent form (26)
           const double o = 2.0 * apq, dd = aqq - app;
-          const double rh = fast_rsqrt(fma(dd, dd, o * o));           // 1 / h
+          const double rh = fast_rsqrt<NR>(fma(dd, dd, o * o));       // 1 / h
           const double c2 = fma(0.5 * fabs(dd), rh, 0.5);
-          const double rc = fast_rsqrt(c2);                            // 1 / c
+          const double rc = fast_rsqrt<NR>(c2);                        // 1 / c
           c = c2 * rc;
           s = (dd >= 0.0 ? 0.5 : -0.5) * o * rh * rc;
           rotating = true;
@@ -471,14 +474,18 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
           A[qi * ld + pj] = diag ? 0.0 : si * t00 + ci * t10;
           A[qi * ld + qj] = si * t01 + ci * t11;
         }
-      } else if (tid >= AW && tid < AW + half * MP) {
-        const int e = tid - AW, pi = e / MP, r = e % MP;
+      } else if (tid >= AW && tid < AW + half * VROWS) {
+        const int e = tid - AW, pi = e / VROWS, r0 = e % VROWS;
         const double c = cs[pi], s = cs[half + pi];
         if (s != 0.0) {
           const int p = pr[pi], q = pr[half + pi];
-          const double vp = V[r * ld + p], vq = V[r * ld + q];
-          V[r * ld + p] = c * vp - s * vq;
-          V[r * ld + q] = s * vp + c * vq;
+#pragma unroll
+          for (int v = 0; v < VR; ++v) {
+            const int r = r0 + v * VROWS;
+            const double vp = V[r * ld + p], vq = V[r * ld + q];
+            V[r * ld + p] = c * vp - s * vq;
+            V[r * ld + q] = s * vp + c * vq;
+          }
         }
       }
       __syncthreads();
@@ -521,13 +528,13 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
   }
 }
 
-template <int MP>
-__global__ void __launch_bounds__(EigFast<MP>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
-                                                                               float* __restrict__ U, float* __restrict__ S,
-                                                                               double* __restrict__ U64, double* __restrict__ S64,
-                                                                               int* __restrict__ info) {
+template <int MP, int NR = 2, int VR = 2>
+__global__ void __launch_bounds__(EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
+                                                                                   float* __restrict__ U, float* __restrict__ S,
+                                                                                   double* __restrict__ U64, double* __restrict__ S64,
+                                                                                   int* __restrict__ info) {
   extern __shared__ double sm[];
-  eig_jacobi_fast<MP>(G, k, U, S, U64, S64, info, sm);
+  eig_jacobi_fast<MP, NR, VR>(G, k, U, S, U64, S64, info, sm);
 }
 
 template <int MP, int NT>
@@ -756,6 +763,12 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
     eig_jacobi_fast_kernel<16><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 0) {
     eig_jacobi_fast_kernel<24><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 1001) {      // A/B variants of the two-barrier body (measured on B200, default = 2 Newton steps
+    // per rsqrt, 2 rows per V thread: 134 us): one row per V thread 140 us (same bits), four rows 138 us (same bits), one
+    // Newton step 129 us but eigenvectors only ~1e-9 from the two-step result -- not taken
+    eig_jacobi_fast_kernel<24, 2, 1><<<1, EigFast<24, 1>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 1003) {
+    eig_jacobi_fast_kernel<24, 1, 2><<<1, EigFast<24, 2>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (mp == 16) {
     if (nt == 32) eig_jacobi_kernel<16, 32><<<1, 32, smem, st>>>(G, m, k, U, S, U64, S64, info);
     else eig_jacobi_kernel<16, 128><<<1, 128, smem, st>>>(G, m, k, U, S, U64, S64, info);

@@ -25,6 +25,14 @@ for tag, knob in (("two-barrier body", 0), ("four-barrier body 288/128 threads",
     lib.et_tune(3, knob)
     print(f"eig 24x24 {tag} us:", timed(lambda: ops.eig_basis(G_p, 6, info=info)), "sweeps/rotations", info.tolist())
     print(f"eig 16x16 {tag} us:", timed(lambda: ops.eig_basis(G_o, 6, info=info)), "sweeps/rotations", info.tolist())
+for tag, knob in (("1 row per V thread", 1001), ("1 Newton step per rsqrt", 1003)):
+    lib.et_tune(3, knob)
+    U, S, U64, S64 = ops.eig_basis(G_p, 6, want64=True)
+    lib.et_tune(3, 0)
+    U0, S0, U640, S640 = ops.eig_basis(G_p, 6, want64=True)
+    lib.et_tune(3, knob)
+    print(f"eig 24x24 two-barrier body, {tag} us:", timed(lambda: ops.eig_basis(G_p, 6, info=info)), "sweeps/rotations", info.tolist(),
+          "projector diff vs default %.1e, S rel %.1e" % (float((U64 @ U64.T - U640 @ U640.T).norm()), float(((S64 - S640).abs() / S640).max())))
 lib.et_tune(3, 0)
 print("eig pair (both bases, one launch) us:", timed(lambda: ops.eig_basis_pair(G_o, G_p, 6)))
 d = et.ETDescriptor(et.DotDict(obs_len=8, pred_len=12, k=6, num_samples=20, traj_dim=2, static_dist=0.3)).to(dev)
