@@ -182,6 +182,14 @@ class BatchKMeans(nn.Module):
         inertia = -(acc.simsum_last / n).mean()
         return labels, final.clone(), n_iter, acc.err.clone(), inertia
 
+    def _workspace(self, l, d, device):
+        """Device scratch of a fit, kept on the object and reused while the problem shape stays the same (a fit of this
+        size allocates ~4 MB of zeroed scratch otherwise; every launch that needs clean counters zeroes them itself)."""
+        key = (l, d, self.n_clusters, device, torch.cuda.current_stream(device).cuda_stream)
+        if getattr(self, "_acc_key", None) != key:
+            self._acc, self._acc_key = ops.KMeansWorkspace(l, d, self.n_clusters, device), key
+        return self._acc
+
     def fit(self, data, centroids=None):
         """Cluster ``data (l, d, N)`` and return the labels ``(l, N)`` of the best restart; the winning centroids
         are kept in the ``centroids`` buffer.  ``centroids (l, d, K)``, if given, seed the first restart
@@ -189,7 +197,7 @@ class BatchKMeans(nn.Module):
         assert data.is_contiguous(), "use .contiguous()"
         x, lead = _as_ldn(data)
         l, d, n = x.shape
-        acc = ops.KMeansWorkspace(l, d, self.n_clusters, x.device)
+        acc = self._workspace(l, d, x.device)
 
         best_centroids = best_labels = None
         best_inertia = 1e32
