@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from ._lib import ETLibraryError
 from .kmeans import BatchKMeans
 
 
@@ -61,7 +62,14 @@ class ETAnchor(nn.Module):
             for mode in self.init_modes:                # k-means++ proper (as sklearn), then the reference's farthest-point rule
                 km = BatchKMeans(n_clusters=self.s, n_redo=self.n_redo, init_mode=mode)
                 np.random.seed(self.kmeans_seed)
-                km.fit(C_pred)
+                try:
+                    km.fit(C_pred)
+                except ETLibraryError:
+                    # the D^2-sampling kernel keeps the points resident on the SMs (~1.3e6 six-dimensional rows); a larger
+                    # initialisation set is seeded by the farthest-point family alone (which has no such limit)
+                    if mode == "d2" and len(self.init_modes) > 1:
+                        continue
+                    raise
                 if best is None or km.inertia_ < best.inertia_:
                     best = km
         finally:
