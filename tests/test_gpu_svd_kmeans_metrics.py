@@ -688,3 +688,18 @@ def test_kmeans_d2_seeding_properties(et):
     np.random.seed(0)
     labels = km.fit(x)
     assert labels.shape == (1, 40_000) and km.inertia_ < 8.0                # ~6 = the blobs' own variance in 6-D
+
+
+def test_anchor_generation_beyond_the_resident_seeding_capacity(et, O):
+    """1.4e6 rows do not fit the resident seeding kernels: k-means++ (D^2) seeding reports it, the farthest-point family
+    falls back to one launch per step, and ``anchor_generation`` still returns anchors (from that family alone)."""
+    obs, pred = O.synthetic_trajectories(1_400_000, seed=2)
+    d = et.ETDescriptor(et.DotDict(HP)).cuda()
+    pred_norm, U_pred = d.parameter_initialization(obs.cuda(), pred.cuda())
+    C = d.to_ET_space(pred_norm, U_pred).unsqueeze(0).contiguous()
+    with pytest.raises(et.ETLibraryError):
+        et.BatchKMeans(n_clusters=20, init_mode="d2").initialize_centroids(C)
+    a = et.ETAnchor(et.DotDict(HP)).cuda()
+    a.n_redo = 2
+    a.anchor_generation(pred_norm, U_pred)
+    assert a.C_anchor.shape == (6, 20) and torch.isfinite(a.C_anchor).all() and a.inertia_ > 0
