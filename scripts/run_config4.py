@@ -104,5 +104,121 @@ def main(scene="zara1", quiet=False):
     return out
 
 
+def train_compare(scene="zara1", quiet=False):
+    """One training epoch of the reference's own loop (``ETSequencedMiniBatchTrainer.train``, utils/trainer.py:117-150:
+    sequential scenes, losses accumulated over ``batch_size`` scenes, backward, gradient clipping, AdamW step) from the
+    same ``state_dict``: twice with the reference's modules (the second run is the noise floor of the predictor's own GPU
+    kernels) and once with ``eigentrajectory_b200`` swapped in -- fused forward, fused losses, sparse arg-min backward.
+    Compares the epoch's mean training loss and the predictor's weights after the epoch."""
+    from oracle import ref_loader
+    import eigentrajectory_b200 as et
+    ref_ET, ref_utils, ref_baseline = ref_loader.load("EigenTrajectory", "utils", "baseline")
+    import utils.trainer as trainer_mod
+
+    cfg = os.path.join(ref_loader.REF_ROOT, "config", "eigentrajectory-{baseline}-" + scene + ".json")
+    hp = ref_utils.get_exp_config(cfg)
+    hp.baseline = "sgcn"
+    hp.dataset_dir = os.path.join(ref_loader.REF_ROOT, "datasets") + "/"
+    hp.checkpoint_dir = "/tmp/et_config4_ckpt"
+
+    ours = build_trainer(ref_utils, ref_baseline, trainer_mod, et.EigenTrajectory, hp)
+    obs = torch.cat([ours.loader_train.dataset.obs_traj, ours.loader_val.dataset.obs_traj], dim=0)
+    pred = torch.cat([ours.loader_train.dataset.pred_traj, ours.loader_val.dataset.pred_traj], dim=0)
+    obs, pred = ref_utils.augment_trajectory(obs, pred)
+    ours.model.calculate_parameters(obs.cuda(), pred.cuda())
+    state = {k: v.detach().clone() for k, v in ours.model.state_dict().items()}
+
+    def epoch(model_cls):
+        trainer = build_trainer(ref_utils, ref_baseline, trainer_mod, model_cls, hp)       # fresh AdamW state
+        missing = trainer.model.load_state_dict(state, strict=False)
+        assert not missing.missing_keys and not missing.unexpected_keys, missing
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stderr(io.StringIO()):
+            trainer.train(0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        weights = torch.cat([p.detach().flatten().double().cpu() for p in trainer.model.baseline_model.parameters()])
+        return trainer.log["train_loss"][-1], weights, dt, len(trainer.loader_train)
+
+    loss_a, w_a, t_a, scenes = epoch(ref_ET.EigenTrajectory)
+    loss_a2, w_a2, _, _ = epoch(ref_ET.EigenTrajectory)
+    launches = et.launch_count()
+    loss_b, w_b, t_b, _ = epoch(et.EigenTrajectory)
+    launches = et.launch_count() - launches
+    w0 = torch.cat([v.flatten().double().cpu() for k, v in state.items() if k.startswith("baseline_model.") and v.dtype.is_floating_point])
+    scale = float(w_a.abs().max())
+    out = {"config": "configs[3]: one ET-SGCN training epoch, " + scene + " train split", "scenes": scenes,
+           "optimizer_steps": (scenes + hp.batch_size - 1) // hp.batch_size,
+           "train_loss_reference": loss_a, "train_loss_ours": loss_b, "train_loss_rel_diff": abs(loss_a - loss_b) / abs(loss_a),
+           "train_loss_rel_diff_reference_rerun": abs(loss_a - loss_a2) / abs(loss_a),
+           "weights_max_abs_diff": float((w_a - w_b).abs().max()), "weights_max_abs_diff_reference_rerun": float((w_a - w_a2).abs().max()),
+           "weights_max_abs": scale, "weights_moved_by": float((w_a - w0).abs().max()) if w0.numel() == w_a.numel() else None,
+           "ms_per_scene_reference_l2": 1e3 * t_a / scenes, "ms_per_scene_ours": 1e3 * t_b / scenes, "speedup": t_a / t_b,
+           "library_launches_per_scene": launches / scenes}
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
+
+
+def grad_compare(scene="zara1", n_scenes=128, quiet=False):
+    """Gradient of the FIRST optimizer step of that loop (losses of the first ``batch_size`` = 128 training scenes
+    accumulated exactly as utils/trainer.py:124-141 does, one backward) with respect to every SGCN weight: reference
+    modules vs this package, same weights.  This is the parity statement for training -- after the optimizer steps AdamW's
+    g / sqrt(v) normalisation turns last-bit gradient noise on near-zero gradients into O(lr) weight differences."""
+    from oracle import ref_loader
+    import eigentrajectory_b200 as et
+    ref_ET, ref_utils, ref_baseline = ref_loader.load("EigenTrajectory", "utils", "baseline")
+    import utils.trainer as trainer_mod
+
+    cfg = os.path.join(ref_loader.REF_ROOT, "config", "eigentrajectory-{baseline}-" + scene + ".json")
+    hp = ref_utils.get_exp_config(cfg)
+    hp.baseline = "sgcn"
+    hp.dataset_dir = os.path.join(ref_loader.REF_ROOT, "datasets") + "/"
+    hp.checkpoint_dir = "/tmp/et_config4_ckpt"
+    ours = build_trainer(ref_utils, ref_baseline, trainer_mod, et.EigenTrajectory, hp)
+    obs = torch.cat([ours.loader_train.dataset.obs_traj, ours.loader_val.dataset.obs_traj], dim=0)
+    pred = torch.cat([ours.loader_train.dataset.pred_traj, ours.loader_val.dataset.pred_traj], dim=0)
+    obs, pred = ref_utils.augment_trajectory(obs, pred)
+    ours.model.calculate_parameters(obs.cuda(), pred.cuda())
+    state = {k: v.detach().clone() for k, v in ours.model.state_dict().items()}
+
+    def first_step(trainer):
+        trainer.model.load_state_dict(state, strict=False)
+        trainer.model.train()
+        trainer.optimizer.zero_grad()
+        total, losses = None, []
+        for cnt, batch in enumerate(trainer.loader_train):
+            if cnt >= n_scenes:
+                break
+            o, p_ = [t.cuda(non_blocking=True) for t in batch[:2]]
+            out = trainer.model(o, p_)
+            loss = out["loss_eigentraj"] + out["loss_euclidean_ade"] + out["loss_euclidean_fde"]
+            loss[torch.isnan(loss)] = 0
+            losses.append(float(loss))
+            total = loss if total is None else total + loss
+        (total / n_scenes).backward()
+        grads = torch.cat([p.grad.detach().flatten().double().cpu() for p in trainer.model.baseline_model.parameters()])
+        return grads, np.asarray(losses)
+
+    g_b, l_b = first_step(ours)
+    ref = build_trainer(ref_utils, ref_baseline, trainer_mod, ref_ET.EigenTrajectory, hp)
+    g_a, l_a = first_step(ref)
+    g_a2, _ = first_step(ref)
+    out = {"config": f"configs[3]: gradient of the first optimizer step ({n_scenes} scenes), {scene} train split",
+           "parameters": int(g_a.numel()), "grad_max_abs": float(g_a.abs().max()),
+           "grad_max_abs_diff": float((g_a - g_b).abs().max()), "grad_rel_max": float((g_a - g_b).abs().max() / g_a.abs().max()),
+           "grad_rel_fro": float((g_a - g_b).norm() / g_a.norm()), "grad_rel_fro_reference_rerun": float((g_a - g_a2).norm() / g_a.norm()),
+           "per_scene_loss_max_rel_diff": float(np.abs(l_a - l_b).max() / np.abs(l_a).max())}
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
+
+
 if __name__ == "__main__":
-    main(*(sys.argv[1:2]))
+    if len(sys.argv) > 1 and sys.argv[1] == "grad":
+        grad_compare(*(sys.argv[2:3]))
+    elif len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_compare(*(sys.argv[2:3]))
+    else:
+        main(*(sys.argv[1:2]))
