@@ -7,6 +7,7 @@
 // all-reduce) between the two steps.  Small problems (N up to ~2000 rows) can instead run a one-sided
 // Hestenes Jacobi directly on the shared-memory resident tall-skinny (N x 2T) matrix.
 #include <math.h>
+#include <stdlib.h>
 
 #include "et_common.cuh"
 
@@ -402,7 +403,19 @@ struct EigFast {
   static constexpr int THREADS = AW + HALF * VROWS;
 };
 
-template <int MP, int NR = 2, int VR = 2>
+// PROF (diagnostic, ET_TUNE_EIG_THREADS = 3001 / 3002): thread 0 accumulates clock64() cycles per phase into info[2..11]:
+// {set-up, rotation parameters, first barrier, update, second barrier, rotating steps, idle steps, idle-step cycles,
+//  ordering, output}; info must then hold 12 ints.
+struct EigProf {
+  long long t_setup = 0, t_param = 0, t_bar1 = 0, t_upd = 0, t_bar2 = 0, t_idle = 0, t_order = 0, t_out = 0;
+  int full = 0, idle = 0;
+  __device__ __forceinline__ void store(int* info) const {
+    info[2] = (int)t_setup; info[3] = (int)t_param; info[4] = (int)t_bar1; info[5] = (int)t_upd; info[6] = (int)t_bar2;
+    info[7] = full; info[8] = idle; info[9] = (int)t_idle; info[10] = (int)t_order; info[11] = (int)t_out;
+  }
+};
+
+template <int MP, int NR = 2, int VR = 2, bool PROF = false>
 __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, int k, float* __restrict__ U,
                                                 float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
                                                 int* __restrict__ info, double* sm) {
@@ -414,6 +427,9 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
   int* order = pr + MP;
   __shared__ double floor2;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  EigProf prof;
+  long long tk = 0;
+  if (PROF) tk = clock64();
   for (int e = tid; e < MP * MP; e += nthr) {
     const int r = e / MP, c = e % MP;
     A[r * ld + c] = 0.5 * (G[r * m + c] + G[c * m + r]);
@@ -426,11 +442,14 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
     floor2 = (1e-18 * mx) * (1e-18 * mx);
   }
   __syncthreads();
+  if (PROF) { const long long t = clock64(); prof.t_setup = t - tk; tk = t; }
   int sweeps_done = 0, total_rot = 0;
   for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
     int n_rot = 0;
     for (int step = 0; step < MP - 1; ++step) {
       bool rotating = false;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (PROF) t0 = clock64();
       if (tid < half) {          // round-robin tournament: position 0 fixed, the others rotate
         const int pi = tid;
         auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (MP - 1); };
@@ -455,9 +474,14 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
         }
         cs[pi] = c; cs[half + pi] = s; pr[pi] = p; pr[half + pi] = q;
       }
+      if (PROF) t1 = clock64();
       const int rotated = __syncthreads_count(rotating);      // barrier + number of rotating pairs, block-uniform
+      if (PROF) t2 = clock64();
       n_rot += rotated;
-      if (rotated == 0) continue;       // nothing to do in this step (typical for the last, confirming sweep)
+      if (rotated == 0) {               // nothing to do in this step (typical for the last, confirming sweep)
+        if (PROF) { ++prof.idle; prof.t_idle += t2 - t0; }
+        continue;
+      }
       if (tid < half * half) {
         const int i = tid / half, j = tid % half;
         const double ci = cs[i], si = cs[half + i], cj = cs[j], sj = cs[half + j];
@@ -488,13 +512,19 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
           }
         }
       }
+      if (PROF) t3 = clock64();
       __syncthreads();
+      if (PROF) {
+        const long long t4 = clock64();
+        ++prof.full; prof.t_param += t1 - t0; prof.t_bar1 += t2 - t1; prof.t_upd += t3 - t2; prof.t_bar2 += t4 - t3;
+      }
     }
     ++sweeps_done;
     total_rot += n_rot;
     if (n_rot == 0) break;
   }
   if (info && tid == 0) { info[0] = sweeps_done; info[1] = total_rot; }
+  if (PROF) tk = clock64();
 
   // order eigenvalues descending (ties: lower index first), canonical sign, S = sqrt(lambda)
   if (tid == 0) {
@@ -507,6 +537,7 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
     }
   }
   __syncthreads();
+  if (PROF) { const long long t = clock64(); prof.t_order = t - tk; tk = t; }
   for (int j = tid; j < k; j += nthr) {
     const int col = order[j];
     const double lam = A[col * ld + col];
@@ -526,15 +557,237 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
     S[j] = (float)sv;
     if (S64) S64[j] = sv;
   }
+  if (PROF) {
+    __syncthreads();
+    if (tid == 0 && info) { prof.t_out = clock64() - tk; prof.store(info); }
+  }
 }
 
-template <int MP, int NR = 2, int VR = 2>
+// Second generation of the two-barrier body (same parallel-ordered cyclic Jacobi, same threshold, same thread roles).  The
+// step time of the first generation is the rotation-parameter phase of ONE warp (the other warps wait at the barrier), so
+// that phase is what is shortened here:
+//  * pair indices come from a table built once in shared memory (23 x 24 bytes) instead of the tournament arithmetic with
+//    its modulo; the parameter threads fetch the NEXT step's pair behind the first barrier, the update threads fetch their
+//    four indices while they wait in front of it -- one dependent shared-memory round after the barrier instead of two;
+//  * the rotation is computed without a branch (the threshold test runs beside the chain and selects at the end) from a
+//    shorter chain: 1/h = rsqrt(dd^2 + o^2) from the hardware seed and ONE Newton step (2^-44: it only sets the ANGLE),
+//    c2 = 1/2 + |dd| / 2h, then (c~, s~) = (c2, +-o / 2h) * rsqrt_seed(c2) -- a vector of the right direction whose
+//    length is 1 + O(2^-21) -- normalised by the series n = 1 - d/2 + 3 d^2 / 8, d = c~^2 + s~^2 - 1 (error 5 d^3 / 16 <
+//    1e-18): c^2 + s^2 = 1 to rounding, 15 dependent float64 operations instead of 28;
+//  * because the angle is no longer exact to the last bit, the rotated pair is stored as computed, not as an exact zero
+//    (zeroing it would perturb the matrix by 2^-44 |a_pq|); convergence and accuracy are unchanged (numpy model of this
+//    body on the 1e6-pedestrian Gram matrices: the same rotation counts per sweep, residual 1e-15);
+//  * ordering by rank counting (m threads) and sign / output by one warp per column instead of one thread.
+__device__ __forceinline__ double lds_f64(unsigned shared_address) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_address) : "memory");
+  return v;
+}
+__device__ __forceinline__ double raw_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+template <int MP, int VR = 2, bool PROF = false>
+__device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, int k, float* __restrict__ U,
+                                                 float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
+                                                 int* __restrict__ info, double* sm) {
+  constexpr int m = MP, half = MP / 2, ld = MP + 1, AW = EigFast<MP, VR>::AW, VROWS = EigFast<MP, VR>::VROWS, NSTEP = MP - 1;
+  static_assert(MP <= 32, "one lane per row in the output phase");
+  double* A = sm;                // MP x MP, row-major with odd pitch
+  double* V = A + MP * ld;
+  double* cs = V + MP * ld;      // half cosines, half sines
+  int* order = reinterpret_cast<int*>(cs + MP) + MP;   // (same layout as the first generation; its pair arrays stay unused)
+  __shared__ double floor2;
+  __shared__ unsigned char tab[NSTEP * MP];            // tab[step][pi] = p, tab[step][half + pi] = q  (p < q)
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  EigProf prof;
+  long long tk = 0;
+  if (PROF) tk = clock64();
+  for (int e = tid; e < MP * MP; e += nthr) {
+    const int r = e / MP, c = e % MP;
+    A[r * ld + c] = 0.5 * (G[r * m + c] + G[c * m + r]);
+    V[r * ld + c] = (r == c) ? 1.0 : 0.0;
+  }
+  for (int e = tid; e < NSTEP * half; e += nthr) {     // round-robin tournament: position 0 fixed, the others rotate
+    const int step = e / half, pi = e % half;
+    auto player = [&](int pos) { return pos == 0 ? 0 : 1 + (pos - 1 + step) % (MP - 1); };
+    int p = player(pi), q = player(MP - 1 - pi);
+    if (p > q) { const int t = p; p = q; q = t; }
+    tab[step * MP + pi] = (unsigned char)p;
+    tab[step * MP + half + pi] = (unsigned char)q;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double mx = 0.0;
+    for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
+    floor2 = (1e-18 * mx) * (1e-18 * mx);
+  }
+  const bool isP = tid < half, isA = tid < half * half, isV = tid >= AW && tid < AW + half * VROWS;
+  const int ai = isA ? tid / half : 0, aj = isA ? tid % half : 0;                      // A: 2 x 2 block (row pair ai, column pair aj)
+  const int vpi = isV ? (tid - AW) / VROWS : 0, vr0 = isV ? (tid - AW) % VROWS : 0;    // V: pair vpi, rows vr0 + v * VROWS
+  // shared-window byte addresses of this parameter thread's a_pp, a_qq, a_pq, kept one step ahead in registers (explicit
+  // ld.shared: the compiler otherwise re-derives the window base from a special register in front of every step's first load)
+  const unsigned a_sh = (unsigned)__cvta_generic_to_shared(A);
+  unsigned adr_pp = a_sh, adr_qq = a_sh, adr_pq = a_sh;
+  auto pair_addresses = [&](int p, int q) {
+    adr_pp = a_sh + (unsigned)(p * (ld + 1)) * 8u;
+    adr_qq = a_sh + (unsigned)(q * (ld + 1)) * 8u;
+    adr_pq = a_sh + (unsigned)(p * ld + q) * 8u;
+  };
+  if (isP) pair_addresses(tab[tid], tab[half + tid]);
+  __syncthreads();
+  if (PROF) { const long long t = clock64(); prof.t_setup = t - tk; tk = t; }
+  int sweeps_done = 0, total_rot = 0;
+  for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
+    int n_rot = 0;
+    for (int step = 0; step < NSTEP; ++step) {
+      const unsigned char* ts = tab + step * MP;
+      bool rotating = false;
+      long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+      if (PROF) t0 = clock64();
+      // this thread's work items of the step (issued first: the loads fly while the parameter chain runs / the barrier waits)
+      int pi_ = 0, qi = 0, pj = 0, qj = 0;
+      if (isA) { pi_ = ts[ai]; qi = ts[half + ai]; pj = ts[aj]; qj = ts[half + aj]; }
+      else if (isV) { pi_ = ts[vpi]; qi = ts[half + vpi]; }
+      if (isP) {
+        const double app = lds_f64(adr_pp), aqq = lds_f64(adr_qq), apq = lds_f64(adr_pq);
+        const double o = 2.0 * apq, dd = aqq - app, apq2 = apq * apq;
+        const double x = fma(dd, dd, o * o);
+        double rh = raw_rsqrt(x);                                   // 1 / h, h = sqrt(dd^2 + o^2)
+        rh = fma(rh * 0.5, fma(-x * rh, rh, 1.0), rh);
+        const double c2 = fma(0.5 * fabs(dd), rh, 0.5);             // cos^2 of the inner rotation angle (|theta| <= pi/4)
+        const double kk = (dd >= 0.0 ? 0.5 : -0.5) * o * rh;
+        const double rc = raw_rsqrt(c2);
+        const double ct = c2 * rc, st = kk * rc;
+        const double d = fma(ct, ct, fma(st, st, -1.0));
+        const double nn = fma(d, fma(0.375, d, -0.5), 1.0);
+        // rotate iff |a_pq| > EIGF_REL sqrt(a_pp a_qq) (compared squared) and above the absolute floor; a pair that does not
+        // rotate may have produced NaN above (0 / 0) -- the selection discards it
+        rotating = apq2 > floor2 && apq2 > (EIGF_REL * EIGF_REL) * fabs(app * aqq);
+        cs[tid] = rotating ? ct * nn : 1.0;
+        cs[half + tid] = rotating ? st * nn : 0.0;
+      }
+      if (PROF) t1 = clock64();
+      const int rotated = __syncthreads_count(rotating);      // barrier + number of rotating pairs, block-uniform
+      if (PROF) t2 = clock64();
+      if (isP) {                                              // next step's pair (the table wraps at the end of a sweep)
+        const unsigned char* tn = tab + (step + 1 == NSTEP ? 0 : step + 1) * MP;
+        pair_addresses(tn[tid], tn[half + tid]);
+      }
+      n_rot += rotated;
+      if (rotated == 0) {               // nothing to do in this step (typical for the last, confirming sweep)
+        if (PROF) { ++prof.idle; prof.t_idle += t2 - t0; }
+        continue;
+      }
+      if (isA) {
+        const double ci = cs[ai], si = cs[half + ai], cj = cs[aj], sj = cs[half + aj];
+        if (si != 0.0 || sj != 0.0) {
+          const double x00 = A[pi_ * ld + pj], x01 = A[pi_ * ld + qj], x10 = A[qi * ld + pj], x11 = A[qi * ld + qj];
+          // columns: X J_j
+          const double t00 = cj * x00 - sj * x01, t01 = sj * x00 + cj * x01;
+          const double t10 = cj * x10 - sj * x11, t11 = sj * x10 + cj * x11;
+          // rows: J_i^T T
+          A[pi_ * ld + pj] = ci * t00 - si * t10;
+          A[pi_ * ld + qj] = ci * t01 - si * t11;
+          A[qi * ld + pj] = si * t00 + ci * t10;
+          A[qi * ld + qj] = si * t01 + ci * t11;
+        }
+      } else if (isV) {
+        const double c = cs[vpi], s = cs[half + vpi];
+        if (s != 0.0) {
+#pragma unroll
+          for (int v = 0; v < VR; ++v) {
+            const int r = vr0 + v * VROWS;
+            const double vp = V[r * ld + pi_], vq = V[r * ld + qi];
+            V[r * ld + pi_] = c * vp - s * vq;
+            V[r * ld + qi] = s * vp + c * vq;
+          }
+        }
+      }
+      if (PROF) t3 = clock64();
+      __syncthreads();
+      if (PROF) {
+        const long long t4 = clock64();
+        ++prof.full; prof.t_param += t1 - t0; prof.t_bar1 += t2 - t1; prof.t_upd += t3 - t2; prof.t_bar2 += t4 - t3;
+      }
+    }
+    ++sweeps_done;
+    total_rot += n_rot;
+    if (n_rot == 0) break;
+  }
+  if (info && tid == 0) { info[0] = sweeps_done; info[1] = total_rot; }
+  if (PROF) tk = clock64();
+
+  // eigenvalues descending (ties: lower index first) by rank counting
+  if (tid < m) order[tid] = tid;
+  __syncthreads();
+  if (tid < m) {
+    const double li = A[tid * ld + tid];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const double lj = A[j * ld + j];
+      rank += (lj > li || (lj == li && j < tid)) ? 1 : 0;
+    }
+    order[rank] = tid;
+  }
+  __syncthreads();
+  if (PROF) { const long long t = clock64(); prof.t_order = t - tk; tk = t; }
+  // one (full) warp per output column, one lane per row: canonical sign (the largest-magnitude component, the first one on
+  // ties, is positive), S = sqrt(lambda)
+  const int warp = tid >> 5, lane = tid & 31, nfull = nthr >> 5;
+  if (warp < nfull) {
+    for (int j = warp; j < k; j += nfull) {
+      const int col = order[j];
+      const double v = lane < m ? V[lane * ld + col] : 0.0;
+      double a = lane < m ? fabs(v) : -1.0;
+      int arg = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double a2 = __shfl_xor_sync(0xffffffffu, a, o);
+        const int g2 = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (a2 > a || (a2 == a && g2 < arg)) { a = a2; arg = g2; }
+      }
+      const double vbig = __shfl_sync(0xffffffffu, v, arg);
+      const double w = vbig < 0.0 ? -v : v;
+      if (lane < m) {
+        U[lane * k + j] = (float)w;
+        if (U64) U64[lane * k + j] = w;
+      }
+      if (lane == 0) {
+        const double lam = A[col * ld + col];
+        const double sv = sqrt(lam > 0.0 ? lam : 0.0);
+        S[j] = (float)sv;
+        if (S64) S64[j] = sv;
+      }
+    }
+  }
+  if (PROF) {
+    __syncthreads();
+    if (tid == 0 && info) { prof.t_out = clock64() - tk; prof.store(info); }
+  }
+}
+
+
+constexpr int EIG_DEFAULT_GEN = 1;      // generation of the two-barrier body taken by default (ET_TUNE_EIG_THREADS 2001 / 2002 force one,
+                                        // the environment variable ET_EIG_GEN = 1 | 2 changes the default of the process)
+static int eig_default_gen() {
+  static const int gen = [] {
+    const char* e = getenv("ET_EIG_GEN");
+    return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : EIG_DEFAULT_GEN;
+  }();
+  return gen;
+}
+
+template <int MP, int NR = 2, int VR = 2, int GEN = 1, bool PROF = false>
 __global__ void __launch_bounds__(EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
                                                                                    float* __restrict__ U, float* __restrict__ S,
                                                                                    double* __restrict__ U64, double* __restrict__ S64,
                                                                                    int* __restrict__ info) {
   extern __shared__ double sm[];
-  eig_jacobi_fast<MP, NR, VR>(G, k, U, S, U64, S64, info, sm);
+  if constexpr (GEN == 2) eig_jacobi_fast2<MP, VR, PROF>(G, k, U, S, U64, S64, info, sm);
+  else eig_jacobi_fast<MP, NR, VR, PROF>(G, k, U, S, U64, S64, info, sm);
 }
 
 template <int MP, int NT>
@@ -549,13 +802,19 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
 // Both bases of one descriptor (16 x 16 observation and 24 x 24 prediction Gram matrices) in ONE launch: block 0 / 1
 // solve them side by side on two SMs, so the pair costs what the larger solve costs.
 constexpr int EIG_PAIR_THREADS = EigFast<24>::THREADS;
+template <int GEN>
 __global__ void __launch_bounds__(EIG_PAIR_THREADS) eig_jacobi_pair_kernel(const double* __restrict__ G_a,
                                                                            const double* __restrict__ G_b, int k,
                                                                            float* __restrict__ U_a, float* __restrict__ S_a,
                                                                            float* __restrict__ U_b, float* __restrict__ S_b) {
   extern __shared__ double sm[];
-  if (blockIdx.x == 0) eig_jacobi_fast<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
-  else eig_jacobi_fast<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
+  if constexpr (GEN == 2) {
+    if (blockIdx.x == 0) eig_jacobi_fast2<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
+    else eig_jacobi_fast2<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
+  } else {
+    if (blockIdx.x == 0) eig_jacobi_fast<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
+    else eig_jacobi_fast<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
+  }
 }
 
 // =======================================================================================
@@ -758,11 +1017,27 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   // 16 x 16: 117 / 90 / 74 us with 32 / 64 / 128; results bit-identical)
   // 16 x 16 / 24 x 24 take the two-barrier body (eig_jacobi_fast: 24 x 24 in ~95 us); ET_TUNE_EIG_THREADS selects the
   // four-barrier body with that many threads for A/B runs (32 = the single-warp variant)
-  const int nt = tune_get(ET_TUNE_EIG_THREADS);
-  if (m == 16 && nt == 0) {
+  int nt = tune_get(ET_TUNE_EIG_THREADS);
+  if (nt == 0) nt = 2000 + eig_default_gen();
+  // 2001 / 2002: first / second generation of the two-barrier body; 3001 / 3002: the same with phase cycle counters in
+  // info[2..11] (diagnostic: info must hold 12 ints)
+  ET_REQUIRE(nt != 3001 && nt != 3002 || (info && (m == 16 || m == 24)), ET_ERR_BADARG, "et_eig_jacobi: profiling variants need info[12] and m = 16 / 24");
+  if (m == 16 && nt == 2001) {
     eig_jacobi_fast_kernel<16><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
-  } else if (m == 24 && nt == 0) {
+  } else if (m == 24 && nt == 2001) {
     eig_jacobi_fast_kernel<24><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 16 && nt == 2002) {
+    eig_jacobi_fast_kernel<16, 2, 2, 2><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 2002) {
+    eig_jacobi_fast_kernel<24, 2, 2, 2><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 16 && nt == 3001) {
+    eig_jacobi_fast_kernel<16, 2, 2, 1, true><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 3001) {
+    eig_jacobi_fast_kernel<24, 2, 2, 1, true><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 16 && nt == 3002) {
+    eig_jacobi_fast_kernel<16, 2, 2, 2, true><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 3002) {
+    eig_jacobi_fast_kernel<24, 2, 2, 2, true><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 1001) {      // A/B variants of the two-barrier body (measured on B200, default = 2 Newton steps
     // per rsqrt, 2 rows per V thread: 134 us): one row per V thread 140 us (same bits), four rows 138 us (same bits), one
     // Newton step 129 us but eigenvectors only ~1e-9 from the two-step result -- not taken
@@ -791,7 +1066,10 @@ int et_eig_jacobi_pair(const double* G_a, int m_a, const double* G_b, int m_b, i
   ET_REQUIRE(k >= 1 && k <= m_a && k <= m_b, ET_ERR_BADARG, "et_eig_jacobi_pair: k = %d outside [1, min(m)]", k);
   if (m_a == 16 && m_b == 24) {
     const size_t smem = (size_t)(2 * 24 * 25 + 24) * sizeof(double) + (size_t)2 * 24 * sizeof(int);
-    eig_jacobi_pair_kernel<<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
+    int gen = tune_get(ET_TUNE_EIG_THREADS);
+    gen = gen == 2001 ? 1 : (gen == 2002 ? 2 : eig_default_gen());
+    if (gen == 2) eig_jacobi_pair_kernel<2><<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
+    else eig_jacobi_pair_kernel<1><<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
     return check_launch("eig_jacobi_pair_kernel");
   }
   int rc = et_eig_jacobi(G_a, m_a, k, U_a, S_a, nullptr, nullptr, nullptr, stream);   // other shapes: two launches
