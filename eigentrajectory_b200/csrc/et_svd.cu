@@ -563,24 +563,36 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
   }
 }
 
-// Second generation of the two-barrier body (same parallel-ordered cyclic Jacobi, same threshold, same thread roles).  The
-// step time of the first generation is the rotation-parameter phase of ONE warp (the other warps wait at the barrier), so
-// that phase is what is shortened here:
-//  * pair indices come from a table built once in shared memory (23 x 24 bytes) instead of the tournament arithmetic with
-//    its modulo; the parameter threads fetch the NEXT step's pair behind the first barrier, the update threads fetch their
-//    four indices while they wait in front of it -- one dependent shared-memory round after the barrier instead of two;
+// Second generation of the two-barrier body (same parallel-ordered cyclic Jacobi, same threshold).  Cycle counters in the
+// first generation (ET_TUNE_EIG_THREADS = 3001, [B200] 24 x 24: 186 rotating steps of ~880 cycles) showed the step split
+// evenly between the rotation-parameter phase of ONE warp (408 cycles, the other warps wait at the barrier) and the update
+// (403 cycles: three dependent shared-memory rounds -- sines, pair indices, matrix entries -- each behind a re-derivation of
+// the shared window base from a special register, and divergent skip branches), plus 26 000 cycles of single-thread
+// selection sort at the end.  Here:
+//  * a dedicated warp computes the rotation parameters; every other thread prepares the shared-memory ADDRESSES of its
+//    work items while it waits for that warp (pair indices come from a table built once, 23 x 24 bytes, instead of the
+//    tournament arithmetic), so the update is ONE round of loads, four dependent float64 levels and the stores;
+//  * all shared-memory traffic of the loop uses explicit 32-bit window addresses (ld.shared / st.shared), computed once;
 //  * the rotation is computed without a branch (the threshold test runs beside the chain and selects at the end) from a
 //    shorter chain: 1/h = rsqrt(dd^2 + o^2) from the hardware seed and ONE Newton step (2^-44: it only sets the ANGLE),
 //    c2 = 1/2 + |dd| / 2h, then (c~, s~) = (c2, +-o / 2h) * rsqrt_seed(c2) -- a vector of the right direction whose
 //    length is 1 + O(2^-21) -- normalised by the series n = 1 - d/2 + 3 d^2 / 8, d = c~^2 + s~^2 - 1 (error 5 d^3 / 16 <
 //    1e-18): c^2 + s^2 = 1 to rounding, 15 dependent float64 operations instead of 28;
 //  * because the angle is no longer exact to the last bit, the rotated pair is stored as computed, not as an exact zero
-//    (zeroing it would perturb the matrix by 2^-44 |a_pq|); convergence and accuracy are unchanged (numpy model of this
-//    body on the 1e6-pedestrian Gram matrices: the same rotation counts per sweep, residual 1e-15);
+//    (zeroing it would perturb the matrix by 2^-44 |a_pq|); convergence and accuracy are unchanged (same rotation counts
+//    per sweep, residual / orthogonality at the 1e-15 level: scripts/exp/eig_gen2.py);
 //  * ordering by rank counting (m threads) and sign / output by one warp per column instead of one thread.
-__device__ __forceinline__ double lds_f64(unsigned shared_address) {
+__device__ __forceinline__ double lds_f64(unsigned a) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_address) : "memory");
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a) {
+  unsigned v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
 __device__ __forceinline__ double raw_rsqrt(double x) {
@@ -589,11 +601,21 @@ __device__ __forceinline__ double raw_rsqrt(double x) {
   return r;
 }
 
+template <int MP, int VR = 2>
+struct EigFast2 {
+  static constexpr int HALF = MP / 2;
+  static constexpr int AW = EigFast<MP, VR>::AW;            // [0, HALF^2): 2 x 2 blocks of A; [AW, AW + HALF * VROWS): V
+  static constexpr int VROWS = EigFast<MP, VR>::VROWS;
+  static constexpr int PW = (AW + HALF * VROWS + 31) & ~31;  // first thread of the rotation-parameter warp
+  static constexpr int THREADS = PW + 32;
+};
+
 template <int MP, int VR = 2, bool PROF = false>
 __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, int k, float* __restrict__ U,
                                                  float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
                                                  int* __restrict__ info, double* sm) {
-  constexpr int m = MP, half = MP / 2, ld = MP + 1, AW = EigFast<MP, VR>::AW, VROWS = EigFast<MP, VR>::VROWS, NSTEP = MP - 1;
+  constexpr int m = MP, half = MP / 2, ld = MP + 1, NSTEP = MP - 1;
+  constexpr int AW = EigFast2<MP, VR>::AW, VROWS = EigFast2<MP, VR>::VROWS, PW = EigFast2<MP, VR>::PW;
   static_assert(MP <= 32, "one lane per row in the output phase");
   double* A = sm;                // MP x MP, row-major with odd pitch
   double* V = A + MP * ld;
@@ -624,34 +646,46 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
     for (int i = 0; i < m; ++i) mx = fmax(mx, fabs(A[i * ld + i]));
     floor2 = (1e-18 * mx) * (1e-18 * mx);
   }
-  const bool isP = tid < half, isA = tid < half * half, isV = tid >= AW && tid < AW + half * VROWS;
+  __syncthreads();
+  // roles and loop-invariant shared-window addresses
+  int role = tid < half * half ? 0 : (tid >= AW && tid < AW + half * VROWS ? 1 : (tid >= PW && tid < PW + half ? 2 : 3));
+  asm volatile("" : "+r"(role));      // opaque: kept in a register instead of being re-derived from %tid.x (a special-register
+                                      // read on the critical path) at the top of every step
+  const bool isA = role == 0, isV = role == 1, isP = role == 2;
+  const bool prof_thread = PROF && tid == PW;
   const int ai = isA ? tid / half : 0, aj = isA ? tid % half : 0;                      // A: 2 x 2 block (row pair ai, column pair aj)
   const int vpi = isV ? (tid - AW) / VROWS : 0, vr0 = isV ? (tid - AW) % VROWS : 0;    // V: pair vpi, rows vr0 + v * VROWS
-  // shared-window byte addresses of this parameter thread's a_pp, a_qq, a_pq, kept one step ahead in registers (explicit
-  // ld.shared: the compiler otherwise re-derives the window base from a special register in front of every step's first load)
-  const unsigned a_sh = (unsigned)__cvta_generic_to_shared(A);
+  const int ppi = isP ? tid - PW : 0;                                                   // parameters of pair ppi
+  unsigned a_sh = (unsigned)__cvta_generic_to_shared(A), v_sh = (unsigned)__cvta_generic_to_shared(V);
+  unsigned cs_sh = (unsigned)__cvta_generic_to_shared(cs), tab_sh = (unsigned)__cvta_generic_to_shared(tab);
+  asm volatile("" : "+r"(a_sh), "+r"(v_sh), "+r"(cs_sh), "+r"(tab_sh));   // (opaque for the same reason: the window base is a special register)
+  const unsigned adr_ci = cs_sh + 8u * (isA ? ai : vpi), adr_si = adr_ci + 8u * half;   // (V threads: their pair's c, s)
+  const unsigned adr_cj = cs_sh + 8u * aj, adr_sj = adr_cj + 8u * half;
+  const unsigned adr_cout = cs_sh + 8u * ppi, adr_sout = adr_cout + 8u * half;
+  const double fl2 = floor2;
+  // the parameter threads keep the addresses of a_pp, a_qq, a_pq of their NEXT pair in registers
   unsigned adr_pp = a_sh, adr_qq = a_sh, adr_pq = a_sh;
-  auto pair_addresses = [&](int p, int q) {
-    adr_pp = a_sh + (unsigned)(p * (ld + 1)) * 8u;
-    adr_qq = a_sh + (unsigned)(q * (ld + 1)) * 8u;
-    adr_pq = a_sh + (unsigned)(p * ld + q) * 8u;
+  auto pair_addresses = [&](unsigned p, unsigned q) {
+    adr_pp = a_sh + p * (unsigned)((ld + 1) * 8);
+    adr_qq = a_sh + q * (unsigned)((ld + 1) * 8);
+    adr_pq = a_sh + (p * (unsigned)ld + q) * 8u;
   };
-  if (isP) pair_addresses(tab[tid], tab[half + tid]);
-  __syncthreads();
+  if (isP) pair_addresses(tab[ppi], tab[half + ppi]);
   if (PROF) { const long long t = clock64(); prof.t_setup = t - tk; tk = t; }
   int sweeps_done = 0, total_rot = 0;
   for (int sweep = 0; sweep < EIG_MAX_SWEEPS; ++sweep) {
     int n_rot = 0;
     for (int step = 0; step < NSTEP; ++step) {
-      const unsigned char* ts = tab + step * MP;
+      const unsigned ts = tab_sh + (unsigned)(step * MP);
       bool rotating = false;
       long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
       if (PROF) t0 = clock64();
-      // this thread's work items of the step (issued first: the loads fly while the parameter chain runs / the barrier waits)
-      int pi_ = 0, qi = 0, pj = 0, qj = 0;
-      if (isA) { pi_ = ts[ai]; qi = ts[half + ai]; pj = ts[aj]; qj = ts[half + aj]; }
-      else if (isV) { pi_ = ts[vpi]; qi = ts[half + vpi]; }
+      unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;        // addresses of this thread's work items (A: x00, x01, x10, x11; V: v_p, v_q of row vr0)
+      unsigned nb0 = 0, nb1 = 0;
       if (isP) {
+        const unsigned tn = tab_sh + (unsigned)((step + 1 == NSTEP ? 0 : step + 1) * MP);   // (the table wraps at the end of a sweep)
+        nb0 = lds_u8(tn + ppi);
+        nb1 = lds_u8(tn + half + ppi);
         const double app = lds_f64(adr_pp), aqq = lds_f64(adr_qq), apq = lds_f64(adr_pq);
         const double o = 2.0 * apq, dd = aqq - app, apq2 = apq * apq;
         const double x = fma(dd, dd, o * o);
@@ -665,50 +699,61 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
         const double nn = fma(d, fma(0.375, d, -0.5), 1.0);
         // rotate iff |a_pq| > EIGF_REL sqrt(a_pp a_qq) (compared squared) and above the absolute floor; a pair that does not
         // rotate may have produced NaN above (0 / 0) -- the selection discards it
-        rotating = apq2 > floor2 && apq2 > (EIGF_REL * EIGF_REL) * fabs(app * aqq);
-        cs[tid] = rotating ? ct * nn : 1.0;
-        cs[half + tid] = rotating ? st * nn : 0.0;
+        rotating = apq2 > fl2 && apq2 > (EIGF_REL * EIGF_REL) * fabs(app * aqq);
+        sts_f64(adr_cout, rotating ? ct * nn : 1.0);
+        sts_f64(adr_sout, rotating ? st * nn : 0.0);
+      } else if (isA) {
+        const unsigned pi_ = lds_u8(ts + ai), qi = lds_u8(ts + half + ai), pj = lds_u8(ts + aj), qj = lds_u8(ts + half + aj);
+        w0 = a_sh + (pi_ * (unsigned)ld + pj) * 8u;
+        w1 = a_sh + (pi_ * (unsigned)ld + qj) * 8u;
+        w2 = a_sh + (qi * (unsigned)ld + pj) * 8u;
+        w3 = a_sh + (qi * (unsigned)ld + qj) * 8u;
+      } else if (isV) {
+        const unsigned vp = lds_u8(ts + vpi), vq = lds_u8(ts + half + vpi);
+        w0 = v_sh + ((unsigned)(vr0 * ld) + vp) * 8u;
+        w1 = v_sh + ((unsigned)(vr0 * ld) + vq) * 8u;
       }
       if (PROF) t1 = clock64();
       const int rotated = __syncthreads_count(rotating);      // barrier + number of rotating pairs, block-uniform
       if (PROF) t2 = clock64();
-      if (isP) {                                              // next step's pair (the table wraps at the end of a sweep)
-        const unsigned char* tn = tab + (step + 1 == NSTEP ? 0 : step + 1) * MP;
-        pair_addresses(tn[tid], tn[half + tid]);
-      }
+      if (isP) pair_addresses(nb0, nb1);
       n_rot += rotated;
       if (rotated == 0) {               // nothing to do in this step (typical for the last, confirming sweep)
-        if (PROF) { ++prof.idle; prof.t_idle += t2 - t0; }
+        if (prof_thread) { ++prof.idle; prof.t_idle += t2 - t0; }
         continue;
       }
       if (isA) {
-        const double ci = cs[ai], si = cs[half + ai], cj = cs[aj], sj = cs[half + aj];
+        const double ci = lds_f64(adr_ci), si = lds_f64(adr_si), cj = lds_f64(adr_cj), sj = lds_f64(adr_sj);
+        const double x00 = lds_f64(w0), x01 = lds_f64(w1), x10 = lds_f64(w2), x11 = lds_f64(w3);
+        // columns: X J_j
+        const double t00 = cj * x00 - sj * x01, t01 = sj * x00 + cj * x01;
+        const double t10 = cj * x10 - sj * x11, t11 = sj * x10 + cj * x11;
+        // rows: J_i^T T  (an identity rotation reproduces its operands exactly; untouched blocks are not stored)
         if (si != 0.0 || sj != 0.0) {
-          const double x00 = A[pi_ * ld + pj], x01 = A[pi_ * ld + qj], x10 = A[qi * ld + pj], x11 = A[qi * ld + qj];
-          // columns: X J_j
-          const double t00 = cj * x00 - sj * x01, t01 = sj * x00 + cj * x01;
-          const double t10 = cj * x10 - sj * x11, t11 = sj * x10 + cj * x11;
-          // rows: J_i^T T
-          A[pi_ * ld + pj] = ci * t00 - si * t10;
-          A[pi_ * ld + qj] = ci * t01 - si * t11;
-          A[qi * ld + pj] = si * t00 + ci * t10;
-          A[qi * ld + qj] = si * t01 + ci * t11;
+          sts_f64(w0, ci * t00 - si * t10);
+          sts_f64(w1, ci * t01 - si * t11);
+          sts_f64(w2, si * t00 + ci * t10);
+          sts_f64(w3, si * t01 + ci * t11);
         }
       } else if (isV) {
-        const double c = cs[vpi], s = cs[half + vpi];
+        const double c = lds_f64(adr_ci), s = lds_f64(adr_si);
+        double vp[VR], vq[VR];
+#pragma unroll
+        for (int v = 0; v < VR; ++v) {
+          vp[v] = lds_f64(w0 + (unsigned)(v * VROWS * ld * 8));
+          vq[v] = lds_f64(w1 + (unsigned)(v * VROWS * ld * 8));
+        }
         if (s != 0.0) {
 #pragma unroll
           for (int v = 0; v < VR; ++v) {
-            const int r = vr0 + v * VROWS;
-            const double vp = V[r * ld + pi_], vq = V[r * ld + qi];
-            V[r * ld + pi_] = c * vp - s * vq;
-            V[r * ld + qi] = s * vp + c * vq;
+            sts_f64(w0 + (unsigned)(v * VROWS * ld * 8), c * vp[v] - s * vq[v]);
+            sts_f64(w1 + (unsigned)(v * VROWS * ld * 8), s * vp[v] + c * vq[v]);
           }
         }
       }
       if (PROF) t3 = clock64();
       __syncthreads();
-      if (PROF) {
+      if (prof_thread) {
         const long long t4 = clock64();
         ++prof.full; prof.t_param += t1 - t0; prof.t_bar1 += t2 - t1; prof.t_upd += t3 - t2; prof.t_bar2 += t4 - t3;
       }
@@ -765,12 +810,11 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
   }
   if (PROF) {
     __syncthreads();
-    if (tid == 0 && info) { prof.t_out = clock64() - tk; prof.store(info); }
+    if (prof_thread && info) { prof.t_out = clock64() - tk; prof.store(info); }
   }
 }
 
-
-constexpr int EIG_DEFAULT_GEN = 1;      // generation of the two-barrier body taken by default (ET_TUNE_EIG_THREADS 2001 / 2002 force one,
+constexpr int EIG_DEFAULT_GEN = 2;      // generation of the two-barrier body taken by default (ET_TUNE_EIG_THREADS 2001 / 2002 force one,
                                         // the environment variable ET_EIG_GEN = 1 | 2 changes the default of the process)
 static int eig_default_gen() {
   static const int gen = [] {
@@ -781,7 +825,7 @@ static int eig_default_gen() {
 }
 
 template <int MP, int NR = 2, int VR = 2, int GEN = 1, bool PROF = false>
-__global__ void __launch_bounds__(EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
+__global__ void __launch_bounds__(GEN == 2 ? EigFast2<MP, VR>::THREADS : EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
                                                                                    float* __restrict__ U, float* __restrict__ S,
                                                                                    double* __restrict__ U64, double* __restrict__ S64,
                                                                                    int* __restrict__ info) {
@@ -801,7 +845,7 @@ __global__ void __launch_bounds__(EIG_MAX_THREADS) eig_jacobi_kernel(const doubl
 
 // Both bases of one descriptor (16 x 16 observation and 24 x 24 prediction Gram matrices) in ONE launch: block 0 / 1
 // solve them side by side on two SMs, so the pair costs what the larger solve costs.
-constexpr int EIG_PAIR_THREADS = EigFast<24>::THREADS;
+constexpr int EIG_PAIR_THREADS = EigFast2<24>::THREADS;   // (the first generation leaves the extra warps idle)
 template <int GEN>
 __global__ void __launch_bounds__(EIG_PAIR_THREADS) eig_jacobi_pair_kernel(const double* __restrict__ G_a,
                                                                            const double* __restrict__ G_b, int k,
@@ -1027,17 +1071,17 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   } else if (m == 24 && nt == 2001) {
     eig_jacobi_fast_kernel<24><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 16 && nt == 2002) {
-    eig_jacobi_fast_kernel<16, 2, 2, 2><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+    eig_jacobi_fast_kernel<16, 2, 2, 2><<<1, EigFast2<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 2002) {
-    eig_jacobi_fast_kernel<24, 2, 2, 2><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+    eig_jacobi_fast_kernel<24, 2, 2, 2><<<1, EigFast2<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 16 && nt == 3001) {
     eig_jacobi_fast_kernel<16, 2, 2, 1, true><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 3001) {
     eig_jacobi_fast_kernel<24, 2, 2, 1, true><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 16 && nt == 3002) {
-    eig_jacobi_fast_kernel<16, 2, 2, 2, true><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+    eig_jacobi_fast_kernel<16, 2, 2, 2, true><<<1, EigFast2<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 3002) {
-    eig_jacobi_fast_kernel<24, 2, 2, 2, true><<<1, EigFast<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+    eig_jacobi_fast_kernel<24, 2, 2, 2, true><<<1, EigFast2<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 1001) {      // A/B variants of the two-barrier body (measured on B200, default = 2 Newton steps
     // per rsqrt, 2 rows per V thread: 134 us): one row per V thread 140 us (same bits), four rows 138 us (same bits), one
     // Newton step 129 us but eigenvectors only ~1e-9 from the two-step result -- not taken

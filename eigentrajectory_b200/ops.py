@@ -618,8 +618,9 @@ def gram_init(obs, pred, ori=True, rot=True, sca=True):
     p = to_dev(pred).to(x.device)
     t_pred = p.size(1)
     dev = x.device
-    G_obs = torch.zeros((2 * t_obs, 2 * t_obs), dtype=torch.float64, device=dev)
-    G_pred = torch.zeros((2 * t_pred, 2 * t_pred), dtype=torch.float64, device=dev)
+    no, npr = 4 * t_obs * t_obs, 4 * t_pred * t_pred
+    G = torch.zeros(no + npr, dtype=torch.float64, device=dev)          # one fill launch for both accumulators
+    G_obs, G_pred = G[:no].view(2 * t_obs, 2 * t_obs), G[no:].view(2 * t_pred, 2 * t_pred)
     pred_norm = torch.empty_like(p)
     o = torch.empty((n, 1, 2), device=dev) if ori else None
     r = torch.empty((n, 2, 2), device=dev) if rot else None
