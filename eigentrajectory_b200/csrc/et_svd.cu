@@ -403,15 +403,19 @@ struct EigFast {
   static constexpr int THREADS = AW + HALF * VROWS;
 };
 
-// PROF (diagnostic, ET_TUNE_EIG_THREADS = 3001 / 3002): thread 0 accumulates clock64() cycles per phase into info[2..11]:
+// PROF (diagnostic, ET_TUNE_EIG_THREADS = 3001 / 3002): thread 0 accumulates clock64() cycles per phase into info[2..13]:
 // {set-up, rotation parameters, first barrier, update, second barrier, rotating steps, idle steps, idle-step cycles,
-//  ordering, output}; info must then hold 12 ints.
+//  ordering, output}; info must then hold 14 ints.
 struct EigProf {
-  long long t_setup = 0, t_param = 0, t_bar1 = 0, t_upd = 0, t_bar2 = 0, t_idle = 0, t_order = 0, t_out = 0;
+  long long t_setup = 0, t_param = 0, t_bar1 = 0, t_upd = 0, t_bar2 = 0, t_idle = 0, t_order = 0, t_out = 0, t_begin = 0, t_wall = 0;
   int full = 0, idle = 0;
   __device__ __forceinline__ void store(int* info) const {
     info[2] = (int)t_setup; info[3] = (int)t_param; info[4] = (int)t_bar1; info[5] = (int)t_upd; info[6] = (int)t_bar2;
     info[7] = full; info[8] = idle; info[9] = (int)t_idle; info[10] = (int)t_order; info[11] = (int)t_out;
+    info[12] = (int)(clock64() - t_begin);      // whole body, entry to here
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    info[13] = (int)(ns - (unsigned long long)t_wall);   // the same in nanoseconds of the global timer
   }
 };
 
@@ -429,7 +433,13 @@ __device__ __forceinline__ void eig_jacobi_fast(const double* __restrict__ G, in
   const int tid = threadIdx.x, nthr = blockDim.x;
   EigProf prof;
   long long tk = 0;
-  if (PROF) tk = clock64();
+  if (PROF) {
+    tk = clock64();
+    prof.t_begin = tk;
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    prof.t_wall = (long long)ns;
+  }
   for (int e = tid; e < MP * MP; e += nthr) {
     const int r = e / MP, c = e % MP;
     A[r * ld + c] = 0.5 * (G[r * m + c] + G[c * m + r]);
@@ -601,21 +611,28 @@ __device__ __forceinline__ double raw_rsqrt(double x) {
   return r;
 }
 
-template <int MP, int VR = 2>
+// SYM: only the 2 x 2 blocks (row pair i, column pair j) with i <= j are updated and every matrix element lives at its
+// canonical place [min(r, c)][max(r, c)] -- the update is bound by the throughput of the float64 pipe (a DFMA / DMUL warp
+// instruction occupies it for ~11-16 cycles on this part), so half the blocks is the largest lever left; it also frees two
+// warps, and the roles are laid out so that every scheduler carries the same number of float64 instructions per step.
+template <int MP, int VR = 2, bool SYM = false>
 struct EigFast2 {
   static constexpr int HALF = MP / 2;
-  static constexpr int AW = EigFast<MP, VR>::AW;            // [0, HALF^2): 2 x 2 blocks of A; [AW, AW + HALF * VROWS): V
+  static constexpr int NA = SYM ? HALF * (HALF + 1) / 2 : HALF * HALF;   // [0, NA): 2 x 2 blocks of A
+  static constexpr int AW = (NA + 31) & ~31;                // [AW, AW + HALF * VROWS): V
   static constexpr int VROWS = EigFast<MP, VR>::VROWS;
   static constexpr int PW = (AW + HALF * VROWS + 31) & ~31;  // first thread of the rotation-parameter warp
   static constexpr int THREADS = PW + 32;
 };
+static_assert(EigFast2<24>::AW == EigFast<24>::AW && EigFast2<16>::AW == EigFast<16>::AW, "full layout = the first generation's");
 
-template <int MP, int VR = 2, bool PROF = false>
+template <int MP, int VR = 2, bool PROF = false, bool SYM = false>
 __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, int k, float* __restrict__ U,
                                                  float* __restrict__ S, double* __restrict__ U64, double* __restrict__ S64,
                                                  int* __restrict__ info, double* sm) {
   constexpr int m = MP, half = MP / 2, ld = MP + 1, NSTEP = MP - 1;
-  constexpr int AW = EigFast2<MP, VR>::AW, VROWS = EigFast2<MP, VR>::VROWS, PW = EigFast2<MP, VR>::PW;
+  constexpr int AW = EigFast2<MP, VR, SYM>::AW, VROWS = EigFast2<MP, VR, SYM>::VROWS, PW = EigFast2<MP, VR, SYM>::PW;
+  constexpr int NA = EigFast2<MP, VR, SYM>::NA;
   static_assert(MP <= 32, "one lane per row in the output phase");
   double* A = sm;                // MP x MP, row-major with odd pitch
   double* V = A + MP * ld;
@@ -626,7 +643,13 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
   const int tid = threadIdx.x, nthr = blockDim.x;
   EigProf prof;
   long long tk = 0;
-  if (PROF) tk = clock64();
+  if (PROF) {
+    tk = clock64();
+    prof.t_begin = tk;
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    prof.t_wall = (long long)ns;
+  }
   for (int e = tid; e < MP * MP; e += nthr) {
     const int r = e / MP, c = e % MP;
     A[r * ld + c] = 0.5 * (G[r * m + c] + G[c * m + r]);
@@ -648,12 +671,17 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
   }
   __syncthreads();
   // roles and loop-invariant shared-window addresses
-  int role = tid < half * half ? 0 : (tid >= AW && tid < AW + half * VROWS ? 1 : (tid >= PW && tid < PW + half ? 2 : 3));
+  int role = tid < NA ? 0 : (tid >= AW && tid < AW + half * VROWS ? 1 : (tid >= PW && tid < PW + half ? 2 : 3));
   asm volatile("" : "+r"(role));      // opaque: kept in a register instead of being re-derived from %tid.x (a special-register
                                       // read on the critical path) at the top of every step
   const bool isA = role == 0, isV = role == 1, isP = role == 2;
   const bool prof_thread = PROF && tid == PW;
-  const int ai = isA ? tid / half : 0, aj = isA ? tid % half : 0;                      // A: 2 x 2 block (row pair ai, column pair aj)
+  int ai = isA ? tid / half : 0, aj = isA ? tid % half : 0;                            // A: 2 x 2 block (row pair ai, column pair aj)
+  if (SYM && isA) {                 // item t of the upper triangle of pair indices, row by row: (0,0) .. (0,half-1), (1,1) ..
+    int t = tid, i = 0;
+    while (t >= half - i) { t -= half - i; ++i; }
+    ai = i; aj = i + t;
+  }
   const int vpi = isV ? (tid - AW) / VROWS : 0, vr0 = isV ? (tid - AW) % VROWS : 0;    // V: pair vpi, rows vr0 + v * VROWS
   const int ppi = isP ? tid - PW : 0;                                                   // parameters of pair ppi
   unsigned a_sh = (unsigned)__cvta_generic_to_shared(A), v_sh = (unsigned)__cvta_generic_to_shared(V);
@@ -704,10 +732,14 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
         sts_f64(adr_sout, rotating ? st * nn : 0.0);
       } else if (isA) {
         const unsigned pi_ = lds_u8(ts + ai), qi = lds_u8(ts + half + ai), pj = lds_u8(ts + aj), qj = lds_u8(ts + half + aj);
-        w0 = a_sh + (pi_ * (unsigned)ld + pj) * 8u;
-        w1 = a_sh + (pi_ * (unsigned)ld + qj) * 8u;
-        w2 = a_sh + (qi * (unsigned)ld + pj) * 8u;
-        w3 = a_sh + (qi * (unsigned)ld + qj) * 8u;
+        auto at = [&](unsigned r, unsigned c) {       // SYM: the canonical place of element {r, c}
+          const unsigned lo = SYM ? (r < c ? r : c) : r, hi = SYM ? (r < c ? c : r) : c;
+          return a_sh + (lo * (unsigned)ld + hi) * 8u;
+        };
+        w0 = at(pi_, pj);
+        w1 = at(pi_, qj);
+        w2 = at(qi, pj);       // (SYM, diagonal block: the same place as w1 -- the block is symmetric; the later store wins)
+        w3 = at(qi, qj);
       } else if (isV) {
         const unsigned vp = lds_u8(ts + vpi), vq = lds_u8(ts + half + vpi);
         w0 = v_sh + ((unsigned)(vr0 * ld) + vp) * 8u;
@@ -814,23 +846,24 @@ __device__ __forceinline__ void eig_jacobi_fast2(const double* __restrict__ G, i
   }
 }
 
-constexpr int EIG_DEFAULT_GEN = 2;      // generation of the two-barrier body taken by default (ET_TUNE_EIG_THREADS 2001 / 2002 force one,
-                                        // the environment variable ET_EIG_GEN = 1 | 2 changes the default of the process)
+constexpr int EIG_DEFAULT_GEN = 3;      // generation of the two-barrier body taken by default (ET_TUNE_EIG_THREADS 2001 / 2002 force one,
+                                        // the environment variable ET_EIG_GEN = 1 | 2 | 3 changes the default of the process; 3 = the second generation
+                                        // with the symmetric update)
 static int eig_default_gen() {
   static const int gen = [] {
     const char* e = getenv("ET_EIG_GEN");
-    return (e && (e[0] == '1' || e[0] == '2') && e[1] == 0) ? e[0] - '0' : EIG_DEFAULT_GEN;
+    return (e && e[0] >= '1' && e[0] <= '3' && e[1] == 0) ? e[0] - '0' : EIG_DEFAULT_GEN;
   }();
   return gen;
 }
 
 template <int MP, int NR = 2, int VR = 2, int GEN = 1, bool PROF = false>
-__global__ void __launch_bounds__(GEN == 2 ? EigFast2<MP, VR>::THREADS : EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
+__global__ void __launch_bounds__(GEN >= 2 ? EigFast2<MP, VR, GEN == 3>::THREADS : EigFast<MP, VR>::THREADS) eig_jacobi_fast_kernel(const double* __restrict__ G, int k,
                                                                                    float* __restrict__ U, float* __restrict__ S,
                                                                                    double* __restrict__ U64, double* __restrict__ S64,
                                                                                    int* __restrict__ info) {
   extern __shared__ double sm[];
-  if constexpr (GEN == 2) eig_jacobi_fast2<MP, VR, PROF>(G, k, U, S, U64, S64, info, sm);
+  if constexpr (GEN >= 2) eig_jacobi_fast2<MP, VR, PROF, GEN == 3>(G, k, U, S, U64, S64, info, sm);
   else eig_jacobi_fast<MP, NR, VR, PROF>(G, k, U, S, U64, S64, info, sm);
 }
 
@@ -852,9 +885,9 @@ __global__ void __launch_bounds__(EIG_PAIR_THREADS) eig_jacobi_pair_kernel(const
                                                                            float* __restrict__ U_a, float* __restrict__ S_a,
                                                                            float* __restrict__ U_b, float* __restrict__ S_b) {
   extern __shared__ double sm[];
-  if constexpr (GEN == 2) {
-    if (blockIdx.x == 0) eig_jacobi_fast2<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
-    else eig_jacobi_fast2<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
+  if constexpr (GEN >= 2) {
+    if (blockIdx.x == 0) eig_jacobi_fast2<16, 2, false, GEN == 3>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
+    else eig_jacobi_fast2<24, 2, false, GEN == 3>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
   } else {
     if (blockIdx.x == 0) eig_jacobi_fast<16>(G_a, k, U_a, S_a, nullptr, nullptr, nullptr, sm);
     else eig_jacobi_fast<24>(G_b, k, U_b, S_b, nullptr, nullptr, nullptr, sm);
@@ -1064,8 +1097,8 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
   int nt = tune_get(ET_TUNE_EIG_THREADS);
   if (nt == 0) nt = 2000 + eig_default_gen();
   // 2001 / 2002: first / second generation of the two-barrier body; 3001 / 3002: the same with phase cycle counters in
-  // info[2..11] (diagnostic: info must hold 12 ints)
-  ET_REQUIRE(nt != 3001 && nt != 3002 || (info && (m == 16 || m == 24)), ET_ERR_BADARG, "et_eig_jacobi: profiling variants need info[12] and m = 16 / 24");
+  // info[2..13] (diagnostic: info must hold 14 ints)
+  ET_REQUIRE((nt != 3001 && nt != 3002 && nt != 3003) || (info && (m == 16 || m == 24)), ET_ERR_BADARG, "et_eig_jacobi: profiling variants need info[14] and m = 16 / 24");
   if (m == 16 && nt == 2001) {
     eig_jacobi_fast_kernel<16><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 2001) {
@@ -1074,6 +1107,12 @@ int et_eig_jacobi(const double* G, int m, int k, float* U, float* S, double* U64
     eig_jacobi_fast_kernel<16, 2, 2, 2><<<1, EigFast2<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 2002) {
     eig_jacobi_fast_kernel<24, 2, 2, 2><<<1, EigFast2<24>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 16 && nt == 2003) {
+    eig_jacobi_fast_kernel<16, 2, 2, 3><<<1, EigFast2<16, 2, true>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 2003) {
+    eig_jacobi_fast_kernel<24, 2, 2, 3><<<1, EigFast2<24, 2, true>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
+  } else if (m == 24 && nt == 3003) {
+    eig_jacobi_fast_kernel<24, 2, 2, 3, true><<<1, EigFast2<24, 2, true>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 16 && nt == 3001) {
     eig_jacobi_fast_kernel<16, 2, 2, 1, true><<<1, EigFast<16>::THREADS, smem, st>>>(G, k, U, S, U64, S64, info);
   } else if (m == 24 && nt == 3001) {
@@ -1111,8 +1150,9 @@ int et_eig_jacobi_pair(const double* G_a, int m_a, const double* G_b, int m_b, i
   if (m_a == 16 && m_b == 24) {
     const size_t smem = (size_t)(2 * 24 * 25 + 24) * sizeof(double) + (size_t)2 * 24 * sizeof(int);
     int gen = tune_get(ET_TUNE_EIG_THREADS);
-    gen = gen == 2001 ? 1 : (gen == 2002 ? 2 : eig_default_gen());
-    if (gen == 2) eig_jacobi_pair_kernel<2><<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
+    gen = gen >= 2001 && gen <= 2003 ? gen - 2000 : eig_default_gen();
+    if (gen == 3) eig_jacobi_pair_kernel<3><<<2, EigFast2<24, 2, true>::THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
+    else if (gen == 2) eig_jacobi_pair_kernel<2><<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
     else eig_jacobi_pair_kernel<1><<<2, EIG_PAIR_THREADS, smem, as_stream(stream)>>>(G_a, G_b, k, U_a, S_a, U_b, S_b);
     return check_launch("eig_jacobi_pair_kernel");
   }

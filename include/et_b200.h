@@ -68,10 +68,11 @@ int et_memcpy_2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_
 
 /* Launch-shape knobs for performance experiments (process-wide; 0 = the shipped default).
  * Results never depend on them beyond the last bits.
- * ET_TUNE_EIG_THREADS: 32 / 96 / 128 / 288 = the four-barrier Jacobi body with that many threads; 2001 / 2002 = first /
- * second generation of the two-barrier body for the 16 x 16 and 24 x 24 bases (default: the second; the environment
- * variable ET_EIG_GEN = 1 | 2 sets the default of the process); 3001 / 3002 = the same with phase cycle counters written
- * to info[2..11] of et_eig_jacobi (diagnostic: info must then hold 12 ints). */
+ * ET_TUNE_EIG_THREADS: 32 / 96 / 128 / 288 = the four-barrier Jacobi body with that many threads; 2001 / 2002 / 2003 =
+ * first generation / second generation / second generation with the symmetric (upper-triangle) update of the two-barrier
+ * body for the 16 x 16 and 24 x 24 bases (default: 2003; the environment variable ET_EIG_GEN = 1 | 2 | 3 sets the default
+ * of the process); 3001 / 3002 / 3003 = the same with phase cycle counters written to info[2..13] of et_eig_jacobi
+ * (diagnostic: info must then hold 14 ints). */
 enum { ET_TUNE_ADE_CONFIG = 0, ET_TUNE_REC_BLOCKS_PER_SM = 1, ET_TUNE_GRAM_UNROLL = 2, ET_TUNE_EIG_THREADS = 3,
        ET_TUNE_PDL = 4, ET_TUNE_SEED_STEPWISE = 5 /* 1: farthest-point seeding as one launch per step */,
        ET_TUNE_KM_TOURNAMENT = 6 /* 1: per-group tournament arg-max instead of the ascending compare/select scan (A/B) */,

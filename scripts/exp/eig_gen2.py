@@ -50,7 +50,7 @@ for name, G in cases:
     m = G.size(0)
     row = {"case": name, "m": m}
     ref = None
-    for gen_id in (1, 2):
+    for gen_id in (1, 2, 3):
         lib.et_tune(3, 2000 + gen_id)
         info = torch.zeros(2, dtype=torch.int32, device=dev)
         U, S, U64, S64 = ops.eig_basis(G, m, want64=True, info=info)
@@ -60,8 +60,8 @@ for name, G in cases:
         if ref is None:
             ref = (U6, S64)
         else:
-            row["projector6_gen2_vs_gen1"] = float((U6 @ U6.T - ref[0] @ ref[0].T).norm())
-            row["S_gen2_vs_gen1_rel_to_S1"] = float(((S64 - ref[1]).abs() / ref[1][0].clamp_min(1e-300)).max())
+            row[f"projector6_gen{gen_id}_vs_gen1"] = float((U6 @ U6.T - ref[0] @ ref[0].T).norm())
+            row[f"S_gen{gen_id}_vs_gen1_rel_to_S1"] = float(((S64 - ref[1]).abs() / ref[1][0].clamp_min(1e-300)).max())
     print(json.dumps(row), flush=True)
     out.append(row)
 lib.et_tune(3, 0)
@@ -89,7 +89,7 @@ def init_cold():
     d.parameter_initialization(obs, pred)
 
 
-for gen_id in (1, 2):
+for gen_id in (1, 2, 3):
     lib.et_tune(3, 2000 + gen_id)
     t = {"generation": gen_id, "eig24_us": timed(lambda: ops.eig_basis(G_p, 6)), "eig16_us": timed(lambda: ops.eig_basis(G_o, 6)),
          "eig_pair_us": timed(lambda: ops.eig_basis_pair(G_o, G_p, 6))}
@@ -103,10 +103,12 @@ for gen_id in (1, 2):
     t["parameter_initialization_us"] = round(ts[len(ts) // 2], 1)
     print(json.dumps(t), flush=True)
 names = ["setup", "param", "barrier1", "update", "barrier2", "rotating_steps", "idle_steps", "idle_step_cycles", "ordering", "output"]
-for gen_id in (1, 2):
+for gen_id in (1, 2, 3):
     for tag, G in (("24x24", G_p), ("16x16", G_o)):
+        if gen_id == 3 and tag == "16x16":
+            continue
         lib.et_tune(3, 3000 + gen_id)
-        info = torch.zeros(12, dtype=torch.int32, device=dev)
+        info = torch.zeros(14, dtype=torch.int32, device=dev)
         ops.eig_basis(G, 6, info=info)
         v = info.tolist()
         print(json.dumps({"profile": f"generation {gen_id} {tag}", "sweeps_rotations": v[:2], **dict(zip(names, v[2:]))}), flush=True)
