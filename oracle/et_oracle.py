@@ -437,3 +437,84 @@ def kmeans_d2_seeding(data, n_clusters, uniform):
         picks.append(cands[best])
         d2 = np.minimum(d2, dist2(x[:, cands[best]]))
     return x[:, picks].copy(), np.asarray(picks)
+
+
+# --------------------------------------------------------------------------------------
+# Jacobi eigen-solve of the Gram matrix: a numpy MODEL of the kernel's arithmetic (eig_jacobi_fast2 in
+# eigentrajectory_b200/csrc/et_svd.cu), not a restatement of the reference -- the reference calls LAPACK
+# (descriptor.py:110) and the parity statement for the bases is made against the golden fp32 / fp64 SVDs.  The model
+# pins what the kernel's shortened rotation chain relies on: a rotation built from ~21-bit reciprocal-square-root seeds
+# is orthogonal to rounding, and the solve needs the same sweeps as one with exactly computed angles.
+# --------------------------------------------------------------------------------------
+
+
+def _rsqrt_seed(x, extra_rel_error=0.0):
+    """A stand-in for rsqrt.approx.ftz.f64: only the upper 32 bits of the operand are looked at and only the upper 32
+    bits of the result are produced (relative error ~2^-21); ``extra_rel_error`` perturbs it further."""
+    import struct
+    hi = struct.unpack("<d", struct.pack("<Q", struct.unpack("<Q", struct.pack("<d", float(x)))[0] & 0xFFFFFFFF00000000))[0]
+    r = (1.0 / np.sqrt(hi)) * (1.0 + extra_rel_error)
+    return struct.unpack("<d", struct.pack("<Q", struct.unpack("<Q", struct.pack("<d", float(r)))[0] & 0xFFFFFFFF00000000))[0]
+
+
+def jacobi_rotation_short_chain(app, aqq, apq, seed_error=0.0):
+    """(c, s) of the inner Jacobi rotation of the pair (p, q) as eig_jacobi_fast2 computes it: 1/h from the seed and one
+    Newton step, c^2 = 1/2 + |dd| / 2h, (c~, s~) = (c^2, +-o / 2h) * seed(c^2), normalised by 1 - d/2 + 3 d^2 / 8."""
+    o, dd = 2.0 * apq, aqq - app
+    x = dd * dd + o * o
+    rh = _rsqrt_seed(x, seed_error)
+    rh = rh * 0.5 * (-x * rh * rh + 1.0) + rh
+    c2 = 0.5 * abs(dd) * rh + 0.5
+    rc = _rsqrt_seed(c2, -seed_error)
+    ct, st = c2 * rc, (0.5 if dd >= 0.0 else -0.5) * o * rh * rc
+    d = ct * ct + (st * st - 1.0)
+    n = 1.0 + d * (-0.5 + 0.375 * d)
+    return ct * n, st * n
+
+
+def jacobi_rotation_exact(app, aqq, apq, seed_error=0.0):
+    """The textbook form (tangent of the inner angle, IEEE sqrt and division)."""
+    o, dd = 2.0 * apq, aqq - app
+    h = np.sqrt(dd * dd + o * o)
+    t = o / (dd + (h if dd >= 0.0 else -h))
+    c = 1.0 / np.sqrt(t * t + 1.0)
+    return c, t * c
+
+
+def jacobi_eig_model(G, k, rotation=jacobi_rotation_short_chain, rel=1e-12, max_sweeps=60, seed_error=0.0):
+    """Parallel-ordered cyclic Jacobi as the kernel runs it: round-robin pairs (position 0 fixed), all rotations of a step
+    from the matrix BEFORE the step, A <- J^T A J on ONE symmetric copy, the rotated pair stored as computed; rotate iff
+    a_pq^2 > rel^2 |a_pp a_qq| and above the floor (1e-18 max diagonal)^2.  Returns (U (m, k), S (k), rotations per sweep,
+    worst |c^2 + s^2 - 1|); columns ordered by descending eigenvalue, largest-magnitude component positive."""
+    A = 0.5 * (np.asarray(G, dtype=np.float64) + np.asarray(G, dtype=np.float64).T)
+    m = A.shape[0]
+    assert m % 2 == 0
+    V = np.eye(m)
+    floor2 = (1e-18 * np.abs(np.diag(A)).max()) ** 2
+    counts, worst = [], 0.0
+    for _ in range(max_sweeps):
+        nrot = 0
+        for step in range(m - 1):
+            def player(pos):
+                return 0 if pos == 0 else 1 + (pos - 1 + step) % (m - 1)
+            J = np.eye(m)
+            for pi in range(m // 2):
+                p, q = sorted((player(pi), player(m - 1 - pi)))
+                app, aqq, apq = A[p, p], A[q, q], A[p, q]
+                if apq * apq > floor2 and apq * apq > rel * rel * abs(app * aqq):
+                    c, s = rotation(app, aqq, apq, seed_error)
+                    worst = max(worst, abs(c * c + s * s - 1.0))
+                    J[p, p], J[q, q], J[p, q], J[q, p] = c, c, s, -s
+                    nrot += 1
+            if nrot:
+                A = J.T @ A @ J
+                A = 0.5 * (A + A.T)
+                V = V @ J
+        counts.append(nrot)
+        if nrot == 0:
+            break
+    lam = np.diag(A)
+    order = np.argsort(-lam, kind="stable")[:k]
+    U = V[:, order]
+    U = U * np.where(U[np.abs(U).argmax(axis=0), np.arange(k)] < 0.0, -1.0, 1.0)
+    return U, np.sqrt(np.maximum(lam[order], 0.0)), counts, worst
