@@ -21,11 +21,11 @@ G_o, G_p, _, _ = ops.gram_init(obs, pred)
 info = torch.zeros(2, dtype=torch.int32, device=dev)
 print("gram (both matrices, normalise fused) us:", timed(lambda: ops.gram(obs, pred, True, True, True), cold=True))
 print("gram_init (+ state + normalised futures) us:", timed(lambda: ops.gram_init(obs, pred), cold=True))
-for tag, knob in (("two-barrier body", 0), ("four-barrier body 288/128 threads", 288)):
+for tag, knob in (("two-barrier body, second generation + symmetric update (default)", 0), ("two-barrier body, second generation", 2002), ("two-barrier body, first generation", 2001), ("four-barrier body 288/128 threads", 288)):
     lib.et_tune(3, knob)
     print(f"eig 24x24 {tag} us:", timed(lambda: ops.eig_basis(G_p, 6, info=info)), "sweeps/rotations", info.tolist())
     print(f"eig 16x16 {tag} us:", timed(lambda: ops.eig_basis(G_o, 6, info=info)), "sweeps/rotations", info.tolist())
-for tag, knob in (("1 row per V thread", 1001), ("1 Newton step per rsqrt", 1003)):
+for tag, knob in (("first generation, 1 row per V thread", 1001), ("first generation, 1 Newton step per rsqrt", 1003)):
     lib.et_tune(3, knob)
     U, S, U64, S64 = ops.eig_basis(G_p, 6, want64=True)
     lib.et_tune(3, 0)
