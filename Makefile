@@ -30,7 +30,14 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/et_b200.h
 $(LIB): $(OBJS)
 	$(NVCC) -shared -cudart static -o $@ $(OBJS) -ldl
 
+# a plain-C host of the library (no Python, no torch): build/c_host
+CUDA_HOME ?= /usr/local/cuda
+example: $(LIB) examples/c_host.c
+	@mkdir -p $(OBJDIR)
+	gcc -std=c99 -Wall -Iinclude -I$(CUDA_HOME)/include examples/c_host.c -o $(OBJDIR)/c_host \
+	    -Leigentrajectory_b200 -let_b200 -L$(CUDA_HOME)/lib64 -lcudart -lm -Wl,-rpath,$(abspath eigentrajectory_b200)
+
 clean:
 	rm -rf $(OBJDIR) $(LIB) oracle/_build oracle/_ref
 
-.PHONY: all clean oracle oracle-ref
+.PHONY: all clean oracle oracle-ref example
